@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Headline benchmark: lcpc commit throughput (field elements / s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Ligero commit of a 2^24-coefficient polynomial over
+the 63-bit field, rho = 1/2, BLAKE3: 512 rows x 32768 -> 65536 columns.  One "step" is one
+commit: encode every row (batched NTT), hash every column, build the Merkle tree.
+At N > 1 the matrix has N x 512 rows of the same width (weak scaling); rows are sharded
+for encoding, an NCCL all-to-all re-shards to column blocks for hashing, every rank
+builds its Merkle subtree and rank 0 joins the N subtree roots.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM,
+CUDA events, max over ranks); `e2e` goes through the host-buffer C-ABI call
+(lcpc_commit_host: pinned host coefficients in, encoded matrix + Merkle tree out).
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/) with
+all host threads on the same workload -- the Rust reference itself cannot be built here.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+FID = 0  # Ft63
+LOG_N = 24
+N_PER_ROW, N_COLS = 32768, 65536
+ROWS_PER_GPU = (1 << LOG_N) // N_PER_ROW  # 512
+METRIC = "ligero_commit_throughput_ft63_2^24"
+UNIT = "field elements/s"
+
+
+def workload_name(n_gpus: int) -> str:
+    rows = ROWS_PER_GPU * n_gpus
+    return (f"Ligero commit, Ft63, rho=1/2, BLAKE3, {rows} rows x {N_PER_ROW} -> {N_COLS} cols "
+            f"({rows * N_PER_ROW} coefficients)")
+
+
+def algorithmic_bytes(n_coeffs: int, n_rows: int) -> int:
+    """read coeffs once + write encoded matrix once + write the tree."""
+    return n_coeffs * 8 + n_rows * N_COLS * 8 + (2 * N_COLS - 1) * 32
+
+
+def make_coeffs(seed: int, n: int) -> np.ndarray:
+    """Seeded Ft63 elements (Montgomery limbs): splitmix64 stream masked to 63 bits, reduced once."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        z = (idx ^ (idx >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    z &= np.uint64((1 << 63) - 1)
+    p = np.uint64(5102708120182849537)
+    z = np.where(z >= p, z - p, z)
+    return z.reshape(n, 1)
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            names = {
+                0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
+                0x100: "display_clock_setting",
+            }
+            for bit, name in names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def start(self):
+        if not self.nv:
+            return
+        self._stop.clear()
+
+        def loop():
+            while not self._stop.is_set():
+                self._sample()
+                time.sleep(0.01)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._sample()
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# per-kernel compulsory HBM bytes for one launch at this workload (DESIGN.md "Kernels")
+def kernel_algorithmic_bytes(name: str, n_rows: int) -> int:
+    enc = n_rows * N_COLS * 8
+    return {
+        "k_ntt_strided": n_rows * N_PER_ROW * 8 + enc,  # reads the coefficients, writes the widened rows
+        "k_ntt_block": 2 * enc,                          # in place over the encoded matrix
+        "k_hash_chunks": enc + ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32,
+        "k_hash_merge": ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32 + N_COLS * 32,
+        "k_merkle_levels": 2 * N_COLS * 32,
+    }.get(name, 0)
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """CPU arm: the oracle's restatement of the reference algorithm, all host threads."""
+    if rank != 0:
+        return
+    from oracle import lcpc_oracle as O
+
+    O.build()
+    cores = O.max_threads()
+    n_rows = ROWS_PER_GPU * max(1, args.gpus)
+    # bounded sample: at most 512 rows of the same width per step (throughput per coefficient does
+    # not depend on the row count: rows are independent and leaves are hashed row-block by row-block)
+    sample_rows = min(n_rows, 512)
+    n = sample_rows * N_PER_ROW
+    coeffs = make_coeffs(2, n)
+    enc = O.LigeroEncoding(FID, N_PER_ROW, N_COLS)
+    steps, warmup = args.steps, args.warmup
+    t_probe = time.perf_counter()
+    O.commit(coeffs, enc)
+    t_probe = time.perf_counter() - t_probe
+    if t_probe * (steps + warmup) > 240:  # keep the run within a few minutes
+        steps = max(1, int(240 / t_probe) - 1)
+        warmup = 0
+    for _ in range(max(0, warmup - 1)):
+        O.commit(coeffs, enc)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c = O.commit(coeffs, enc)
+    dt = time.perf_counter() - t0
+    value = n * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (63-bit prime field, Montgomery)", "data": "synthetic",
+        "config": {"workload": workload_name(max(1, args.gpus)), "sample": f"{sample_rows} of {n_rows} rows per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_rows} rows x {N_PER_ROW} -> {N_COLS} (full width), C restatement "
+                                   f"of the reference algorithm, OpenMP over rows / 32-column blocks"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "root": c.get_root().hex(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    import lcpc_proof_of_storage_b200 as P
+    from lcpc_proof_of_storage_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lcpc_proof_of_storage_b200 has no CPU fallback")
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    stream = torch.cuda.current_stream()
+    ctx = P.Context(local_rank, stream=stream.cuda_stream)
+    enc = P.LigeroEncoding(FID, N_PER_ROW, N_COLS, ctx=ctx)
+
+    n_rows_total = ROWS_PER_GPU * world
+    n_total = n_rows_total * N_PER_ROW
+    np2 = N_COLS
+    # this rank's rows of the coefficient matrix (seed 2 stream, sliced by row block)
+    h_coeffs_np = make_coeffs(2, n_total)[rank * ROWS_PER_GPU * N_PER_ROW:(rank + 1) * ROWS_PER_GPU * N_PER_ROW]
+    h_coeffs = torch.from_numpy(h_coeffs_np.view(np.int64).reshape(-1)).pin_memory()
+    d_coeffs = h_coeffs.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    if world == 1:
+        d_comm = torch.empty(ROWS_PER_GPU * N_COLS, dtype=torch.int64, device="cuda")
+        d_hashes = torch.zeros((2 * np2 - 1) * 32, dtype=torch.uint8, device="cuda")
+
+        def step():
+            _lib.check(lib.lcpc_dev_encode(enc.plan, d_coeffs.data_ptr(), ROWS_PER_GPU, d_comm.data_ptr()))
+            _lib.check(lib.lcpc_dev_hash_columns(ctx.handle, FID, d_comm.data_ptr(), ROWS_PER_GPU, N_COLS, N_COLS,
+                                                 d_hashes.data_ptr()))
+            _lib.check(lib.lcpc_dev_merkle_tree(ctx.handle, d_hashes.data_ptr(), np2))
+
+        def root_hex():
+            return bytes(d_hashes[-32:].cpu().numpy()).hex()
+    else:
+        from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter
+
+        sc = ShardedLigeroCommitter(enc, n_rows_total, dist.group.WORLD)
+
+        def step():
+            sc.commit(d_coeffs)
+
+        def root_hex():
+            return sc.root().hex() if rank == 0 else ""
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    ctx.kernel_timing(True)
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    kt = ctx.kernel_timing_report()
+    ctx.kernel_timing(False)
+    launches = ctx.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / steps
+    value = n_total / (ms_per_step * 1e-3)
+    gpu_root = root_hex()
+
+    # ---- end to end through the host-buffer C-ABI call (N = 1 path per rank) ----------------------
+    e2e = None
+    h_comm = torch.empty(ROWS_PER_GPU * N_COLS, dtype=torch.int64).pin_memory()
+    h_hashes = torch.empty((2 * np2 - 1) * 32, dtype=torch.uint8).pin_memory()
+    n_local = ROWS_PER_GPU * N_PER_ROW
+    e2e_steps = max(1, min(steps, 20))
+
+    def e2e_step():
+        _lib.check(lib.lcpc_commit_host(enc.plan, h_coeffs.data_ptr(), n_local, None, h_comm.data_ptr(),
+                                        h_hashes.data_ptr(), None))
+
+    if world == 1:
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        sampler.stop()
+        e2e = {"value": n_local * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_local * 8,
+               "d2h_bytes_per_step": ROWS_PER_GPU * N_COLS * 8 + (2 * np2 - 1) * 32, "ms_per_step": 1e3 * dt / e2e_steps,
+               "steps": e2e_steps, "api": "lcpc_commit_host (pinned host coeffs in; LcCommit.comm + LcCommit.hashes out)"}
+        assert bytes(h_hashes[-32:].numpy()).hex() == gpu_root, "e2e root differs from the device-resident root"
+    else:
+        # sharded end to end: pinned host rows in, root (32 B) out on rank 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d = h_coeffs.cuda(non_blocking=True)
+            sc.commit(d)
+            r = sc.root()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": n_total * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_local * 8 * world,
+               "d2h_bytes_per_step": 32, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "api": "ShardedLigeroCommitter.commit (pinned host row shards in; Merkle root out on rank 0)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event timings from the timed region) ----------
+    peak, peak_src = measured_peak_gbs()
+    roofline = None
+    if kt:
+        dom = max(kt.items(), key=lambda kv: kv[1][1])
+        name, (count, total_ms) = dom
+        per_launch_ms = total_ms / count
+        alg = kernel_algorithmic_bytes(name, ROWS_PER_GPU if world == 1 else ROWS_PER_GPU)
+        ach = alg / (per_launch_ms * 1e-3) / 1e9 if alg else None
+        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
+                    "share_of_step": total_ms / ms_total,
+                    "kernels_ms_per_step": {k: v[1] / steps for k, v in kt.items()},
+                    "note": "integer-pipe bound (64-bit Montgomery + BLAKE3 ARX on 32-bit IMAD/ALU), see DESIGN.md"}
+    step_gbs = algorithmic_bytes(n_total, n_rows_total) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- CPU baseline: oracle on the same input, all host threads; also the parity gate ------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import lcpc_oracle as O
+
+        O.build()
+        oenc = O.LigeroEncoding(FID, N_PER_ROW, N_COLS)
+        sample_rows = ROWS_PER_GPU * (world if world <= 2 else 1)
+        if world == 1 or world == 2:
+            cpu_in = make_coeffs(2, n_total)
+        else:
+            cpu_in = h_coeffs_np
+        t0 = time.perf_counter()
+        oc = O.commit(cpu_in, oenc)
+        dt = time.perf_counter() - t0
+        cpu = {"value": cpu_in.shape[0] / dt, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
+               "sample": f"one commit of {sample_rows} rows x {N_PER_ROW} -> {N_COLS} ({dt:.2f} s), C restatement of the "
+                         f"reference algorithm with its rayon decomposition as OpenMP",
+               "root_matches_gpu": (oc.get_root().hex() == gpu_root) if world <= 2 else None}
+        if world <= 2:
+            assert oc.get_root().hex() == gpu_root, "GPU Merkle root differs from the CPU oracle"
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (63-bit prime field, Montgomery)", "data": "synthetic",
+        "config": {"workload": workload_name(world), "field": "Ft63", "n_rows": n_rows_total, "n_per_row": N_PER_ROW,
+                   "n_cols": N_COLS, "digest": "BLAKE3", "l2": "inputs larger than L2 (128 MiB in, 256 MiB out per GPU)",
+                   "parallelism": "single GPU" if world == 1 else f"row shards x{world} + NCCL all-to-all + subtree roots"},
+        "algorithmic_GBps": step_gbs,
+        "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+        "root": gpu_root,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,220 @@
+/*
+ * lcpc_b200 -- C ABI of the B200-native lcpc commitment hot path.
+ *
+ * This is the drop-in boundary: the reference (TrevorGKann/lcpc_proof_of_storage) is
+ * pure Rust and has no FFI of its own, so each entry point below names the Rust item
+ * it stands in for (paths relative to the reference checkout).  INTEGRATION.md shows
+ * the `extern "C"` block and the `LcEncoding` wrapper a maintainer adds on the Rust
+ * side.
+ *
+ * Conventions
+ *  - A field element is LIMBS x uint64_t, least-significant limb first, holding the
+ *    Montgomery residue a*2^(64*LIMBS) mod p, fully reduced -- bit-identical to the
+ *    ff_derive newtypes (lcpc-test-fields/src/lib.rs:18-70), so a Rust `&[F]` is
+ *    passed as `(const uint64_t*)slice.as_ptr()` with `len * LIMBS` words.
+ *  - Matrices are row-major: coeffs[r*n_per_row + j], comm[r*n_cols + j]
+ *    (lcpc-2d/src/lib.rs:174-191).
+ *  - Digests are 32-byte BLAKE3 outputs; `hashes` is the flat tree
+ *    [np2 leaves | np2/2 | ... | root], np2 = next_power_of_two(n_cols), 2*np2-1
+ *    entries, padding leaves all-zero (lib.rs:685-695, 720-734).
+ *  - Every function returns an lcpc_status (0 = ok).  No C++ exception crosses the
+ *    boundary.  Handles are internally locked: calls on one handle may come from any
+ *    thread (`LcEncoding: Sync`, lib.rs:75).  Calls are synchronous on return.
+ *  - "host" entry points take host pointers (pageable or pinned) and move the data
+ *    themselves; "dev" entry points take device pointers on the context's device and
+ *    enqueue on the context's stream (used for device-resident pipelines and for the
+ *    one-process-per-GPU sharded path).
+ *  - There is no CPU fallback: every entry point fails with LCPC_ERR_CUDA when no
+ *    usable device is present.
+ */
+#ifndef LCPC_B200_H
+#define LCPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCPC_DIGEST_BYTES 32
+
+/* prime fields of the reference (lcpc-test-fields/src/lib.rs; WriteableFt63 =
+ * proof-of-storage/src/fields/writable_ft63.rs has Ft63's modulus) */
+typedef enum {
+    LCPC_FT63 = 0,  /* p = 5102708120182849537, 1 limb  */
+    LCPC_FT127 = 1, /* 2 limbs */
+    LCPC_FT191 = 2, /* 3 limbs */
+    LCPC_FT255 = 3  /* 4 limbs */
+} lcpc_field;
+
+/* status codes; the first block maps onto lcpc_2d::ProverError (lib.rs:113-132) */
+typedef enum {
+    LCPC_OK = 0,
+    LCPC_ERR_TOO_BIG = -1,       /* ProverError::TooBig                           */
+    LCPC_ERR_ENCODE = -2,        /* ProverError::Encode(E::Err)                   */
+    LCPC_ERR_COMMIT = -3,        /* ProverError::Commit (check_comm, :703-718)    */
+    LCPC_ERR_COLUMN_NUMBER = -4, /* ProverError::ColumnNumber (:829-831)          */
+    LCPC_ERR_OUTER_TENSOR = -5,  /* ProverError::OuterTensor (:1046-1048)         */
+    LCPC_ERR_DIMS = -6,          /* the assert!s at lib.rs:659-661 / dims_ok      */
+    LCPC_ERR_INVALID_ARG = -7,   /* null pointer, unknown field, ...              */
+    LCPC_ERR_CUDA = -8,          /* CUDA runtime failure or no device             */
+    LCPC_ERR_NOMEM = -9          /* device or host allocation failed              */
+} lcpc_status;
+
+typedef struct lcpc_ctx lcpc_ctx;       /* one device + stream                      */
+typedef struct lcpc_plan lcpc_plan;     /* one encoding instance (an `E: LcEncoding`) */
+typedef struct lcpc_commit lcpc_commit; /* a device-resident LcCommit               */
+
+/* sprs::CsMat<F> in CSC storage, as lcpc-brakedown-pc keeps its pre/postcodes
+ * (lcpc-brakedown-pc/src/matgen.rs:187): indptr[cols+1], indices[nnz] = row numbers,
+ * data[nnz*LIMBS] Montgomery limbs.  All host pointers. */
+typedef struct {
+    uint64_t rows;
+    uint64_t cols;
+    const uint64_t *indptr;
+    const uint64_t *indices;
+    const uint64_t *data;
+} lcpc_csc;
+
+/* ---- library / context --------------------------------------------------------- */
+
+/* ABI version of this header (bumped on any signature change). */
+uint32_t lcpc_abi_version(void);
+/* Message for the last failure on this thread (never NULL). */
+const char *lcpc_last_error(void);
+/* LIMBS of a field, or 0 for an unknown id. */
+int32_t lcpc_field_limbs(int32_t field);
+/* Field constants (modulus, R mod p = F::ONE, 2-adicity S, ROOT_OF_UNITY in Montgomery
+ * form); any out pointer may be NULL. */
+int32_t lcpc_field_constants(int32_t field, uint64_t *modulus, uint64_t *one_mont,
+                             uint64_t *root_of_unity_mont, int32_t *two_adicity, int32_t *num_bits);
+
+/* Context on `device` with its own non-blocking stream. */
+int32_t lcpc_ctx_create(int32_t device, lcpc_ctx **out);
+/* Context that enqueues on a caller-owned cudaStream_t (e.g. torch's current stream). */
+int32_t lcpc_ctx_create_on_stream(int32_t device, void *cuda_stream, lcpc_ctx **out);
+int32_t lcpc_ctx_synchronize(lcpc_ctx *ctx);
+void lcpc_ctx_destroy(lcpc_ctx *ctx);
+
+/* ---- plans = encodings ------------------------------------------------------------ */
+
+/* LigeroEncodingRho::new_from_dims(n_per_row, n_cols) (lcpc-ligero-pc/src/lib.rs:138-148):
+ * requires n_per_row < n_cols, n_cols a power of two <= 2^S (_dims_ok, :114-118).
+ * `root_of_unity_mont` is the n_cols-th root the NTT uses, LIMBS words; NULL selects
+ * ROOT_OF_UNITY^(2^(S-k)), what fffft::precomp_fft(n_cols) derives (:140).  The encode
+ * is fffft's fft_io: in-order input, bit-reversed output (:162-164). */
+int32_t lcpc_plan_ligero(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size_t n_cols,
+                         const uint64_t *root_of_unity_mont, lcpc_plan **out);
+
+/* SdigEncodingS from already generated matrices (lcpc-brakedown-pc/src/lib.rs:126-137,
+ * matgen.rs:28-53): n_levels precodes and postcodes; n_cols must equal
+ * codeword_length(pre, post) (encode.rs:18-33). */
+int32_t lcpc_plan_brakedown(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size_t n_cols,
+                            size_t n_levels, const lcpc_csc *precodes, const lcpc_csc *postcodes,
+                            lcpc_plan **out);
+
+/* LcEncoding::get_dims (lib.rs:166-169 / brakedown lib.rs:155-158) */
+int32_t lcpc_plan_get_dims(const lcpc_plan *plan, size_t len, size_t *n_rows, size_t *n_per_row,
+                           size_t *n_cols);
+void lcpc_plan_destroy(lcpc_plan *plan);
+
+/* LcEncoding::encode on `n_rows` rows at once, in place, host memory: each row has
+ * n_cols elements, the first n_per_row are the message and the rest must be zero on
+ * entry (lcpc-2d/src/lib.rs:677-682; verifier use at :912-918, :944-950). */
+int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows);
+
+/* ---- commit ----------------------------------------------------------------------- */
+
+/* LcCommit::commit (lcpc-2d/src/lib.rs:314 -> commit :651-700): pad, encode every row,
+ * hash every column, build the Merkle tree.
+ *   coeffs      n_coeffs elements (host)
+ *   coeffs_out  nullable; n_rows*n_per_row elements  = LcCommit.coeffs
+ *   comm_out    nullable; n_rows*n_cols elements     = LcCommit.comm
+ *   hashes_out  nullable; (2*np2-1)*32 bytes         = LcCommit.hashes
+ *   keep        nullable; receives a device-resident handle for fold/open calls
+ * Errors: LCPC_ERR_DIMS when n_coeffs == 0; LCPC_ERR_TOO_BIG when next_power_of_two
+ * overflows (:685-687). */
+int32_t lcpc_commit_host(lcpc_plan *plan, const uint64_t *coeffs, size_t n_coeffs,
+                         uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out,
+                         lcpc_commit **keep);
+
+/* proof-of-storage path: DataField::from_byte_vec for WriteableFt63 (7 file bytes ->
+ * one element whose limb IS the little-endian integer, proof-of-storage/src/fields/
+ * writable_ft63.rs:35-40, data_field.rs:38-46) fused in front of the commit
+ * (lcpc_online.rs:81-143 convert_file_data_to_commit, CommitRequestType::Commit).
+ * Plan field must be LCPC_FT63. */
+int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_t n_bytes,
+                               uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out,
+                               lcpc_commit **keep);
+
+/* Same as lcpc_commit_host with the coefficients already on the device; nothing is
+ * copied to the host.  The handle owns coeffs (padded), comm and hashes in HBM. */
+int32_t lcpc_commit_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_coeffs, lcpc_commit **keep);
+
+int32_t lcpc_commit_get_dims(const lcpc_commit *c, size_t *n_rows, size_t *n_per_row, size_t *n_cols);
+/* LcCommit::get_root (lib.rs:291-296) */
+int32_t lcpc_commit_root(lcpc_commit *c, uint8_t root_out[LCPC_DIGEST_BYTES]);
+/* Copies of the handle's buffers to host memory; any pointer may be NULL. */
+int32_t lcpc_commit_download(lcpc_commit *c, uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out);
+/* Raw device pointers of the handle's buffers (borrowed; valid until lcpc_commit_free). */
+int32_t lcpc_commit_device_ptrs(lcpc_commit *c, uint64_t **d_coeffs, uint64_t **d_comm, uint8_t **d_hashes);
+void lcpc_commit_free(lcpc_commit *c);
+
+/* ---- fold / open ------------------------------------------------------------------ */
+
+/* collapse_columns (lib.rs:1126-1154): out[t][j] = sum_r tensors[t][r] * M[r][j].
+ *   which = 0: M = coeffs (n_per_row wide)  -- prove's p_random / p_eval (:1064-1092)
+ *   which = 1: M = comm   (n_cols wide)     -- proof-of-storage
+ *              verifiable_polynomial_evaluation (lcpc_online.rs:454-484), tests' eval_outer_fft
+ * tensors: n_tensors * n_rows elements (host); out: n_tensors * width elements (host). */
+int32_t lcpc_fold_host(lcpc_commit *c, int32_t which, const uint64_t *tensors, size_t n_tensors,
+                       uint64_t *out);
+
+/* open_column for `n` columns at once (lib.rs:818-855): cols_out[i] = the n_rows
+ * elements of column cols[i]; paths_out[i] = log2(np2) sibling digests, leaf level
+ * first.  LCPC_ERR_COLUMN_NUMBER if any index >= n_cols.  Either output may be NULL
+ * (ColumnsWithoutPath, lcpc_online.rs:191-225). */
+int32_t lcpc_open_columns_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
+                               uint8_t *paths_out);
+
+/* Leaf digests of selected columns only (CommitRequestType::Leaves, lcpc_online.rs:144-190). */
+int32_t lcpc_leaves_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint8_t *leaves_out);
+
+/* ---- device-pointer building blocks (sharded / device-resident pipelines) --------- */
+
+/* rows [0, n_rows) of the padded coefficient matrix -> encoded rows.  d_coeffs has
+ * row stride n_per_row, d_comm row stride n_cols.  d_coeffs may alias nothing in d_comm. */
+int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);
+/* hash_columns (lib.rs:736-775) on a column window: leaves[j] for j in [0, n_cols) of a
+ * matrix with `n_rows` rows whose row stride is `row_stride` elements, starting at d_mat. */
+int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows,
+                              size_t row_stride, size_t n_cols, uint8_t *d_leaves);
+/* merkle_tree (lib.rs:777-815) in place over [n_leaves | n_leaves/2 | ... | 1]; n_leaves a power of two. */
+int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves);
+/* collapse_columns on device buffers; d_out has n_tensors*width elements. */
+int32_t lcpc_dev_fold(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t width,
+                      size_t row_stride, const uint64_t *d_tensors, size_t n_tensors, uint64_t *d_out);
+/* element-wise modular sum of `n_parts` partial fold results (the reduction after the
+ * all-gather in the row-sharded fold): d_out[i] = sum_k d_parts[k*n + i]. */
+int32_t lcpc_dev_add_partials(lcpc_ctx *ctx, int32_t field, const uint64_t *d_parts, size_t n_parts,
+                              size_t n, uint64_t *d_out);
+/* strided gather of columns: d_out[i*n_rows + r] = d_mat[r*row_stride + cols[i]] (d_cols on device). */
+int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows,
+                                size_t row_stride, const uint64_t *d_cols, size_t n, uint64_t *d_out);
+/* 7-byte packing (WriteableFt63::from_data_bytes): n_elems = ceil(n_bytes/7) limbs written. */
+int32_t lcpc_dev_pack_bytes7(lcpc_ctx *ctx, const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems);
+
+/* number of kernels this library has launched on this context since creation */
+uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx);
+/* Per-kernel device timing: when enabled, every launch on this context is bracketed by
+ * CUDA events on the context's stream.  The report drains the records collected so far:
+ * one line per kernel name, "<name> <launches> <total_ms>\n" (owned by the context,
+ * valid until the next call). */
+int32_t lcpc_ctx_kernel_timing(lcpc_ctx *ctx, int32_t enable);
+const char *lcpc_ctx_kernel_timing_report(lcpc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCPC_B200_H */

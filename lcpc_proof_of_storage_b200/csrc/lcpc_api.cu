@@ -1,0 +1,793 @@
+// C ABI of lcpc_b200 (see include/lcpc_b200.h for the contract and the reference
+// items each entry point replaces).  Handles own device memory; host buffers belong to
+// the caller.  No CPU fallback: without a CUDA device every call fails loudly.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lcpc_b200.h"
+#include "lcpc_field.cuh"
+#include "lcpc_kernels.h"
+
+using namespace lcpc;
+
+namespace lcpc {
+// CUDA-event stopwatch around every kernel launch of a context (off by default).
+struct KernelTimer {
+    struct Rec {
+        const char *name;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!pool.empty()) {
+            e = pool.back();
+            pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+    ~KernelTimer() {
+        for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+void timer_begin(KernelTimer *t, const char *name, cudaStream_t s) {
+    KernelTimer::Rec r{name, t->get(), t->get()};
+    cudaEventRecord(r.a, s);
+    t->recs.push_back(r);
+}
+void timer_end(KernelTimer *t, cudaStream_t s) {
+    if (!t->recs.empty()) cudaEventRecord(t->recs.back().b, s);
+}
+}  // namespace lcpc
+
+struct lcpc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    lcpc::KernelTimer *timer = nullptr;
+    std::string timing_report;
+    std::mutex mu;
+    std::atomic<int> refs{1};  // the creator + every live plan
+    lcpc::Launch lc() { return lcpc::Launch{stream, &launches, timer}; }
+};
+
+struct lcpc_plan {
+    lcpc_ctx *ctx = nullptr;
+    int kind = 0;  // 0 = Ligero (NTT), 1 = Brakedown (SpMV chain)
+    int fid = 0;
+    size_t n_per_row = 0, n_cols = 0;
+    NttPlan ntt;
+    SdigPlan sdig;
+    std::mutex mu;
+    std::atomic<int> refs{1};  // the creator + every live commit
+};
+
+struct lcpc_commit {
+    lcpc_plan *plan = nullptr;
+    size_t n_rows = 0, n_per_row = 0, n_cols = 0, np2 = 0;
+    uint64_t *d_coeffs = nullptr;
+    uint64_t *d_comm = nullptr;
+    uint8_t *d_hashes = nullptr;
+    std::mutex mu;
+};
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int32_t fail(int32_t code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+int32_t cuda_fail(cudaError_t e, const char *what) {
+    cudaGetLastError();  // clear sticky-less errors
+    return fail(e == cudaErrorMemoryAllocation ? LCPC_ERR_NOMEM : LCPC_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+bool valid_field(int32_t f) { return f >= 0 && f < N_FIELDS; }
+int limbs_of(int fid) { return field_consts(fid).limbs; }
+
+size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) {
+        if (p > (SIZE_MAX >> 1)) return 0;
+        p <<= 1;
+    }
+    return p;
+}
+
+// stream-ordered device buffer that frees itself
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        if (bytes == 0) bytes = 8;
+        return cudaMallocAsync(&p, bytes, stream);
+    }
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    template <class T>
+    T *as() { return reinterpret_cast<T *>(p); }
+};
+
+void free_csr(DevCsr &m) {
+    if (m.d_rowptr) cudaFree(m.d_rowptr);
+    if (m.d_colidx) cudaFree(m.d_colidx);
+    if (m.d_data) cudaFree(m.d_data);
+    m = DevCsr{};
+}
+
+// CSC (host, caller's) -> CSR (device)
+int32_t upload_csr(const lcpc_csc &a, int L, DevCsr &out) {
+    if (!a.indptr || (a.indptr[a.cols] && (!a.indices || !a.data))) return fail(LCPC_ERR_INVALID_ARG, "null CSC arrays");
+    const size_t nnz = (size_t)a.indptr[a.cols];
+    if (a.rows > 0xffffffffull || a.cols > 0xffffffffull || nnz > 0xffffffffull)
+        return fail(LCPC_ERR_TOO_BIG, "code matrix too large for 32-bit indices");
+    std::vector<uint32_t> rowptr(a.rows + 1, 0), colidx(nnz);
+    std::vector<uint64_t> data(nnz * (size_t)L);
+    for (size_t k = 0; k < nnz; k++) {
+        if (a.indices[k] >= a.rows) return fail(LCPC_ERR_INVALID_ARG, "CSC row index out of range");
+        rowptr[a.indices[k] + 1]++;
+    }
+    for (size_t i = 0; i < a.rows; i++) rowptr[i + 1] += rowptr[i];
+    std::vector<uint32_t> fill(rowptr.begin(), rowptr.end() - 1);
+    for (size_t j = 0; j < a.cols; j++)
+        for (uint64_t k = a.indptr[j]; k < a.indptr[j + 1]; k++) {
+            const uint32_t dst = fill[a.indices[k]]++;
+            colidx[dst] = (uint32_t)j;
+            std::memcpy(&data[(size_t)dst * L], &a.data[k * L], L * sizeof(uint64_t));
+        }
+    out.rows = a.rows;
+    out.cols = a.cols;
+    out.nnz = nnz;
+    CU(cudaMalloc(&out.d_rowptr, (a.rows + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&out.d_colidx, (nnz ? nnz : 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&out.d_data, (nnz ? nnz : 1) * L * sizeof(uint64_t)));
+    CU(cudaMemcpy(out.d_rowptr, rowptr.data(), (a.rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (nnz) {
+        CU(cudaMemcpy(out.d_colidx, colidx.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(out.d_data, data.data(), nnz * L * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    return LCPC_OK;
+}
+
+// encode rows already resident: ligero reads d_coeffs (stride n_per_row), brakedown widens first
+int32_t encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm) {
+    lcpc_ctx *ctx = plan->ctx;
+    if (plan->kind == 0) {
+        CU(ntt_encode(plan->ntt, d_coeffs, plan->n_per_row, plan->n_per_row, d_comm, n_rows, ctx->lc()));
+    } else {
+        CU(widen_rows(plan->fid, d_coeffs, plan->n_per_row, d_comm, plan->n_cols, n_rows, ctx->lc()));
+        DevBuf tmp;
+        CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * limbs_of(plan->fid) * sizeof(uint64_t), ctx->stream));
+        CU(sdig_encode(plan->sdig, d_comm, n_rows, tmp.as<uint64_t>(), ctx->lc()));
+    }
+    return LCPC_OK;
+}
+
+int32_t merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_rows, size_t n_cols, size_t np2,
+                      uint8_t *d_hashes) {
+    // padding leaves n_cols..np2 stay all-zero (lib.rs:685-695)
+    if (np2 > n_cols) CU(cudaMemsetAsync(d_hashes + n_cols * 32, 0, (np2 - n_cols) * 32, ctx->stream));
+    DevBuf scratch;
+    CU(scratch.alloc(hash_scratch_bytes(fid, n_rows, n_cols), ctx->stream));
+    CU(hash_columns(fid, d_comm, n_rows, n_cols, n_cols, nullptr, d_hashes, scratch.as<uint8_t>(), ctx->lc()));
+    CU(merkle_tree(d_hashes, np2, ctx->lc()));
+    return LCPC_OK;
+}
+
+// Handles are reference counted (ctx <- plan <- commit), so the order in which a caller
+// (e.g. a garbage collector) destroys them does not matter.
+void ctx_unref(lcpc_ctx *ctx) {
+    if (!ctx || ctx->refs.fetch_sub(1) != 1) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->timer;
+    delete ctx;
+}
+
+void plan_unref(lcpc_plan *plan) {
+    if (!plan || plan->refs.fetch_sub(1) != 1) return;
+    lcpc_ctx *ctx = plan->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ntt_plan_free(plan->ntt);
+    for (auto &m : plan->sdig.pre) free_csr(m);
+    for (auto &m : plan->sdig.post) free_csr(m);
+    delete plan;
+    ctx_unref(ctx);
+}
+
+
+void commit_release(lcpc_commit *c) {
+    if (!c) return;
+    if (c->plan) {
+        cudaStream_t s = c->plan->ctx->stream;
+        if (c->d_coeffs) cudaFreeAsync(c->d_coeffs, s);
+        if (c->d_comm) cudaFreeAsync(c->d_comm, s);
+        if (c->d_hashes) cudaFreeAsync(c->d_hashes, s);
+    }
+    lcpc_plan *plan = c->plan;
+    delete c;
+    plan_unref(plan);
+}
+
+// shared tail of the commit entry points: d_coeffs (padded, device) is ready in `c`
+int32_t commit_finish(lcpc_plan *plan, lcpc_commit *c, uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out) {
+    lcpc_ctx *ctx = plan->ctx;
+    const int L = limbs_of(plan->fid);
+    const size_t wbytes = (size_t)L * sizeof(uint64_t);
+    CU(cudaMallocAsync((void **)&c->d_comm, c->n_rows * c->n_cols * wbytes, ctx->stream));
+    CU(cudaMallocAsync((void **)&c->d_hashes, (2 * c->np2 - 1) * 32, ctx->stream));
+    int32_t rc = encode_dev(plan, c->d_coeffs, c->n_rows, c->d_comm);
+    if (rc != LCPC_OK) return rc;
+    rc = merkleize_dev(ctx, plan->fid, c->d_comm, c->n_rows, c->n_cols, c->np2, c->d_hashes);
+    if (rc != LCPC_OK) return rc;
+    if (coeffs_out)
+        CU(cudaMemcpyAsync(coeffs_out, c->d_coeffs, c->n_rows * c->n_per_row * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (comm_out)
+        CU(cudaMemcpyAsync(comm_out, c->d_comm, c->n_rows * c->n_cols * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hashes_out)
+        CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t commit_shape(lcpc_plan *plan, size_t n_coeffs, lcpc_commit *c) {
+    // lib.rs:656-661
+    if (n_coeffs == 0) return fail(LCPC_ERR_DIMS, "cannot commit to zero coefficients");
+    c->plan = plan;
+    plan->refs.fetch_add(1);
+    c->n_per_row = plan->n_per_row;
+    c->n_cols = plan->n_cols;
+    c->n_rows = (n_coeffs + plan->n_per_row - 1) / plan->n_per_row;
+    c->np2 = next_pow2(plan->n_cols);
+    if (c->np2 == 0) return fail(LCPC_ERR_TOO_BIG, "n_cols is too large for this encoding");
+    return LCPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t lcpc_abi_version(void) { return 1; }
+
+const char *lcpc_last_error(void) { return g_err.c_str(); }
+
+int32_t lcpc_field_limbs(int32_t field) { return valid_field(field) ? limbs_of(field) : 0; }
+
+int32_t lcpc_field_constants(int32_t field, uint64_t *modulus, uint64_t *one_mont, uint64_t *root_of_unity_mont,
+                             int32_t *two_adicity, int32_t *num_bits) {
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    const FieldConsts fc = field_consts(field);
+    for (int i = 0; i < fc.limbs; i++) {
+        if (modulus) modulus[i] = fc.p[i];
+        if (one_mont) one_mont[i] = fc.r[i];
+        if (root_of_unity_mont) root_of_unity_mont[i] = fc.root[i];
+    }
+    if (two_adicity) *two_adicity = fc.two_adicity;
+    if (num_bits) *num_bits = fc.num_bits;
+    return LCPC_OK;
+}
+
+static int32_t ctx_create(int32_t device, void *stream, bool own, lcpc_ctx **out) {
+    if (!out) return fail(LCPC_ERR_INVALID_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LCPC_ERR_CUDA, std::string("no CUDA device available (lcpc_b200 has no CPU fallback): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(LCPC_ERR_INVALID_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    lcpc_ctx *ctx = new (std::nothrow) lcpc_ctx;
+    if (!ctx) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    ctx->device = device;
+    if (own) {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return cuda_fail(e, "cudaStreamCreateWithFlags");
+        }
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)stream;
+    }
+    // keep freed blocks in the pool: repeated commits reuse them without driver calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    *out = ctx;
+    return LCPC_OK;
+}
+
+int32_t lcpc_ctx_create(int32_t device, lcpc_ctx **out) { return ctx_create(device, nullptr, true, out); }
+
+int32_t lcpc_ctx_create_on_stream(int32_t device, void *cuda_stream, lcpc_ctx **out) {
+    return ctx_create(device, cuda_stream, false, out);
+}
+
+int32_t lcpc_ctx_synchronize(lcpc_ctx *ctx) {
+    if (!ctx) return fail(LCPC_ERR_INVALID_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+void lcpc_ctx_destroy(lcpc_ctx *ctx) { ctx_unref(ctx); }
+
+uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t lcpc_ctx_kernel_timing(lcpc_ctx *ctx, int32_t enable) {
+    if (!ctx) return fail(LCPC_ERR_INVALID_ARG, "null context");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (enable && !ctx->timer) ctx->timer = new (std::nothrow) lcpc::KernelTimer;
+    if (!enable && ctx->timer) {
+        cudaStreamSynchronize(ctx->stream);
+        delete ctx->timer;
+        ctx->timer = nullptr;
+    }
+    return LCPC_OK;
+}
+
+const char *lcpc_ctx_kernel_timing_report(lcpc_ctx *ctx) {
+    if (!ctx) return "";
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->timing_report.clear();
+    if (!ctx->timer) return ctx->timing_report.c_str();
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    struct Agg { const char *name; uint64_t n; double ms; };
+    std::vector<Agg> agg;
+    for (auto &r : ctx->timer->recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        bool found = false;
+        for (auto &a : agg)
+            if (std::strcmp(a.name, r.name) == 0) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back({r.name, 1, (double)ms});
+        ctx->timer->pool.push_back(r.a);
+        ctx->timer->pool.push_back(r.b);
+    }
+    ctx->timer->recs.clear();
+    char line[160];
+    for (auto &a : agg) {
+        std::snprintf(line, sizeof line, "%s %llu %.6f\n", a.name, (unsigned long long)a.n, a.ms);
+        ctx->timing_report += line;
+    }
+    return ctx->timing_report.c_str();
+}
+
+int32_t lcpc_plan_ligero(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size_t n_cols,
+                         const uint64_t *root_of_unity_mont, lcpc_plan **out) {
+    if (!ctx || !out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    // _dims_ok (lcpc-ligero-pc/src/lib.rs:114-118) + the 2-adicity bound of precomp_fft
+    if (!(n_per_row < n_cols) || n_per_row == 0 || (n_cols & (n_cols - 1)) != 0)
+        return fail(LCPC_ERR_DIMS, "need 0 < n_per_row < n_cols and n_cols a power of two");
+    int log_n = 0;
+    while (((size_t)1 << log_n) < n_cols) log_n++;
+    if (log_n > field_consts(field).two_adicity) return fail(LCPC_ERR_TOO_BIG, "n_cols exceeds the field's 2-adicity");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    lcpc_plan *p = new (std::nothrow) lcpc_plan;
+    if (!p) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    p->ctx = ctx;
+    ctx->refs.fetch_add(1);
+    p->kind = 0;
+    p->fid = field;
+    p->n_per_row = n_per_row;
+    p->n_cols = n_cols;
+    cudaError_t e = ntt_plan_build(p->ntt, field, log_n, root_of_unity_mont, ctx->lc());
+    if (e != cudaSuccess) {
+        ntt_plan_free(p->ntt);
+        delete p;
+        ctx->refs.fetch_sub(1);
+        return cuda_fail(e, "ntt_plan_build");
+    }
+    *out = p;
+    return LCPC_OK;
+}
+
+int32_t lcpc_plan_brakedown(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size_t n_cols, size_t n_levels,
+                            const lcpc_csc *precodes, const lcpc_csc *postcodes, lcpc_plan **out) {
+    if (!ctx || !out || !precodes || !postcodes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    if (n_levels == 0) return fail(LCPC_ERR_DIMS, "need at least one code level");
+    // codeword_length (encode.rs:18-33) and the dims_ok checks of brakedown lib.rs:160-167
+    size_t len = precodes[0].cols + postcodes[n_levels - 1].cols;
+    for (size_t l = 0; l + 1 < n_levels; l++) len += precodes[l].rows;
+    for (size_t l = 0; l < n_levels; l++) len += postcodes[l].rows;
+    if (precodes[0].cols != n_per_row || len != n_cols || !(n_per_row < n_cols))
+        return fail(LCPC_ERR_DIMS, "n_per_row / n_cols do not match the code matrices");
+    // chain consistency: what each product reads must be what earlier levels wrote
+    for (size_t l = 0; l + 1 < n_levels; l++)
+        if (precodes[l + 1].cols != precodes[l].rows) return fail(LCPC_ERR_DIMS, "precode chain mismatch");
+    {
+        size_t in_len = postcodes[n_levels - 1].cols;
+        for (size_t l = n_levels; l-- > 0;) {
+            if (postcodes[l].cols != in_len) return fail(LCPC_ERR_DIMS, "postcode chain mismatch");
+            if (l > 0) in_len = precodes[l - 1].rows + in_len + postcodes[l].rows;
+        }
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    lcpc_plan *p = new (std::nothrow) lcpc_plan;
+    if (!p) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    p->ctx = ctx;
+    ctx->refs.fetch_add(1);
+    p->kind = 1;
+    p->fid = field;
+    p->n_per_row = n_per_row;
+    p->n_cols = n_cols;
+    p->sdig.fid = field;
+    p->sdig.n_per_row = n_per_row;
+    p->sdig.n_cols = n_cols;
+    p->sdig.pre.resize(n_levels);
+    p->sdig.post.resize(n_levels);
+    const int L = limbs_of(field);
+    for (size_t l = 0; l < n_levels; l++) {
+        int32_t rc = upload_csr(precodes[l], L, p->sdig.pre[l]);
+        if (rc == LCPC_OK) rc = upload_csr(postcodes[l], L, p->sdig.post[l]);
+        if (rc != LCPC_OK) {
+            lcpc_plan_destroy(p);
+            return rc;
+        }
+    }
+    *out = p;
+    return LCPC_OK;
+}
+
+int32_t lcpc_plan_get_dims(const lcpc_plan *plan, size_t len, size_t *n_rows, size_t *n_per_row, size_t *n_cols) {
+    if (!plan) return fail(LCPC_ERR_INVALID_ARG, "null plan");
+    if (n_rows) *n_rows = (len + plan->n_per_row - 1) / plan->n_per_row;
+    if (n_per_row) *n_per_row = plan->n_per_row;
+    if (n_cols) *n_cols = plan->n_cols;
+    return LCPC_OK;
+}
+
+void lcpc_plan_destroy(lcpc_plan *plan) { plan_unref(plan); }
+
+
+int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
+    if (!plan || (!rows && n_rows)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (n_rows == 0) return LCPC_OK;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const int L = limbs_of(plan->fid);
+    const size_t bytes = n_rows * plan->n_cols * L * sizeof(uint64_t);
+    DevBuf buf;
+    CU(buf.alloc(bytes, ctx->stream));
+    CU(cudaMemcpyAsync(buf.p, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (plan->kind == 0) {
+        // fft_io_pc transforms whatever the row holds (all n_cols entries)
+        CU(ntt_encode(plan->ntt, buf.as<uint64_t>(), plan->n_cols, plan->n_cols, buf.as<uint64_t>(), n_rows, ctx->lc()));
+    } else {
+        DevBuf tmp;
+        CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * L * sizeof(uint64_t), ctx->stream));
+        CU(sdig_encode(plan->sdig, buf.as<uint64_t>(), n_rows, tmp.as<uint64_t>(), ctx->lc()));
+    }
+    CU(cudaMemcpyAsync(rows, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_commit_host(lcpc_plan *plan, const uint64_t *coeffs, size_t n_coeffs, uint64_t *coeffs_out,
+                         uint64_t *comm_out, uint8_t *hashes_out, lcpc_commit **keep) {
+    if (keep) *keep = nullptr;
+    if (!plan || !coeffs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    lcpc_commit *c = new (std::nothrow) lcpc_commit;
+    if (!c) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    int32_t rc = commit_shape(plan, n_coeffs, c);
+    const size_t wbytes = (size_t)limbs_of(plan->fid) * sizeof(uint64_t);
+    auto body = [&]() -> int32_t {
+        const size_t padded = c->n_rows * c->n_per_row;
+        CU(cudaMallocAsync((void **)&c->d_coeffs, padded * wbytes, ctx->stream));
+        CU(cudaMemcpyAsync(c->d_coeffs, coeffs, n_coeffs * wbytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (padded > n_coeffs)  // lib.rs:665-674: the last row is zero-filled
+            CU(cudaMemsetAsync(c->d_coeffs + n_coeffs * limbs_of(plan->fid), 0, (padded - n_coeffs) * wbytes, ctx->stream));
+        return commit_finish(plan, c, coeffs_out, comm_out, hashes_out);
+    };
+    if (rc == LCPC_OK) rc = body();
+    if (rc != LCPC_OK || !keep) {
+        commit_release(c);
+        if (rc == LCPC_OK) cudaStreamSynchronize(ctx->stream);
+    } else {
+        *keep = c;
+    }
+    return rc;
+}
+
+int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_t n_bytes, uint64_t *coeffs_out,
+                               uint64_t *comm_out, uint8_t *hashes_out, lcpc_commit **keep) {
+    if (keep) *keep = nullptr;
+    if (!plan || !file_bytes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (plan->fid != FT63) return fail(LCPC_ERR_INVALID_ARG, "byte packing is defined for the 63-bit field only");
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t n_coeffs = (n_bytes + 6) / 7;
+    lcpc_commit *c = new (std::nothrow) lcpc_commit;
+    if (!c) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    int32_t rc = commit_shape(plan, n_coeffs, c);
+    auto body = [&]() -> int32_t {
+        const size_t padded = c->n_rows * c->n_per_row;
+        DevBuf raw;
+        CU(raw.alloc(n_bytes, ctx->stream));
+        CU(cudaMemcpyAsync(raw.p, file_bytes, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMallocAsync((void **)&c->d_coeffs, padded * sizeof(uint64_t), ctx->stream));
+        CU(pack_bytes7(raw.as<uint8_t>(), n_bytes, c->d_coeffs, ctx->lc()));
+        if (padded > n_coeffs)
+            CU(cudaMemsetAsync(c->d_coeffs + n_coeffs, 0, (padded - n_coeffs) * sizeof(uint64_t), ctx->stream));
+        return commit_finish(plan, c, coeffs_out, comm_out, hashes_out);
+    };
+    if (rc == LCPC_OK) rc = body();
+    if (rc != LCPC_OK || !keep) {
+        commit_release(c);
+        if (rc == LCPC_OK) cudaStreamSynchronize(ctx->stream);
+    } else {
+        *keep = c;
+    }
+    return rc;
+}
+
+int32_t lcpc_commit_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_coeffs, lcpc_commit **keep) {
+    if (!plan || !d_coeffs || !keep) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    *keep = nullptr;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    lcpc_commit *c = new (std::nothrow) lcpc_commit;
+    if (!c) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    int32_t rc = commit_shape(plan, n_coeffs, c);
+    const int L = limbs_of(plan->fid);
+    const size_t wbytes = (size_t)L * sizeof(uint64_t);
+    auto body = [&]() -> int32_t {
+        const size_t padded = c->n_rows * c->n_per_row;
+        CU(cudaMallocAsync((void **)&c->d_coeffs, padded * wbytes, ctx->stream));
+        CU(cudaMemcpyAsync(c->d_coeffs, d_coeffs, n_coeffs * wbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (padded > n_coeffs)
+            CU(cudaMemsetAsync(c->d_coeffs + n_coeffs * L, 0, (padded - n_coeffs) * wbytes, ctx->stream));
+        return commit_finish(plan, c, nullptr, nullptr, nullptr);
+    };
+    if (rc == LCPC_OK) rc = body();
+    if (rc != LCPC_OK) {
+        commit_release(c);
+        return rc;
+    }
+    *keep = c;
+    return LCPC_OK;
+}
+
+int32_t lcpc_commit_get_dims(const lcpc_commit *c, size_t *n_rows, size_t *n_per_row, size_t *n_cols) {
+    if (!c) return fail(LCPC_ERR_INVALID_ARG, "null commit");
+    if (n_rows) *n_rows = c->n_rows;
+    if (n_per_row) *n_per_row = c->n_per_row;
+    if (n_cols) *n_cols = c->n_cols;
+    return LCPC_OK;
+}
+
+int32_t lcpc_commit_root(lcpc_commit *c, uint8_t root_out[LCPC_DIGEST_BYTES]) {
+    if (!c || !root_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    lcpc_ctx *ctx = c->plan->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(root_out, c->d_hashes + (2 * c->np2 - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_commit_download(lcpc_commit *c, uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out) {
+    if (!c) return fail(LCPC_ERR_INVALID_ARG, "null commit");
+    lcpc_ctx *ctx = c->plan->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t wbytes = (size_t)limbs_of(c->plan->fid) * sizeof(uint64_t);
+    if (coeffs_out)
+        CU(cudaMemcpyAsync(coeffs_out, c->d_coeffs, c->n_rows * c->n_per_row * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (comm_out)
+        CU(cudaMemcpyAsync(comm_out, c->d_comm, c->n_rows * c->n_cols * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hashes_out)
+        CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_commit_device_ptrs(lcpc_commit *c, uint64_t **d_coeffs, uint64_t **d_comm, uint8_t **d_hashes) {
+    if (!c) return fail(LCPC_ERR_INVALID_ARG, "null commit");
+    if (d_coeffs) *d_coeffs = c->d_coeffs;
+    if (d_comm) *d_comm = c->d_comm;
+    if (d_hashes) *d_hashes = c->d_hashes;
+    return LCPC_OK;
+}
+
+void lcpc_commit_free(lcpc_commit *c) {
+    if (!c) return;
+    if (c->plan) cudaSetDevice(c->plan->ctx->device);
+    commit_release(c);  // may drop the last reference to the plan / context: hold no lock here
+}
+
+int32_t lcpc_fold_host(lcpc_commit *c, int32_t which, const uint64_t *tensors, size_t n_tensors, uint64_t *out) {
+    if (!c || !tensors || !out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (which != 0 && which != 1) return fail(LCPC_ERR_INVALID_ARG, "which must be 0 (coeffs) or 1 (comm)");
+    if (n_tensors == 0) return LCPC_OK;
+    lcpc_ctx *ctx = c->plan->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const int fid = c->plan->fid;
+    const size_t wbytes = (size_t)limbs_of(fid) * sizeof(uint64_t);
+    const size_t width = which == 0 ? c->n_per_row : c->n_cols;
+    const uint64_t *mat = which == 0 ? c->d_coeffs : c->d_comm;
+    DevBuf d_t, d_o, d_s;
+    CU(d_t.alloc(n_tensors * c->n_rows * wbytes, ctx->stream));
+    CU(d_o.alloc(n_tensors * width * wbytes, ctx->stream));
+    CU(d_s.alloc(fold_scratch_bytes(fid, c->n_rows, width, n_tensors), ctx->stream));
+    CU(cudaMemcpyAsync(d_t.p, tensors, n_tensors * c->n_rows * wbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(fold(fid, mat, c->n_rows, width, width, d_t.as<uint64_t>(), n_tensors, d_o.as<uint64_t>(), d_s.as<uint64_t>(),
+            ctx->lc()));
+    CU(cudaMemcpyAsync(out, d_o.p, n_tensors * width * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_open_columns_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out, uint8_t *paths_out) {
+    if (!c || (!cols && n)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    for (size_t i = 0; i < n; i++)
+        if (cols[i] >= c->n_cols) return fail(LCPC_ERR_COLUMN_NUMBER, "bad column number");
+    if (n == 0) return LCPC_OK;
+    lcpc_ctx *ctx = c->plan->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const int fid = c->plan->fid;
+    const size_t wbytes = (size_t)limbs_of(fid) * sizeof(uint64_t);
+    int depth = 0;
+    while (((size_t)1 << depth) < c->np2) depth++;
+    DevBuf d_cols, d_out, d_paths;
+    CU(d_cols.alloc(n * sizeof(uint64_t), ctx->stream));
+    CU(cudaMemcpyAsync(d_cols.p, cols, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (cols_out) {
+        CU(d_out.alloc(n * c->n_rows * wbytes, ctx->stream));
+        CU(gather_columns(fid, c->d_comm, c->n_rows, c->n_cols, d_cols.as<uint64_t>(), n, d_out.as<uint64_t>(), ctx->lc()));
+        CU(cudaMemcpyAsync(cols_out, d_out.p, n * c->n_rows * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (paths_out && depth > 0) {
+        CU(d_paths.alloc(n * (size_t)depth * 32, ctx->stream));
+        CU(gather_paths(c->d_hashes, c->np2, d_cols.as<uint64_t>(), n, d_paths.as<uint8_t>(), ctx->lc()));
+        CU(cudaMemcpyAsync(paths_out, d_paths.p, n * (size_t)depth * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_leaves_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint8_t *leaves_out) {
+    if (!c || (!cols && n) || (!leaves_out && n)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    for (size_t i = 0; i < n; i++)
+        if (cols[i] >= c->n_cols) return fail(LCPC_ERR_COLUMN_NUMBER, "bad column number");
+    if (n == 0) return LCPC_OK;
+    lcpc_ctx *ctx = c->plan->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const int fid = c->plan->fid;
+    DevBuf d_cols, d_leaves, d_s;
+    CU(d_cols.alloc(n * sizeof(uint64_t), ctx->stream));
+    CU(d_leaves.alloc(n * 32, ctx->stream));
+    CU(d_s.alloc(hash_scratch_bytes(fid, c->n_rows, n), ctx->stream));
+    CU(cudaMemcpyAsync(d_cols.p, cols, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(hash_columns(fid, c->d_comm, c->n_rows, c->n_cols, n, d_cols.as<uint64_t>(), d_leaves.as<uint8_t>(), d_s.as<uint8_t>(),
+                    ctx->lc()));
+    CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+// ---- device-pointer building blocks -------------------------------------------------
+
+int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm) {
+    if (!plan || !d_coeffs || !d_comm) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(plan->ctx->mu);
+    CU(cudaSetDevice(plan->ctx->device));
+    return encode_dev(plan, d_coeffs, n_rows, d_comm);
+}
+
+int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
+                              size_t n_cols, uint8_t *d_leaves) {
+    if (!ctx || !d_mat || !d_leaves) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    DevBuf scratch;
+    CU(scratch.alloc(hash_scratch_bytes(field, n_rows, n_cols), ctx->stream));
+    CU(hash_columns(field, d_mat, n_rows, row_stride, n_cols, nullptr, d_leaves, scratch.as<uint8_t>(), ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves) {
+    if (!ctx || !d_hashes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(merkle_tree(d_hashes, n_leaves, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_fold(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t width,
+                      size_t row_stride, const uint64_t *d_tensors, size_t n_tensors, uint64_t *d_out) {
+    if (!ctx || !d_mat || !d_tensors || !d_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d_s;
+    CU(d_s.alloc(fold_scratch_bytes(field, n_rows, width, n_tensors), ctx->stream));
+    CU(fold(field, d_mat, n_rows, width, row_stride, d_tensors, n_tensors, d_out, d_s.as<uint64_t>(), ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_add_partials(lcpc_ctx *ctx, int32_t field, const uint64_t *d_parts, size_t n_parts, size_t n,
+                              uint64_t *d_out) {
+    if (!ctx || !d_parts || !d_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(add_partials(field, d_parts, n_parts, n, d_out, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
+                                const uint64_t *d_cols, size_t n, uint64_t *d_out) {
+    if (!ctx || !d_mat || !d_cols || !d_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(gather_columns(field, d_mat, n_rows, row_stride, d_cols, n, d_out, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_pack_bytes7(lcpc_ctx *ctx, const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems) {
+    if (!ctx || !d_bytes || !d_elems) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(pack_bytes7(d_bytes, n_bytes, d_elems, ctx->lc()));
+    return LCPC_OK;
+}
+
+}  // extern "C"

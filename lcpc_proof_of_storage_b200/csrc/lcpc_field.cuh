@@ -1,0 +1,290 @@
+// Prime-field arithmetic for the lcpc fields on sm_100a.
+//
+// Elements are LIMBS x u64, least-significant limb first, Montgomery form with
+// R = 2^(64*LIMBS), always fully reduced on loads/stores to global memory -- the
+// in-memory form ff_derive 0.13 gives the reference's fields
+// (lcpc-test-fields/src/lib.rs:18-70; WriteableFt63: proof-of-storage/src/fields/
+// writable_ft63.rs:8-12).  All four moduli are p = c*2^40 + 1 in their low limb, so
+// -p^-1 mod 2^32 = 0xffffffff: the Montgomery quotient digit is a negation.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lcpc {
+
+enum FieldId : int { FT63 = 0, FT127 = 1, FT191 = 2, FT255 = 3, N_FIELDS = 4 };
+
+template <int L>
+struct Fe {
+    uint64_t v[L];
+};
+
+// Host-visible constant tables (also used by the API for lcpc_field_constants).
+struct FieldConsts {
+    int limbs, num_bits, two_adicity;
+    uint64_t p[4], inv, r[4], r2[4], root[4];
+};
+
+__host__ __device__ constexpr FieldConsts field_consts(int fid) {
+    switch (fid) {
+    case FT63:
+        return {1, 63, 41,
+                {0x46d0760000000001ull, 0, 0, 0},
+                0x46d075ffffffffffull,
+                {0x2b8e9dfffffffffdull, 0, 0, 0},
+                {0x13085abb0716119eull, 0, 0, 0},
+                {0x23bcb75f84213a43ull, 0, 0, 0}};
+    case FT127:
+        return {2, 127, 40,
+                {0x7f2bd90000000001ull, 0x6e754097ba20e0bfull, 0, 0},
+                0x7f2bd8ffffffffffull,
+                {0x01a84dfffffffffeull, 0x23157ed08bbe3e81ull, 0, 0},
+                {0x816bd5407cf6dce5ull, 0x2c1637057de6fce8ull, 0, 0},
+                {0xf491a1dff39975f8ull, 0x178fd41c0f6a04faull, 0, 0}};
+    case FT191:
+        return {3, 191, 41,
+                {0xd246820000000001ull, 0x936888270ceecbcdull, 0x453708aa3fbc8ddaull, 0},
+                0xd24681ffffffffffull,
+                {0x892c79fffffffffdull, 0x45c6678ad9339c96ull, 0x305ae60140ca5670ull, 0},
+                {0x6c25128031d873e2ull, 0xf71a3697a97ffdceull, 0x07ef71ae547daef9ull, 0},
+                {0xecd905456df2b092ull, 0x53ce189f0df0a05aull, 0x3f6e6da556ed31d9ull, 0}};
+    default:
+        return {4, 255, 41,
+                {0x02a4f20000000001ull, 0xef73c79086595f30ull, 0xfda9df04b9575969ull, 0x663c799b6e4d2900ull},
+                0x02a4f1ffffffffffull,
+                {0xfab61bfffffffffeull, 0x211870def34d419full, 0x04ac41f68d514d2cull, 0x33870cc92365adfeull},
+                {0xcf06aad260ab9990ull, 0x12f0d8856156a683ull, 0x5da77ded73588e21ull, 0x38725a1646845639ull},
+                {0x9c745ae52a496067ull, 0x95ee9a4091329682ull, 0x854a3ee53365b80eull, 0x16edffae79969e76ull}};
+    }
+}
+
+// Compile-time field description: P(i) etc. are constexpr calls that fold to
+// immediates inside fully unrolled loops.
+template <int FID>
+struct Field {
+    static constexpr int LIMBS = field_consts(FID).limbs;
+    static constexpr int NUM_BITS = field_consts(FID).num_bits;
+    static constexpr int TWO_ADICITY = field_consts(FID).two_adicity;
+    using E = Fe<LIMBS>;
+
+    __host__ __device__ static constexpr uint64_t P(int i) { return field_consts(FID).p[i]; }
+    __host__ __device__ static constexpr uint64_t INV() { return field_consts(FID).inv; }
+    __host__ __device__ static constexpr uint64_t RMODP(int i) { return field_consts(FID).r[i]; }
+
+    __device__ __forceinline__ static E zero() {
+        E r;
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) r.v[i] = 0;
+        return r;
+    }
+    __device__ __forceinline__ static E one() {
+        E r;
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) r.v[i] = RMODP(i);
+        return r;
+    }
+    __device__ __forceinline__ static bool is_zero(const E &a) {
+        uint64_t o = 0;
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) o |= a.v[i];
+        return o == 0;
+    }
+
+    // a >= p ?
+    __device__ __forceinline__ static bool geq_p(const uint64_t *a) {
+        if constexpr (LIMBS == 1) {
+            return a[0] >= P(0);
+        } else {
+            // borrow of a - p
+            uint64_t borrow = 0;
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) {
+                uint64_t pi = P(i);
+                uint64_t d = a[i] - pi;
+                uint64_t b1 = a[i] < pi;
+                uint64_t b2 = d < borrow;
+                borrow = b1 | b2;
+            }
+            return borrow == 0;
+        }
+    }
+    __device__ __forceinline__ static void sub_p(uint64_t *a) {
+        uint64_t borrow = 0;
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) {
+            uint64_t pi = P(i);
+            uint64_t d = a[i] - pi;
+            uint64_t b1 = a[i] < pi;
+            uint64_t d2 = d - borrow;
+            uint64_t b2 = d < borrow;
+            a[i] = d2;
+            borrow = b1 | b2;
+        }
+    }
+
+    __device__ __forceinline__ static E add(const E &a, const E &b) {
+        E r;
+        if constexpr (LIMBS == 1) {
+            uint64_t s = a.v[0] + b.v[0];  // < 2^64: both < p < 2^63
+            r.v[0] = s >= P(0) ? s - P(0) : s;
+        } else {
+            uint64_t carry = 0;
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) {
+                uint64_t s = a.v[i] + b.v[i];
+                uint64_t c1 = s < a.v[i];
+                uint64_t s2 = s + carry;
+                uint64_t c2 = s2 < s;
+                r.v[i] = s2;
+                carry = c1 | c2;
+            }
+            // top bit of every modulus is clear (2p < R): no carry out
+            if (geq_p(r.v)) sub_p(r.v);
+        }
+        return r;
+    }
+
+    __device__ __forceinline__ static E sub(const E &a, const E &b) {
+        E r;
+        if constexpr (LIMBS == 1) {
+            uint64_t d = a.v[0] - b.v[0];
+            r.v[0] = a.v[0] < b.v[0] ? d + P(0) : d;
+        } else {
+            uint64_t borrow = 0;
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) {
+                uint64_t d = a.v[i] - b.v[i];
+                uint64_t b1 = a.v[i] < b.v[i];
+                uint64_t d2 = d - borrow;
+                uint64_t b2 = d < borrow;
+                r.v[i] = d2;
+                borrow = b1 | b2;
+            }
+            if (borrow) {
+                uint64_t carry = 0;
+#pragma unroll
+                for (int i = 0; i < LIMBS; i++) {
+                    uint64_t s = r.v[i] + P(i);
+                    uint64_t c1 = s < r.v[i];
+                    uint64_t s2 = s + carry;
+                    uint64_t c2 = s2 < s;
+                    r.v[i] = s2;
+                    carry = c1 | c2;
+                }
+            }
+        }
+        return r;
+    }
+
+    // Montgomery product a*b*R^-1 mod p, fully reduced.
+    __device__ __forceinline__ static E mul(const E &a, const E &b) {
+        E r;
+        if constexpr (LIMBS == 1) {
+            uint64_t lo = a.v[0] * b.v[0];
+            uint64_t hi = __umul64hi(a.v[0], b.v[0]);
+            uint64_t m = lo * INV();
+            uint64_t mp_hi = __umul64hi(m, P(0));
+            // lo + low64(m*p) == 0 mod 2^64: carry out iff lo != 0
+            uint64_t t = hi + mp_hi + (lo != 0);
+            r.v[0] = t >= P(0) ? t - P(0) : t;
+        } else {
+            // coarsely integrated operand scanning over 64-bit limbs
+            uint64_t t[LIMBS + 2];
+#pragma unroll
+            for (int i = 0; i < LIMBS + 2; i++) t[i] = 0;
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) {
+                unsigned __int128 c = 0;
+#pragma unroll
+                for (int j = 0; j < LIMBS; j++) {
+                    c += (unsigned __int128)a.v[j] * b.v[i] + t[j];
+                    t[j] = (uint64_t)c;
+                    c >>= 64;
+                }
+                c += t[LIMBS];
+                t[LIMBS] = (uint64_t)c;
+                t[LIMBS + 1] = (uint64_t)(c >> 64);
+                uint64_t m = t[0] * INV();
+                c = (unsigned __int128)m * P(0) + t[0];
+                c >>= 64;
+#pragma unroll
+                for (int j = 1; j < LIMBS; j++) {
+                    c += (unsigned __int128)m * P(j) + t[j];
+                    t[j - 1] = (uint64_t)c;
+                    c >>= 64;
+                }
+                c += t[LIMBS];
+                t[LIMBS - 1] = (uint64_t)c;
+                t[LIMBS] = t[LIMBS + 1] + (uint64_t)(c >> 64);
+            }
+            // a, b < p < R/2  =>  t < 2p < R: t[LIMBS] == 0
+            if (geq_p(t)) sub_p(t);
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) r.v[i] = t[i];
+        }
+        return r;
+    }
+
+    // canonical value (PrimeField::to_repr limbs): a * R^-1 mod p
+    __device__ __forceinline__ static E to_canon(const E &a) {
+        if constexpr (LIMBS == 1) {
+            E r;
+            uint64_t lo = a.v[0];
+            uint64_t m = lo * INV();
+            uint64_t t = __umul64hi(m, P(0)) + (lo != 0);
+            r.v[0] = t >= P(0) ? t - P(0) : t;
+            return r;
+        } else {
+            E o = zero();
+            o.v[0] = 1;
+            return mul(a, o);
+        }
+    }
+
+    __device__ static E pow(E base, uint64_t e) {
+        E acc = one();
+        while (e) {
+            if (e & 1) acc = mul(acc, base);
+            base = mul(base, base);
+            e >>= 1;
+        }
+        return acc;
+    }
+};
+
+// 16-byte / 32-byte vector loads and stores of one element (global memory is AoS).
+template <int L>
+__device__ __forceinline__ Fe<L> ld_fe(const uint64_t *p) {
+    Fe<L> r;
+    if constexpr (L == 1) {
+        r.v[0] = p[0];
+    } else if constexpr (L == 2) {
+        ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p);
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else if constexpr (L == 4) {
+        ulonglong2 t0 = reinterpret_cast<const ulonglong2 *>(p)[0];
+        ulonglong2 t1 = reinterpret_cast<const ulonglong2 *>(p)[1];
+        r.v[0] = t0.x; r.v[1] = t0.y; r.v[2] = t1.x; r.v[3] = t1.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; i++) r.v[i] = p[i];
+    }
+    return r;
+}
+
+template <int L>
+__device__ __forceinline__ void st_fe(uint64_t *p, const Fe<L> &a) {
+    if constexpr (L == 1) {
+        p[0] = a.v[0];
+    } else if constexpr (L == 2) {
+        *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a.v[0], a.v[1]);
+    } else if constexpr (L == 4) {
+        reinterpret_cast<ulonglong2 *>(p)[0] = make_ulonglong2(a.v[0], a.v[1]);
+        reinterpret_cast<ulonglong2 *>(p)[1] = make_ulonglong2(a.v[2], a.v[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; i++) p[i] = a.v[i];
+    }
+}
+
+}  // namespace lcpc

@@ -1,0 +1,279 @@
+// Column-leaf hashing fused with the column gather, and the Merkle reduction.
+//
+// Leaf j = BLAKE3(0^32 || repr(M[0][j]) || ... || repr(M[n_rows-1][j])) with repr = the
+// canonical little-endian bytes of the element (lcpc-2d/src/lib.rs:736-775, FieldHash
+// :35-59); internal node = BLAKE3(left || right) (:777-815); tree array
+// [np2 leaves | np2/2 | ... | root] with all-zero padding leaves (:685-695, :720-734).
+//
+// B200 mapping: the matrix stays row-major.  One thread owns one (column, BLAKE3 chunk)
+// pair: adjacent threads read adjacent columns of the same row, so the strided "column
+// gather" is a sequence of fully coalesced row-segment loads, and the de-Montgomery
+// reduction happens in registers on the way into the message block.  BLAKE3's own chunk
+// tree gives a second grid dimension (1024-byte chunks are independent), which is what
+// fills 148 SMs when n_cols alone is only 2^16; a second small kernel folds the chunk
+// chaining values per column.  Merkle levels are reduced 9 at a time inside one CTA.
+#include "lcpc_blake3.cuh"
+#include "lcpc_field.cuh"
+#include "lcpc_kernels.h"
+
+namespace lcpc {
+
+// ------------------------------------------------------------------ leaf hashing
+
+// Message words of BLAKE3 block `B` (global block index over the column's byte stream)
+// for column `col`.  Stream = 8 zero words, then 2L words per row.
+template <int FID>
+__device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t *__restrict__ mat, size_t n_rows,
+                                                 size_t row_stride, size_t col, uint64_t B) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    constexpr int WPE = 2 * L;                  // 32-bit words per element
+    constexpr int K = (8 + WPE - 1) / WPE;      // virtual zero elements covering the prefix
+    constexpr int O = WPE * K - 8;              // word offset of the prefix inside them
+    constexpr int NE = (16 + WPE - 1) / WPE + 1;  // elements a block can touch (upper bound)
+    // virtual word index of m[0]
+    const uint64_t vw0 = 16 * B + O;
+    const uint64_t ve0 = vw0 / WPE;
+    const int sw0 = (int)(vw0 % WPE);
+    if constexpr (16 % WPE == 0 && O == 0) {
+        // whole elements per block (L = 1, 2, 4)
+        constexpr int EPB = 16 / WPE;
+#pragma unroll
+        for (int e = 0; e < EPB; e++) {
+            const int64_t row = (int64_t)(ve0 + e) - K;
+            E c = F::zero();
+            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)row * row_stride + col) * L));
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                m[e * WPE + 2 * l] = (uint32_t)c.v[l];
+                m[e * WPE + 2 * l + 1] = (uint32_t)(c.v[l] >> 32);
+            }
+        }
+    } else {
+        // elements straddle blocks (L = 3): three phases of sw0, resolved by a switch so
+        // that every message index stays a compile-time constant
+        uint32_t w[NE * WPE];
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            const int64_t row = (int64_t)(ve0 + e) - K;
+            E c = F::zero();
+            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)row * row_stride + col) * L));
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                w[e * WPE + 2 * l] = (uint32_t)c.v[l];
+                w[e * WPE + 2 * l + 1] = (uint32_t)(c.v[l] >> 32);
+            }
+        }
+        switch (sw0) {
+        case 0:
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = w[i];
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = w[i + 2];
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = w[i + 4];
+            break;
+        }
+    }
+}
+
+// One thread per (column, chunk): chaining value of that chunk, or the leaf itself when
+// the whole message is a single chunk.
+template <int FID>
+__global__ void __launch_bounds__(128)
+k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
+              const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks, uint32_t *__restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    const size_t col = col_idx ? (size_t)col_idx[j] : j;
+    for (uint64_t c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+        const uint64_t chunk_bytes = (c + 1 == n_chunks) ? total_bytes - c * b3::CHUNK_BYTES : b3::CHUNK_BYTES;
+        const uint32_t nb = (uint32_t)((chunk_bytes + b3::BLOCK_BYTES - 1) / b3::BLOCK_BYTES);
+        uint32_t cv[8];
+        b3::set_iv(cv);
+        for (uint32_t b = 0; b < nb; b++) {
+            uint32_t m[16];
+            load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b);
+            uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
+            uint32_t len = b3::BLOCK_BYTES;
+            if (b + 1 == nb) {
+                flags |= b3::CHUNK_END;
+                if (n_chunks == 1) flags |= b3::ROOT;
+                len = (uint32_t)(chunk_bytes - (uint64_t)b * b3::BLOCK_BYTES);
+            }
+            b3::compress(cv, m, n_chunks == 1 ? 0 : c, len, flags);
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(out + (c * n_cols + j) * 8);
+        o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+        o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    }
+}
+
+// One thread per column: BLAKE3 tree over the column's chunk chaining values
+// (left subtree = largest power of two of chunks strictly below the total).
+__global__ void __launch_bounds__(128)
+k_hash_merge(const uint32_t *__restrict__ cvs, size_t n_cols, uint64_t n_chunks, uint32_t *__restrict__ leaves) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    uint32_t stack[40][8];
+    int sp = 0;
+    uint32_t cv[8];
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const uint4 *in = reinterpret_cast<const uint4 *>(cvs + (c * n_cols + j) * 8);
+        uint4 a = in[0], b = in[1];
+        cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w;
+        cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
+        if (c + 1 == n_chunks) break;
+        uint64_t total = c + 1;
+        while ((total & 1) == 0) {
+            sp--;
+            b3::parent_cv(stack[sp], cv, 0, cv);
+            total >>= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) stack[sp][i] = cv[i];
+        sp++;
+    }
+    while (sp > 0) {
+        sp--;
+        b3::parent_cv(stack[sp], cv, sp == 0 ? b3::ROOT : 0u, cv);
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(leaves + j * 8);
+    o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+static uint64_t leaf_bytes(int fid, size_t n_rows) { return 32 + (uint64_t)n_rows * 8 * field_consts(fid).limbs; }
+static uint64_t leaf_chunks(int fid, size_t n_rows) {
+    return (leaf_bytes(fid, n_rows) + b3::CHUNK_BYTES - 1) / b3::CHUNK_BYTES;
+}
+
+size_t hash_scratch_bytes(int fid, size_t n_rows, size_t n_cols) {
+    uint64_t nc = leaf_chunks(fid, n_rows);
+    return nc <= 1 ? 0 : (size_t)(nc * n_cols * 32);
+}
+
+template <int FID>
+static cudaError_t hash_columns_t(const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols,
+                                  const uint64_t *d_col_idx, uint8_t *d_leaves, uint8_t *d_cv_scratch,
+                                  const Launch &lc) {
+    if (n_cols == 0) return cudaSuccess;
+    const uint64_t total = leaf_bytes(FID, n_rows), nc = leaf_chunks(FID, n_rows);
+    const unsigned gx = (unsigned)((n_cols + 127) / 128);
+    const unsigned gy = (unsigned)(nc < 65535 ? nc : 65535);
+    uint32_t *out = nc == 1 ? reinterpret_cast<uint32_t *>(d_leaves) : reinterpret_cast<uint32_t *>(d_cv_scratch);
+    lc.begin("k_hash_chunks");
+    k_hash_chunks<FID><<<dim3(gx, gy), 128, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_col_idx, total, nc, out);
+    lc.end();
+    if (nc > 1) {
+        lc.begin("k_hash_merge");
+        k_hash_merge<<<gx, 128, 0, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cv_scratch), n_cols, nc,
+                                        reinterpret_cast<uint32_t *>(d_leaves));
+        lc.end();
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t hash_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols,
+                         const uint64_t *d_col_idx, uint8_t *d_leaves, uint8_t *d_cv_scratch, const Launch &lc) {
+    switch (fid) {
+    case FT63: return hash_columns_t<FT63>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
+    case FT127: return hash_columns_t<FT127>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
+    case FT191: return hash_columns_t<FT191>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
+    case FT255: return hash_columns_t<FT255>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------ Merkle tree
+
+constexpr int MERKLE_TILE = 512;  // input digests per CTA (256 threads)
+
+// Reduces up to 9 levels of the tree over a tile of `MERKLE_TILE` inputs in shared memory.
+// level_in points at a full level of n_in digests; the following levels are contiguous
+// after it in the flat array (lib.rs:784-789 split_at_mut layout).
+__global__ void __launch_bounds__(256) k_merkle_levels(uint8_t *level_in, size_t n_in, int n_levels) {
+    __shared__ uint32_t buf[2][MERKLE_TILE][8];
+    const size_t tile0 = (size_t)blockIdx.x * MERKLE_TILE;
+    const size_t tile_n = n_in - tile0 < MERKLE_TILE ? n_in - tile0 : MERKLE_TILE;
+    const uint4 *in = reinterpret_cast<const uint4 *>(level_in + tile0 * 32);
+    for (size_t i = threadIdx.x; i < tile_n * 2; i += blockDim.x) reinterpret_cast<uint4 *>(&buf[0][0][0])[i] = in[i];
+    __syncthreads();
+    uint8_t *level_out = level_in + n_in * 32;
+    size_t level_n = n_in / 2;   // digests in the output level (whole tree)
+    size_t cur = tile_n;         // digests in this tile at the current level
+    size_t out0 = tile0 / 2;
+    int src = 0;
+    for (int l = 0; l < n_levels; l++) {
+        const size_t n_out = cur / 2;
+        for (size_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+            uint32_t o[8];
+            b3::hash_pair(buf[src][2 * i], buf[src][2 * i + 1], o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) buf[src ^ 1][i][k] = o[k];
+            uint4 *g = reinterpret_cast<uint4 *>(level_out + (out0 + i) * 32);
+            g[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            g[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        __syncthreads();
+        src ^= 1;
+        cur = n_out;
+        level_out += level_n * 32;
+        level_n /= 2;
+        out0 /= 2;
+    }
+}
+
+cudaError_t merkle_tree(uint8_t *d_hashes, size_t n_leaves, const Launch &lc) {
+    uint8_t *level = d_hashes;
+    size_t n_in = n_leaves;
+    while (n_in > 1) {
+        int levels = 0;
+        size_t tile = n_in < (size_t)MERKLE_TILE ? n_in : (size_t)MERKLE_TILE;
+        while (((size_t)1 << levels) < tile) levels++;
+        unsigned blocks = (unsigned)((n_in + MERKLE_TILE - 1) / MERKLE_TILE);
+        lc.begin("k_merkle_levels");
+        k_merkle_levels<<<blocks, 256, 0, lc.s>>>(level, n_in, levels);
+        lc.end();
+        for (int l = 0; l < levels; l++) {
+            level += n_in * 32;
+            n_in /= 2;
+        }
+    }
+    return cudaGetLastError();
+}
+
+// paths[i][l] = level_l[(col >> l) ^ 1]   (open_column, lib.rs:836-851)
+__global__ void k_gather_paths(const uint8_t *__restrict__ hashes, size_t np2, int depth, const uint64_t *__restrict__ cols,
+                               size_t n, uint8_t *__restrict__ paths) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (size_t)depth) return;
+    const size_t i = t / depth;
+    const int l = (int)(t % depth);
+    // offset of level l: sum_{k<l} np2 >> k = 2*np2 - (np2 >> (l-1)) for l >= 1
+    const size_t off = l == 0 ? 0 : 2 * np2 - (np2 >> (l - 1));
+    const size_t node = ((size_t)cols[i] >> l) ^ 1;
+    const uint4 *srcp = reinterpret_cast<const uint4 *>(hashes + (off + node) * 32);
+    uint4 *dstp = reinterpret_cast<uint4 *>(paths + t * 32);
+    dstp[0] = srcp[0];
+    dstp[1] = srcp[1];
+}
+
+cudaError_t gather_paths(const uint8_t *d_hashes, size_t np2, const uint64_t *d_cols, size_t n, uint8_t *d_paths,
+                         const Launch &lc) {
+    int depth = 0;
+    while (((size_t)1 << depth) < np2) depth++;
+    if (n == 0 || depth == 0) return cudaSuccess;
+    size_t total = n * (size_t)depth;
+    lc.begin("k_gather_paths");
+    k_gather_paths<<<(unsigned)((total + 255) / 256), 256, 0, lc.s>>>(d_hashes, np2, depth, d_cols, n, d_paths);
+    lc.end();
+    return cudaGetLastError();
+}
+
+}  // namespace lcpc

@@ -1,0 +1,110 @@
+// Internal launcher interface between the CUDA kernels (lcpc_*.cu) and the C ABI
+// (lcpc_api.cu).  Everything takes raw device pointers and a stream; `launches`
+// counts kernels enqueued.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+namespace lcpc {
+
+constexpr int MAX_LIMBS = 4;
+
+// Per-kernel device timing (CUDA events around every launch), off unless enabled on the
+// context; bench.py reads it to get the dominant kernel's duration inside the timed step.
+struct KernelTimer;
+void timer_begin(KernelTimer *t, const char *name, cudaStream_t s);
+void timer_end(KernelTimer *t, cudaStream_t s);
+
+// Where and how a launcher enqueues: stream, launch counter, optional timer.
+struct Launch {
+    cudaStream_t s;
+    uint64_t *count;
+    KernelTimer *timer;
+    void begin(const char *name) const {
+        if (timer) timer_begin(timer, name, s);
+    }
+    void end() const {
+        ++*count;
+        if (timer) timer_end(timer, s);
+    }
+};
+
+// w16^e, e = 0..7 (Montgomery), passed to NTT kernels by value (constant bank).
+struct SmallTwRaw {
+    uint64_t w[8][MAX_LIMBS];
+};
+
+struct NttPass {
+    int kind;        // 0 = strided register-radix pass over global memory, 1 = shared-memory block pass
+    int bits;        // radix bits R (kind 0) or block bits LB (kind 1)
+    int log_sub;     // log2 of the sub-transform size this pass starts from
+    size_t tw_off;   // element offset of this pass's twiddle table in d_tw
+};
+
+struct NttPlan {
+    int fid = 0;
+    int log_n = 0;
+    size_t n = 0;
+    std::vector<NttPass> passes;
+    uint64_t *d_tw = nullptr;  // all twiddle tables, device
+    size_t tw_elems = 0;
+    SmallTwRaw stw{};
+};
+
+// Builds twiddle tables for a 2^log_n-point transform.  root_mont: LIMBS words (host), or
+// nullptr for ROOT_OF_UNITY^(2^(S-log_n)).
+cudaError_t ntt_plan_build(NttPlan &plan, int fid, int log_n, const uint64_t *root_mont, const Launch &lc);
+void ntt_plan_free(NttPlan &plan);
+
+// n_rows independent transforms.  src rows have stride src_stride and src_valid leading
+// valid elements (the rest of each row reads as zero); dst rows have stride n.
+// src == dst (with src_stride == n) is the in-place case.
+cudaError_t ntt_encode(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
+                       uint64_t *dst, size_t n_rows, const Launch &lc);
+
+// Column hashing.  d_col_idx == nullptr hashes columns [0, n_cols); otherwise column
+// d_col_idx[j] for j < n_cols.  d_cv_scratch needs hash_scratch_bytes().
+size_t hash_scratch_bytes(int fid, size_t n_rows, size_t n_cols);
+cudaError_t hash_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols,
+                         const uint64_t *d_col_idx, uint8_t *d_leaves, uint8_t *d_cv_scratch, const Launch &lc);
+
+cudaError_t merkle_tree(uint8_t *d_hashes, size_t n_leaves, const Launch &lc);
+
+// out[t][j] = sum_r tensors[t][r] * mat[r][j].  d_scratch needs fold_scratch_bytes().
+size_t fold_scratch_bytes(int fid, size_t n_rows, size_t width, size_t n_tensors);
+cudaError_t fold(int fid, const uint64_t *d_mat, size_t n_rows, size_t width, size_t row_stride,
+                 const uint64_t *d_tensors, size_t n_tensors, uint64_t *d_out, uint64_t *d_scratch,
+                 const Launch &lc);
+cudaError_t add_partials(int fid, const uint64_t *d_parts, size_t n_parts, size_t n, uint64_t *d_out,
+                         const Launch &lc);
+
+cudaError_t gather_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
+                           const uint64_t *d_cols, size_t n, uint64_t *d_out, const Launch &lc);
+// paths[i][l] = level_l[(cols[i] >> l) ^ 1], depth entries per column
+cudaError_t gather_paths(const uint8_t *d_hashes, size_t np2, const uint64_t *d_cols, size_t n, uint8_t *d_paths,
+                         const Launch &lc);
+
+cudaError_t pack_bytes7(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems, const Launch &lc);
+
+// Brakedown: matrices in CSR on the device (converted from the caller's CSC once).
+struct DevCsr {
+    size_t rows = 0, cols = 0, nnz = 0;
+    uint32_t *d_rowptr = nullptr;  // rows + 1
+    uint32_t *d_colidx = nullptr;  // nnz
+    uint64_t *d_data = nullptr;    // nnz * LIMBS
+};
+struct SdigPlan {
+    int fid = 0;
+    size_t n_per_row = 0, n_cols = 0;
+    std::vector<DevCsr> pre, post;
+};
+// rows of d_comm (stride n_cols) already hold the message in their first n_per_row entries.
+cudaError_t sdig_encode(const SdigPlan &plan, uint64_t *d_comm, size_t n_rows, uint64_t *d_tmp, const Launch &lc);
+size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows);
+// copy coeff rows (stride n_per_row) into the head of comm rows (stride n_cols), zero the rest
+cudaError_t widen_rows(int fid, const uint64_t *d_coeffs, size_t n_per_row, uint64_t *d_comm, size_t n_cols,
+                       size_t n_rows, const Launch &lc);
+
+}  // namespace lcpc

@@ -1,0 +1,65 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol include/lcpc_b200.h declares.  No compute call is made without a GPU --
+except to check that the product fails loudly (no CPU fallback) when there is none."""
+import ctypes as C
+
+import pytest
+
+from lcpc_proof_of_storage_b200 import _lib
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lcpc_b200.h but not exported"
+    # and the binding table covers the header exactly
+    assert sorted(_lib._SIGNATURES) == declared
+    assert lib.lcpc_abi_version() == 1
+
+
+def test_field_constants_match_reference_moduli():
+    lib = _lib.load()
+    moduli = {
+        0: 5102708120182849537,
+        1: 146823888364060453008360742206866194433,
+        2: 1697146272512170708389931801544665676545308500647389167617,
+        3: 46242760681095663677370860714659204618859642560429202607213929836750194081793,
+    }
+    gens = {0: 10, 1: 3, 2: 5, 3: 5}
+    for fid, p in moduli.items():
+        L = lib.lcpc_field_limbs(fid)
+        assert L == (p.bit_length() + 63) // 64
+        m = (C.c_uint64 * 4)()
+        one = (C.c_uint64 * 4)()
+        root = (C.c_uint64 * 4)()
+        s = C.c_int32()
+        nb = C.c_int32()
+        assert lib.lcpc_field_constants(fid, m, one, root, C.byref(s), C.byref(nb)) == 0
+        toint = lambda a: sum(int(a[i]) << (64 * i) for i in range(L))
+        R = 1 << (64 * L)
+        assert toint(m) == p and toint(one) == R % p and nb.value == p.bit_length()
+        t, S = p - 1, 0
+        while t % 2 == 0:
+            t //= 2
+            S += 1
+        assert s.value == S
+        assert toint(root) == pow(gens[fid], t, p) * R % p
+    assert lib.lcpc_field_limbs(7) == 0
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.lcpc_ctx_create(0, C.byref(h))
+    assert rc == -8  # LCPC_ERR_CUDA
+    assert b"no CUDA device" in lib.lcpc_last_error()
+    with pytest.raises(_lib.LcpcError):
+        from lcpc_proof_of_storage_b200 import Context
+
+        Context(0)
