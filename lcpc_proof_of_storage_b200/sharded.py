@@ -1,0 +1,223 @@
+"""One-process-per-GPU commitment: rows sharded for encoding, an all-to-all re-shards the
+encoded matrix to column blocks for hashing, every rank builds its Merkle subtree and rank 0
+joins the subtree roots (SURVEY.md section 8 e).
+
+The reference has no multi-process path; what is sharded here is the loop structure of
+lcpc-2d/src/lib.rs:651-700: `par_chunks_mut` over rows (:677-682) becomes the row shard,
+`hash_columns`' column recursion (:736-775) becomes the column shard, and the top
+log2(world) levels of `merkle_tree` (:777-815) are computed once on rank 0.  The result
+(root, tree, fold vectors, opened columns) is bit-identical to the single-GPU commit.
+
+`torch.distributed` carries the plumbing (NCCL over NVLink on GPUs; gloo in the CPU tests,
+where the numerical back end is injected by the test).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .lcpc2d import FIELD_LIMBS, LcColumn, LigeroEncoding, log2, next_pow2
+
+
+def row_partition(n_rows: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced row blocks: rank q owns rows [start, start + count)."""
+    base, rem = divmod(n_rows, world)
+    out, start = [], 0
+    for q in range(world):
+        cnt = base + (1 if q < rem else 0)
+        out.append((start, cnt))
+        start += cnt
+    return out
+
+
+class GpuOps:
+    """Numerical back end on the local GPU: the device-pointer entry points of the C ABI."""
+
+    def __init__(self, enc):
+        self.enc = enc
+        self.lib = _lib.load()
+        self.fid = enc.fid
+        self.L = FIELD_LIMBS[enc.fid]
+        self.device = torch.device("cuda", enc.ctx.device)
+
+    def encode(self, coeffs: torch.Tensor, n_rows: int) -> torch.Tensor:
+        comm = torch.empty(n_rows * self.enc.n_cols * self.L, dtype=torch.int64, device=self.device)
+        if n_rows:
+            _lib.check(self.lib.lcpc_dev_encode(self.enc.plan, coeffs.data_ptr(), n_rows, comm.data_ptr()))
+        return comm
+
+    def hash_columns(self, mat: torch.Tensor, n_rows: int, row_stride: int, n_cols: int, out: torch.Tensor) -> None:
+        _lib.check(self.lib.lcpc_dev_hash_columns(self.enc.ctx.handle, self.fid, mat.data_ptr(), n_rows, row_stride,
+                                                  n_cols, out.data_ptr()))
+
+    def merkle_tree(self, hashes: torch.Tensor, n_leaves: int) -> None:
+        _lib.check(self.lib.lcpc_dev_merkle_tree(self.enc.ctx.handle, hashes.data_ptr(), n_leaves))
+
+    def fold(self, mat: torch.Tensor, n_rows: int, width: int, row_stride: int, tensors: torch.Tensor,
+             n_tensors: int) -> torch.Tensor:
+        out = torch.zeros(n_tensors * width * self.L, dtype=torch.int64, device=self.device)
+        if n_rows:
+            _lib.check(self.lib.lcpc_dev_fold(self.enc.ctx.handle, self.fid, mat.data_ptr(), n_rows, width, row_stride,
+                                              tensors.data_ptr(), n_tensors, out.data_ptr()))
+        return out
+
+    def add_partials(self, parts: torch.Tensor, n_parts: int, n: int) -> torch.Tensor:
+        out = torch.empty(n * self.L, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.lcpc_dev_add_partials(self.enc.ctx.handle, self.fid, parts.data_ptr(), n_parts, n,
+                                                  out.data_ptr()))
+        return out
+
+
+class ShardedLigeroCommitter:
+    """Commit one (n_rows_total x n_per_row) coefficient matrix across the ranks of `group`.
+
+    Rank q passes its own row block (row_partition) to `commit`.  After it, every rank holds
+    its column block of the encoded matrix and the matching Merkle subtree; rank 0 also holds
+    the top of the tree and the root.
+    """
+
+    def __init__(self, enc, n_rows_total: int, group=None, ops=None):
+        self.enc = enc
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.ops = ops or GpuOps(enc)
+        self.L = FIELD_LIMBS[enc.fid]
+        self.n_rows = n_rows_total
+        self.n_per_row, self.n_cols = enc.n_per_row, enc.n_cols
+        self.np2 = next_pow2(self.n_cols)
+        if self.world & (self.world - 1) or self.world > self.np2:
+            raise ValueError("world size must be a power of two not exceeding the padded column count")
+        # the PADDED leaf range is sharded, so padding (all-zero) leaves fall in the last shards
+        self.cb = self.np2 // self.world
+        self.rows = row_partition(n_rows_total, self.world)
+        self.row0, self.rows_local = self.rows[self.rank]
+        self.col0 = self.rank * self.cb
+        self.cols_local = max(0, min(self.n_cols, self.col0 + self.cb) - self.col0)  # real columns in my block
+        self.coeffs_local: Optional[torch.Tensor] = None
+        self.comm_cols: Optional[torch.Tensor] = None   # [n_rows_total, cb, L]: my column block, all rows
+        self.subtree: Optional[torch.Tensor] = None     # [(2*cb-1)*32] uint8
+        self.top: Optional[torch.Tensor] = None         # rank 0: [(2*world-1)*32] uint8
+
+    # ------------------------------------------------------------------ commit
+    def commit(self, coeffs_local: torch.Tensor) -> None:
+        L, cb, W = self.L, self.cb, self.world
+        assert coeffs_local.numel() == self.rows_local * self.n_per_row * L
+        dev = coeffs_local.device
+        self.coeffs_local = coeffs_local
+        comm = self.ops.encode(coeffs_local, self.rows_local)  # [rows_local, n_cols, L]
+        # pack: one contiguous slab per destination rank = that rank's column block of my rows
+        if self.np2 != self.n_cols:
+            padded = torch.zeros(self.rows_local, self.np2, L, dtype=torch.int64, device=dev)
+            padded[:, :self.n_cols] = comm.view(self.rows_local, self.n_cols, L)
+            comm3 = padded
+        else:
+            comm3 = comm.view(self.rows_local, self.n_cols, L)
+        send = comm3.view(self.rows_local, W, cb * L).transpose(0, 1).contiguous()  # [W, rows_local, cb*L]
+        recv = torch.empty(self.n_rows * cb * L, dtype=torch.int64, device=dev)
+        in_splits = [self.rows_local * cb * L] * W
+        out_splits = [cnt * cb * L for (_, cnt) in self.rows]
+        if W > 1:
+            dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=self.group)
+        else:
+            recv = send.view(-1)
+        self.comm_cols = recv  # row-major [n_rows_total, cb, L] because row blocks arrive in rank order
+        # leaves of my column block + my subtree
+        self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
+        if self.cols_local:
+            self.ops.hash_columns(recv, self.n_rows, cb, self.cols_local, self.subtree)
+        self.ops.merkle_tree(self.subtree, cb)
+        # only the subtree roots travel
+        my_root = self.subtree[-32:].contiguous()
+        if W > 1:
+            gathered = [torch.empty(32, dtype=torch.uint8, device=dev) for _ in range(W)] if self.rank == 0 else None
+            dist.gather(my_root, gathered, dst=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+            if self.rank == 0:
+                self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
+                self.top[:W * 32] = torch.cat(gathered)
+                self.ops.merkle_tree(self.top, W)
+        else:
+            self.top = my_root.clone()
+
+    def root(self) -> bytes:
+        """LcCommit::get_root on rank 0."""
+        assert self.rank == 0 and self.top is not None
+        return bytes(self.top[-32:].cpu().numpy())
+
+    def gather_hashes(self) -> Optional[torch.Tensor]:
+        """The full flat tree `LcCommit.hashes` ([np2 | np2/2 | ... | 1] digests) on rank 0."""
+        W, cb = self.world, self.cb
+        dev = self.subtree.device
+        if W == 1:
+            return self.subtree.clone()
+        parts = [torch.empty_like(self.subtree) for _ in range(W)] if self.rank == 0 else None
+        dist.gather(self.subtree, parts, dst=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+        if self.rank != 0:
+            return None
+        out = torch.empty((2 * self.np2 - 1) * 32, dtype=torch.uint8, device=dev)
+        pos, sub_off, n = 0, 0, cb
+        while n >= 1:  # levels that live inside the subtrees
+            for q in range(W):
+                out[pos:pos + n * 32] = parts[q][sub_off:sub_off + n * 32]
+                pos += n * 32
+            sub_off += n * 32
+            n //= 2
+        out[pos:] = self.top[W * 32:]  # levels above the subtree roots
+        return out
+
+    # ------------------------------------------------------------------ fold (prove)
+    def fold(self, tensors: torch.Tensor) -> torch.Tensor:
+        """collapse_columns over the unencoded coefficients for a batch of tensors
+        ([n_tensors, n_rows_total, L] on every rank): partial sums over the local rows, an
+        all-gather of the partials, and a local modular sum (NCCL has no mod-p reduction)."""
+        L = self.L
+        n_t = tensors.numel() // (self.n_rows * L)
+        t3 = tensors.view(n_t, self.n_rows, L)
+        local_t = t3[:, self.row0:self.row0 + self.rows_local].contiguous()
+        part = self.ops.fold(self.coeffs_local, self.rows_local, self.n_per_row, self.n_per_row, local_t, n_t)
+        if self.world == 1:
+            return part
+        allp = torch.empty(self.world * part.numel(), dtype=torch.int64, device=part.device)
+        dist.all_gather_into_tensor(allp, part, group=self.group)
+        return self.ops.add_partials(allp, self.world, n_t * self.n_per_row)
+
+    # ------------------------------------------------------------------ open
+    def open_columns(self, cols: Sequence[int]) -> Optional[List[LcColumn]]:
+        """open_column for each index; the column values come from the rank owning that column
+        block, the path from the gathered tree.  Result on rank 0 (None elsewhere)."""
+        import numpy as np
+
+        L, cb = self.L, self.cb
+        for c in cols:
+            if not 0 <= c < self.n_cols:
+                from .lcpc2d import ProverError
+
+                raise ProverError("ColumnNumber", "bad column number")
+        mine = [c for c in cols if c // cb == self.rank]
+        m3 = self.comm_cols.view(self.n_rows, cb, L)
+        vals = torch.stack([m3[:, c - self.col0] for c in mine]) if mine else torch.empty(0, self.n_rows, L, dtype=torch.int64,
+                                                                                             device=self.comm_cols.device)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (mine, vals.cpu().numpy().view(np.uint64)), group=self.group)
+        hashes = self.gather_hashes()
+        if self.rank != 0:
+            return None
+        h = hashes.cpu().numpy().reshape(-1, 32)
+        by_col = {}
+        for cols_q, vals_q in gathered:
+            for c, v in zip(cols_q, vals_q):
+                by_col[c] = v
+        out = []
+        depth = log2(self.n_cols)
+        for c in cols:
+            path, off, n, idx = [], 0, self.np2, c
+            for _ in range(depth):
+                path.append(h[off + (idx ^ 1)])
+                off += n
+                n //= 2
+                idx >>= 1
+            out.append(LcColumn(by_col[c], np.stack(path) if path else np.empty((0, 32), np.uint8)))
+        return out

@@ -1,0 +1,129 @@
+"""The N > 1 path on CPU: world_size-2 (and 4) gloo runs of ShardedLigeroCommitter with the
+numerical back end replaced by the oracle (injected by this test -- the product never imports
+oracle/).  Checks the host logic: row partition, all-to-all packing/splits, subtree + top-of-tree
+assembly, sharded fold and column opening, all bit-identical to the single-process commit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleOps:
+    """Same interface as sharded.GpuOps, computed by the CPU oracle (test double)."""
+
+    def __init__(self, O, fid, n_per_row, n_cols):
+        self.O, self.fid, self.n_per_row, self.n_cols = O, fid, n_per_row, n_cols
+        self.L = O.LIMBS[fid]
+
+    def _np(self, t):
+        return t.numpy().view(np.uint64)
+
+    def encode(self, coeffs, n_rows):
+        rows = np.zeros((n_rows, self.n_cols, self.L), dtype=np.uint64)
+        rows[:, :self.n_per_row] = self._np(coeffs).reshape(n_rows, self.n_per_row, self.L)
+        out = self.O.fft_io(self.fid, rows) if n_rows else rows
+        return torch.from_numpy(out.view(np.int64).reshape(-1).copy())
+
+    def hash_columns(self, mat, n_rows, row_stride, n_cols, out):
+        m = self._np(mat).reshape(n_rows, row_stride, self.L)[:, :n_cols]
+        out[:n_cols * 32] = torch.from_numpy(self.O.hash_columns(self.fid, np.ascontiguousarray(m)).reshape(-1))
+
+    def merkle_tree(self, hashes, n_leaves):
+        arr = hashes.numpy().reshape(-1, 32)
+        hashes[:] = torch.from_numpy(self.O.merkle_tree(arr[:n_leaves].copy()).reshape(-1))
+
+    def fold(self, mat, n_rows, width, row_stride, tensors, n_tensors):
+        m = self._np(mat).reshape(n_rows, row_stride, self.L)[:, :width]
+        t = self._np(tensors).reshape(n_tensors, n_rows, self.L)
+        out = np.stack([self.O.collapse_columns(self.fid, np.ascontiguousarray(m), t[i]) for i in range(n_tensors)])
+        return torch.from_numpy(out.view(np.int64).reshape(-1).copy())
+
+    def add_partials(self, parts, n_parts, n):
+        p = self._np(parts).reshape(n_parts, n, self.L)
+        acc = p[0].copy()
+        for k in range(1, n_parts):
+            acc = self.O.fe_add(self.fid, acc, p[k])
+        return torch.from_numpy(acc.view(np.int64).reshape(-1).copy())
+
+
+class _Enc:
+    def __init__(self, fid, n_per_row, n_cols):
+        self.fid, self.n_per_row, self.n_cols = fid, n_per_row, n_cols
+
+
+def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import lcpc_oracle as O
+        from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter, row_partition
+
+        O.set_threads(1)
+        L = O.LIMBS[fid]
+        n = n_rows * n_per_row - 5  # ragged last row
+        coeffs = np.zeros((n_rows * n_per_row, L), dtype=np.uint64)
+        coeffs[:n] = O.random_field_elements(fid, 99, n)
+        enc = _Enc(fid, n_per_row, n_cols)
+        sc = ShardedLigeroCommitter(enc, n_rows, None, ops=OracleOps(O, fid, n_per_row, n_cols))
+        r0, cnt = row_partition(n_rows, world)[rank]
+        local = coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt]
+        sc.commit(torch.from_numpy(np.ascontiguousarray(local).view(np.int64).reshape(-1)))
+        hashes = sc.gather_hashes()
+        tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, L)
+        folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()))
+        cols = [0, n_cols - 1, n_cols // 2, 3]
+        opened = sc.open_columns(cols)
+        if rank == 0:
+            exp = O.commit(coeffs[:n], O.LigeroEncoding(fid, n_per_row, n_cols))
+            ok = sc.root() == exp.get_root()
+            ok &= np.array_equal(hashes.numpy().reshape(-1, 32), exp.hashes)
+            f = folded.numpy().view(np.uint64).reshape(2, n_per_row, L)
+            for t in range(2):
+                ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+            for c, col in zip(cols, opened):
+                e = O.open_column(exp, c)
+                ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)
+                ok &= O.verify_column_path(fid, O.LcColumn(np.ascontiguousarray(col.col), np.ascontiguousarray(col.path)), c,
+                                           exp.get_root())
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,fid,n_rows,n_per_row,n_cols", [(2, 0, 7, 16, 32), (2, 3, 4, 8, 16), (4, 0, 10, 16, 64)])
+def test_sharded_commit_matches_single_process(oracle, world, fid, n_rows, n_per_row, n_cols):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fid, n_rows, n_per_row, n_cols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_row_partition():
+    from lcpc_proof_of_storage_b200.sharded import row_partition
+
+    assert row_partition(7, 2) == [(0, 4), (4, 3)]
+    assert row_partition(2, 4) == [(0, 1), (1, 1), (2, 0), (2, 0)]
+    assert row_partition(512, 8) == [(64 * i, 64) for i in range(8)]
