@@ -59,12 +59,22 @@ typedef enum {
     LCPC_ERR_DIMS = -6,          /* the assert!s at lib.rs:659-661 / dims_ok      */
     LCPC_ERR_INVALID_ARG = -7,   /* null pointer, unknown field, ...              */
     LCPC_ERR_CUDA = -8,          /* CUDA runtime failure or no device             */
-    LCPC_ERR_NOMEM = -9          /* device or host allocation failed              */
+    LCPC_ERR_NOMEM = -9,         /* device or host allocation failed              */
+    /* lcpc_2d::VerifierError (lib.rs:139-167), returned by lcpc_verify */
+    LCPC_VERR_NUM_COL_OPENS = -20, /* VerifierError::NumColOpens  */
+    LCPC_VERR_COLUMN_PATH = -21,   /* VerifierError::ColumnPath   */
+    LCPC_VERR_COLUMN_EVAL = -22,   /* VerifierError::ColumnEval   */
+    LCPC_VERR_COLUMN_DEGREE = -23, /* VerifierError::ColumnDegree */
+    LCPC_VERR_OUTER_TENSOR = -24,  /* VerifierError::OuterTensor  */
+    LCPC_VERR_INNER_TENSOR = -25,  /* VerifierError::InnerTensor  */
+    LCPC_VERR_ENCODING_DIMS = -26, /* VerifierError::EncodingDims */
+    LCPC_VERR_ENCODE = -27         /* VerifierError::Encode(E::Err) */
 } lcpc_status;
 
 typedef struct lcpc_ctx lcpc_ctx;       /* one device + stream                      */
 typedef struct lcpc_plan lcpc_plan;     /* one encoding instance (an `E: LcEncoding`) */
 typedef struct lcpc_commit lcpc_commit; /* a device-resident LcCommit               */
+typedef struct lcpc_transcript lcpc_transcript; /* a merlin::Transcript (host)         */
 
 /* sprs::CsMat<F> in CSC storage, as lcpc-brakedown-pc keeps its pre/postcodes
  * (lcpc-brakedown-pc/src/matgen.rs:187): indptr[cols+1], indices[nnz] = row numbers,
@@ -180,6 +190,65 @@ int32_t lcpc_open_columns_host(lcpc_commit *c, const uint64_t *cols, size_t n, u
 
 /* Leaf digests of selected columns only (CommitRequestType::Leaves, lcpc_online.rs:144-190). */
 int32_t lcpc_leaves_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint8_t *leaves_out);
+
+/* ---- prove / verify ---------------------------------------------------------------- */
+
+/* merlin::Transcript (merlin 2.0: STROBE-128 over Keccak-f[1600]); host-side, no device
+ * needed.  new = Transcript::new(label); the other two are append_message and
+ * challenge_bytes (call sites lcpc-2d/src/lib.rs:49, 901, 934, 1057, 1104). */
+int32_t lcpc_transcript_new(const uint8_t *label, size_t label_len, lcpc_transcript **out);
+int32_t lcpc_transcript_clone(const lcpc_transcript *t, lcpc_transcript **out);
+int32_t lcpc_transcript_append_message(lcpc_transcript *t, const uint8_t *label, size_t label_len,
+                                       const uint8_t *msg, size_t msg_len);
+int32_t lcpc_transcript_challenge_bytes(lcpc_transcript *t, const uint8_t *label, size_t label_len,
+                                        uint8_t *dest, size_t dest_len);
+void lcpc_transcript_free(lcpc_transcript *t);
+
+/* Challenge expansion as prove/verify do it (host-side): n x F::random from
+ * ChaCha20Rng::from_seed(key) (lib.rs:1058-1062), and n x Uniform(0, n_cols) column
+ * indices, with replacement (lib.rs:1105-1110). */
+int32_t lcpc_random_field_vec(int32_t field, const uint8_t key[32], uint64_t *out, size_t n);
+int32_t lcpc_random_columns(const uint8_t key[32], uint64_t n_cols, uint64_t *out, size_t n);
+
+/* LcCommit::prove (lib.rs:319 -> prove :1034-1123).  n_degree_tests / n_col_opens are the
+ * encoding's get_n_degree_tests() / get_n_col_opens().  Outputs (host):
+ *   p_eval_out    n_per_row elements                       = LcEvalProof.p_eval
+ *   p_random_out  n_degree_tests * n_per_row elements      = LcEvalProof.p_random_vec
+ *   col_idx_out   nullable; the n_col_opens sampled column numbers
+ *   columns_out   n_col_opens * n_rows elements            = LcEvalProof.columns[i].col
+ *   paths_out     n_col_opens * log2(np2) * 32 bytes       = LcEvalProof.columns[i].path
+ * LCPC_ERR_OUTER_TENSOR when outer_len != n_rows. */
+int32_t lcpc_prove(lcpc_commit *c, const uint64_t *outer_tensor, size_t outer_len, size_t n_degree_tests,
+                   size_t n_col_opens, lcpc_transcript *tr, uint64_t *p_eval_out, uint64_t *p_random_out,
+                   uint64_t *col_idx_out, uint64_t *columns_out, uint8_t *paths_out);
+
+/* LcEvalProof::verify (lib.rs:547 -> verify :862-982).  The proof is passed flat:
+ * p_eval (n_per_row), p_random (n_p_random vectors of n_per_row), columns (n_columns x
+ * n_rows), paths (n_columns x path_len digests), proof_n_cols = LcEvalProof.n_cols.
+ * On success writes sum_j inner[j] * p_eval[j] (LIMBS words) to result_out; otherwise
+ * returns the LCPC_VERR_* code of the VerifierError variant the reference would raise. */
+int32_t lcpc_verify(lcpc_plan *plan, const uint8_t root[LCPC_DIGEST_BYTES], const uint64_t *outer_tensor,
+                    size_t outer_len, const uint64_t *inner_tensor, size_t inner_len, size_t proof_n_cols,
+                    const uint64_t *p_eval, size_t n_per_row, const uint64_t *p_random, size_t n_p_random,
+                    const uint64_t *columns, size_t n_rows, const uint8_t *paths, size_t path_len,
+                    size_t n_columns, size_t n_col_opens, size_t n_degree_tests, lcpc_transcript *tr,
+                    uint64_t *result_out);
+
+/* ---- Brakedown code generation (host-side) ------------------------------------------ */
+
+/* matgen::get_dims (lcpc-brakedown-pc/src/matgen.rs:56-111) for SdigCode<code> (1..6,
+ * codespec.rs:168-232): per level (n, m, d) = (columns, rows, non-zeros per column) of the
+ * precode and the postcode, 3 words each. */
+int32_t lcpc_sdig_get_dims(int32_t code, uint64_t n_per_row, int32_t field, uint64_t *pre_dims,
+                           uint64_t *post_dims, int32_t max_levels, int32_t *n_levels);
+/* matgen::generate for one level (matgen.rs:38-49, gen_code :114-188): fills CSC arrays
+ * (indptr[n+1], indices[n*d], data[n*d*LIMBS]) for the level's precode and postcode. */
+int32_t lcpc_sdig_gen_level(int32_t field, uint64_t seed, uint64_t level, const uint64_t pre_dim[3],
+                            const uint64_t post_dim[3], uint64_t *pre_indptr, uint64_t *pre_indices,
+                            uint64_t *pre_data, uint64_t *post_indptr, uint64_t *post_indices,
+                            uint64_t *post_data);
+/* SdigSpecification::dist (codespec.rs:40-44) */
+double lcpc_sdig_dist(int32_t code);
 
 /* ---- device-pointer building blocks (sharded / device-resident pipelines) --------- */
 

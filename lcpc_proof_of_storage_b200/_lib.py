@@ -23,6 +23,11 @@ STATUS_NAMES = {
     0: "Ok", -1: "TooBig", -2: "Encode", -3: "Commit", -4: "ColumnNumber", -5: "OuterTensor",
     -6: "Dims", -7: "InvalidArg", -8: "Cuda", -9: "NoMem",
 }
+VERIFIER_ERRORS = {
+    -20: "NumColOpens", -21: "ColumnPath", -22: "ColumnEval", -23: "ColumnDegree", -24: "OuterTensor",
+    -25: "InnerTensor", -26: "EncodingDims", -27: "Encode",
+}
+STATUS_NAMES.update({k: "Verifier" + v for k, v in VERIFIER_ERRORS.items()})
 
 
 class LcpcCsc(C.Structure):
@@ -67,6 +72,21 @@ _SIGNATURES = {
     "lcpc_fold_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lcpc_open_columns_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "lcpc_leaves_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lcpc_transcript_new": (C.c_int32, [C.c_char_p, C.c_size_t, vpp]),
+    "lcpc_transcript_clone": (C.c_int32, [C.c_void_p, vpp]),
+    "lcpc_transcript_append_message": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+    "lcpc_transcript_challenge_bytes": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "lcpc_transcript_free": (None, [C.c_void_p]),
+    "lcpc_random_field_vec": (C.c_int32, [C.c_int32, C.c_char_p, C.c_void_p, C.c_size_t]),
+    "lcpc_random_columns": (C.c_int32, [C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "lcpc_prove": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lcpc_verify": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "lcpc_sdig_get_dims": (C.c_int32, [C.c_int32, C.c_uint64, C.c_int32, u64p, u64p, C.c_int32, C.POINTER(C.c_int32)]),
+    "lcpc_sdig_gen_level": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),
+    "lcpc_sdig_dist": (C.c_double, [C.c_int32]),
     "lcpc_dev_encode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lcpc_dev_hash_columns": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_merkle_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -1,44 +1,12 @@
 // C ABI of lcpc_b200 (see include/lcpc_b200.h for the contract and the reference
 // items each entry point replaces).  Handles own device memory; host buffers belong to
 // the caller.  No CPU fallback: without a CUDA device every call fails loudly.
-#include <atomic>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <vector>
-
-#include "../../include/lcpc_b200.h"
-#include "lcpc_field.cuh"
-#include "lcpc_kernels.h"
+#include "lcpc_handles.h"
 
 using namespace lcpc;
+using namespace lcpc::abi;
 
 namespace lcpc {
-// CUDA-event stopwatch around every kernel launch of a context (off by default).
-struct KernelTimer {
-    struct Rec {
-        const char *name;
-        cudaEvent_t a, b;
-    };
-    std::vector<Rec> recs;
-    std::vector<cudaEvent_t> pool;
-    cudaEvent_t get() {
-        cudaEvent_t e;
-        if (!pool.empty()) {
-            e = pool.back();
-            pool.pop_back();
-        } else {
-            cudaEventCreate(&e);
-        }
-        return e;
-    }
-    ~KernelTimer() {
-        for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-        for (auto e : pool) cudaEventDestroy(e);
-    }
-};
 void timer_begin(KernelTimer *t, const char *name, cudaStream_t s) {
     KernelTimer::Rec r{name, t->get(), t->get()};
     cudaEventRecord(r.a, s);
@@ -47,88 +15,29 @@ void timer_begin(KernelTimer *t, const char *name, cudaStream_t s) {
 void timer_end(KernelTimer *t, cudaStream_t s) {
     if (!t->recs.empty()) cudaEventRecord(t->recs.back().b, s);
 }
+namespace abi {
+std::string &last_error() {
+    thread_local std::string err;
+    return err;
+}
+}  // namespace abi
 }  // namespace lcpc
 
-struct lcpc_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    uint64_t launches = 0;
-    lcpc::KernelTimer *timer = nullptr;
-    std::string timing_report;
-    std::mutex mu;
-    std::atomic<int> refs{1};  // the creator + every live plan
-    lcpc::Launch lc() { return lcpc::Launch{stream, &launches, timer}; }
-};
-
-struct lcpc_plan {
-    lcpc_ctx *ctx = nullptr;
-    int kind = 0;  // 0 = Ligero (NTT), 1 = Brakedown (SpMV chain)
-    int fid = 0;
-    size_t n_per_row = 0, n_cols = 0;
-    NttPlan ntt;
-    SdigPlan sdig;
-    std::mutex mu;
-    std::atomic<int> refs{1};  // the creator + every live commit
-};
-
-struct lcpc_commit {
-    lcpc_plan *plan = nullptr;
-    size_t n_rows = 0, n_per_row = 0, n_cols = 0, np2 = 0;
-    uint64_t *d_coeffs = nullptr;
-    uint64_t *d_comm = nullptr;
-    uint8_t *d_hashes = nullptr;
-    std::mutex mu;
-};
+// encode rows already resident: ligero reads d_coeffs (stride n_per_row), brakedown widens first
+int32_t lcpc::abi::encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm) {
+    lcpc_ctx *ctx = plan->ctx;
+    if (plan->kind == 0) {
+        CU(ntt_encode(plan->ntt, d_coeffs, plan->n_per_row, plan->n_per_row, d_comm, n_rows, ctx->lc()));
+    } else {
+        CU(widen_rows(plan->fid, d_coeffs, plan->n_per_row, d_comm, plan->n_cols, n_rows, ctx->lc()));
+        DevBuf tmp;
+        CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * limbs_of(plan->fid) * sizeof(uint64_t), ctx->stream));
+        CU(sdig_encode(plan->sdig, d_comm, n_rows, tmp.as<uint64_t>(), ctx->lc()));
+    }
+    return LCPC_OK;
+}
 
 namespace {
-
-thread_local std::string g_err = "";
-
-int32_t fail(int32_t code, const std::string &msg) {
-    g_err = msg;
-    return code;
-}
-
-int32_t cuda_fail(cudaError_t e, const char *what) {
-    cudaGetLastError();  // clear sticky-less errors
-    return fail(e == cudaErrorMemoryAllocation ? LCPC_ERR_NOMEM : LCPC_ERR_CUDA,
-                std::string(what) + ": " + cudaGetErrorString(e));
-}
-
-#define CU(call)                                        \
-    do {                                                \
-        cudaError_t e__ = (call);                       \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-    } while (0)
-
-bool valid_field(int32_t f) { return f >= 0 && f < N_FIELDS; }
-int limbs_of(int fid) { return field_consts(fid).limbs; }
-
-size_t next_pow2(size_t v) {
-    size_t p = 1;
-    while (p < v) {
-        if (p > (SIZE_MAX >> 1)) return 0;
-        p <<= 1;
-    }
-    return p;
-}
-
-// stream-ordered device buffer that frees itself
-struct DevBuf {
-    void *p = nullptr;
-    cudaStream_t s = nullptr;
-    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
-        s = stream;
-        if (bytes == 0) bytes = 8;
-        return cudaMallocAsync(&p, bytes, stream);
-    }
-    ~DevBuf() {
-        if (p) cudaFreeAsync(p, s);
-    }
-    template <class T>
-    T *as() { return reinterpret_cast<T *>(p); }
-};
 
 void free_csr(DevCsr &m) {
     if (m.d_rowptr) cudaFree(m.d_rowptr);
@@ -167,20 +76,6 @@ int32_t upload_csr(const lcpc_csc &a, int L, DevCsr &out) {
     if (nnz) {
         CU(cudaMemcpy(out.d_colidx, colidx.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(out.d_data, data.data(), nnz * L * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    }
-    return LCPC_OK;
-}
-
-// encode rows already resident: ligero reads d_coeffs (stride n_per_row), brakedown widens first
-int32_t encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm) {
-    lcpc_ctx *ctx = plan->ctx;
-    if (plan->kind == 0) {
-        CU(ntt_encode(plan->ntt, d_coeffs, plan->n_per_row, plan->n_per_row, d_comm, n_rows, ctx->lc()));
-    } else {
-        CU(widen_rows(plan->fid, d_coeffs, plan->n_per_row, d_comm, plan->n_cols, n_rows, ctx->lc()));
-        DevBuf tmp;
-        CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * limbs_of(plan->fid) * sizeof(uint64_t), ctx->stream));
-        CU(sdig_encode(plan->sdig, d_comm, n_rows, tmp.as<uint64_t>(), ctx->lc()));
     }
     return LCPC_OK;
 }
@@ -273,7 +168,7 @@ extern "C" {
 
 uint32_t lcpc_abi_version(void) { return 1; }
 
-const char *lcpc_last_error(void) { return g_err.c_str(); }
+const char *lcpc_last_error(void) { return last_error().c_str(); }
 
 int32_t lcpc_field_limbs(int32_t field) { return valid_field(field) ? limbs_of(field) : 0; }
 

@@ -1,0 +1,129 @@
+// Internal handle definitions and small helpers shared by the C-ABI translation units
+// (lcpc_api.cu, lcpc_scheme.cu).  Not part of the public interface.
+#pragma once
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lcpc_b200.h"
+#include "lcpc_field.cuh"
+#include "lcpc_kernels.h"
+
+namespace lcpc {
+// CUDA-event stopwatch around every kernel launch of a context (off by default).
+struct KernelTimer {
+    struct Rec {
+        const char *name;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!pool.empty()) {
+            e = pool.back();
+            pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+    ~KernelTimer() {
+        for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+}  // namespace lcpc
+
+struct lcpc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    lcpc::KernelTimer *timer = nullptr;
+    std::string timing_report;
+    std::mutex mu;
+    std::atomic<int> refs{1};  // the creator + every live plan
+    lcpc::Launch lc() { return lcpc::Launch{stream, &launches, timer}; }
+};
+
+struct lcpc_plan {
+    lcpc_ctx *ctx = nullptr;
+    int kind = 0;  // 0 = Ligero (NTT), 1 = Brakedown (SpMV chain)
+    int fid = 0;
+    size_t n_per_row = 0, n_cols = 0;
+    lcpc::NttPlan ntt;
+    lcpc::SdigPlan sdig;
+    std::mutex mu;
+    std::atomic<int> refs{1};  // the creator + every live commit
+};
+
+struct lcpc_commit {
+    lcpc_plan *plan = nullptr;
+    size_t n_rows = 0, n_per_row = 0, n_cols = 0, np2 = 0;
+    uint64_t *d_coeffs = nullptr;
+    uint64_t *d_comm = nullptr;
+    uint8_t *d_hashes = nullptr;
+    std::mutex mu;
+};
+
+
+namespace lcpc {
+namespace abi {
+
+std::string &last_error();
+
+inline int32_t fail(int32_t code, const std::string &msg) {
+    last_error() = msg;
+    return code;
+}
+
+inline int32_t cuda_fail(cudaError_t e, const char *what) {
+    cudaGetLastError();  // clear the non-sticky error state
+    return fail(e == cudaErrorMemoryAllocation ? LCPC_ERR_NOMEM : LCPC_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                                          \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return ::lcpc::abi::cuda_fail(e__, #call); \
+    } while (0)
+
+inline bool valid_field(int32_t f) { return f >= 0 && f < N_FIELDS; }
+inline int limbs_of(int fid) { return field_consts(fid).limbs; }
+
+inline size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) {
+        if (p > (SIZE_MAX >> 1)) return 0;
+        p <<= 1;
+    }
+    return p;
+}
+
+// stream-ordered device buffer that frees itself
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        if (bytes == 0) bytes = 8;
+        return cudaMallocAsync(&p, bytes, stream);
+    }
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    template <class T>
+    T *as() { return reinterpret_cast<T *>(p); }
+};
+
+// encode rows already on the device (Ligero reads d_coeffs with stride n_per_row; Brakedown widens first)
+int32_t encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);
+
+}  // namespace abi
+}  // namespace lcpc

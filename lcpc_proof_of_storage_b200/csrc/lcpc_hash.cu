@@ -276,4 +276,43 @@ cudaError_t gather_paths(const uint8_t *d_hashes, size_t np2, const uint64_t *d_
     return cudaGetLastError();
 }
 
+// verify_column_path's climb (lib.rs:999-1011): from each leaf digest up its sibling path;
+// ok[i] = 1 when the recomputed root equals `root`.
+__global__ void k_verify_paths(const uint8_t *__restrict__ leaves, const uint8_t *__restrict__ paths, int depth,
+                               const uint64_t *__restrict__ cols, size_t n, const uint8_t *__restrict__ root,
+                               uint32_t *__restrict__ ok) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h[8], sib[8];
+    const uint32_t *lp = reinterpret_cast<const uint32_t *>(leaves + i * 32);
+#pragma unroll
+    for (int k = 0; k < 8; k++) h[k] = lp[k];
+    uint64_t col = cols[i];
+    for (int l = 0; l < depth; l++) {
+        const uint32_t *sp = reinterpret_cast<const uint32_t *>(paths + (i * (size_t)depth + l) * 32);
+#pragma unroll
+        for (int k = 0; k < 8; k++) sib[k] = sp[k];
+        uint32_t o[8];
+        if ((col & 1) == 0) b3::hash_pair(h, sib, o);
+        else b3::hash_pair(sib, h, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) h[k] = o[k];
+        col >>= 1;
+    }
+    const uint32_t *rp = reinterpret_cast<const uint32_t *>(root);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) diff |= h[k] ^ rp[k];
+    ok[i] = diff == 0 ? 1u : 0u;
+}
+
+cudaError_t verify_paths(const uint8_t *d_leaves, const uint8_t *d_paths, int depth, const uint64_t *d_cols, size_t n,
+                         const uint8_t *d_root, uint32_t *d_ok, const Launch &lc) {
+    if (n == 0) return cudaSuccess;
+    lc.begin("k_verify_paths");
+    k_verify_paths<<<(unsigned)((n + 63) / 64), 64, 0, lc.s>>>(d_leaves, d_paths, depth, d_cols, n, d_root, d_ok);
+    lc.end();
+    return cudaGetLastError();
+}
+
 }  // namespace lcpc

@@ -86,6 +86,13 @@ cudaError_t gather_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t
 cudaError_t gather_paths(const uint8_t *d_hashes, size_t np2, const uint64_t *d_cols, size_t n, uint8_t *d_paths,
                          const Launch &lc);
 
+// verifier / transcript helpers
+cudaError_t to_canon(int fid, const uint64_t *d_in, size_t n, uint64_t *d_out, const Launch &lc);
+cudaError_t column_dots(int fid, const uint64_t *d_cols, size_t n_rows, size_t n_open, const uint64_t *d_tensors,
+                        size_t n_tensors, uint64_t *d_out, const Launch &lc);
+cudaError_t verify_paths(const uint8_t *d_leaves, const uint8_t *d_paths, int depth, const uint64_t *d_cols, size_t n,
+                         const uint8_t *d_root, uint32_t *d_ok, const Launch &lc);
+
 cudaError_t pack_bytes7(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems, const Launch &lc);
 
 // Brakedown: matrices in CSR on the device (converted from the caller's CSC once).

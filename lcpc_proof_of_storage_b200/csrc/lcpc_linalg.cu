@@ -162,6 +162,69 @@ cudaError_t gather_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ verifier helpers
+
+// canonical (de-Montgomery) limbs of each element: what FieldHash::to_hash_repr feeds the
+// transcript (lcpc-2d/src/lib.rs:48-58)
+template <int FID>
+__global__ void k_to_canon(const uint64_t *__restrict__ in, size_t n, uint64_t *__restrict__ out) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_fe<L>(out + i * L, F::to_canon(ld_fe<L>(in + i * L)));
+}
+
+template <int FID>
+static cudaError_t to_canon_t(const uint64_t *d_in, size_t n, uint64_t *d_out, const Launch &lc) {
+    if (n == 0) return cudaSuccess;
+    lc.begin("k_to_canon");
+    k_to_canon<FID><<<(unsigned)((n + 255) / 256), 256, 0, lc.s>>>(d_in, n, d_out);
+    lc.end();
+    return cudaGetLastError();
+}
+
+cudaError_t to_canon(int fid, const uint64_t *d_in, size_t n, uint64_t *d_out, const Launch &lc) {
+#define CALL(F) to_canon_t<F>(d_in, n, d_out, lc)
+    LCPC_FIELD_SWITCH(fid, CALL)
+#undef CALL
+}
+
+// verify_column_value for every (opened column i, tensor t) pair (lib.rs:1015-1030):
+// out[i*n_tensors + t] = sum_r tensors[t][r] * cols[i][r]
+template <int FID>
+__global__ void k_column_dots(const uint64_t *__restrict__ cols, size_t n_rows, size_t n_open,
+                              const uint64_t *__restrict__ tensors, size_t n_tensors, uint64_t *__restrict__ out) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_open * n_tensors) return;
+    const size_t i = idx / n_tensors, t = idx % n_tensors;
+    E acc = F::zero();
+    for (size_t r = 0; r < n_rows; r++)
+        acc = F::add(acc, F::mul(ld_fe<L>(tensors + (t * n_rows + r) * L), ld_fe<L>(cols + (i * n_rows + r) * L)));
+    st_fe<L>(out + idx * L, acc);
+}
+
+template <int FID>
+static cudaError_t column_dots_t(const uint64_t *d_cols, size_t n_rows, size_t n_open, const uint64_t *d_tensors,
+                                 size_t n_tensors, uint64_t *d_out, const Launch &lc) {
+    const size_t total = n_open * n_tensors;
+    if (total == 0) return cudaSuccess;
+    lc.begin("k_column_dots");
+    k_column_dots<FID><<<(unsigned)((total + 63) / 64), 64, 0, lc.s>>>(d_cols, n_rows, n_open, d_tensors, n_tensors, d_out);
+    lc.end();
+    return cudaGetLastError();
+}
+
+cudaError_t column_dots(int fid, const uint64_t *d_cols, size_t n_rows, size_t n_open, const uint64_t *d_tensors,
+                        size_t n_tensors, uint64_t *d_out, const Launch &lc) {
+#define CALL(F) column_dots_t<F>(d_cols, n_rows, n_open, d_tensors, n_tensors, d_out, lc)
+    LCPC_FIELD_SWITCH(fid, CALL)
+#undef CALL
+}
+
 // ------------------------------------------------------------------ 7-byte packing
 
 // element k = little-endian integer of bytes [7k, 7k+7), zero-extended; the value is

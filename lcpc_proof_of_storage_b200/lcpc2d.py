@@ -134,6 +134,39 @@ def default_context() -> Context:
     return _default_ctx
 
 
+class Transcript:
+    """merlin::Transcript (host-side; lcpc_transcript_* of the C ABI)."""
+
+    def __init__(self, label: bytes, _handle=None):
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = C.c_void_p()
+        check(_lib.load().lcpc_transcript_new(label, len(label), C.byref(h)))
+        self._h = h
+
+    def append_message(self, label: bytes, message: bytes) -> None:
+        check(_lib.load().lcpc_transcript_append_message(self._h, label, len(label), message, len(message)))
+
+    def challenge_bytes(self, label: bytes, n: int) -> bytes:
+        out = (C.c_uint8 * n)()
+        check(_lib.load().lcpc_transcript_challenge_bytes(self._h, label, len(label), out, n))
+        return bytes(out)
+
+    def clone(self) -> "Transcript":
+        h = C.c_void_p()
+        check(_lib.load().lcpc_transcript_clone(self._h, C.byref(h)))
+        return Transcript(b"", _handle=h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().lcpc_transcript_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
 class _Encoding:
     """Common part of the `LcEncoding` implementations (lib.rs:75-105)."""
 
@@ -303,6 +336,80 @@ class SdigEncoding(_Encoding):
         check(_lib.load().lcpc_plan_brakedown(self.ctx.handle, fid, self.n_per_row, self.n_cols, n, pre, post, C.byref(h)))
         self._plan = h
 
+    # -- construction from a seed, as the reference does (host-side generation) ---------------
+    @staticmethod
+    def generate(fid: int, n_per_row: int, seed: int, code: int = 3):
+        """matgen::generate::<Ft, SdigCode<code>>(n_per_row, seed) (matgen.rs:28-53)."""
+        lib = _lib.load()
+        L = FIELD_LIMBS[fid]
+        pre_d = np.zeros(3 * 64, dtype=np.uint64)
+        post_d = np.zeros(3 * 64, dtype=np.uint64)
+        n_levels = C.c_int32()
+        check(lib.lcpc_sdig_get_dims(code, n_per_row, fid, pre_d.ctypes.data_as(u64p), post_d.ctypes.data_as(u64p), 64,
+                                     C.byref(n_levels)))
+        pres, posts = [], []
+        for lvl in range(n_levels.value):
+            ni, mi, cn = (int(x) for x in pre_d[3 * lvl:3 * lvl + 3])
+            nip, mip, dn = (int(x) for x in post_d[3 * lvl:3 * lvl + 3])
+            a = CscMatrix(mi, ni, np.zeros(ni + 1, np.uint64), np.zeros(ni * cn, np.uint64), np.zeros((ni * cn, L), np.uint64))
+            b = CscMatrix(mip, nip, np.zeros(nip + 1, np.uint64), np.zeros(nip * dn, np.uint64), np.zeros((nip * dn, L), np.uint64))
+            pd = np.array([ni, mi, cn], dtype=np.uint64)
+            qd = np.array([nip, mip, dn], dtype=np.uint64)
+            p64 = lambda x: x.ctypes.data_as(u64p)
+            check(lib.lcpc_sdig_gen_level(fid, seed, lvl, p64(pd), p64(qd), p64(a.indptr), p64(a.indices), p64(a.data),
+                                          p64(b.indptr), p64(b.indices), p64(b.data)))
+            pres.append(a)
+            posts.append(b)
+        return pres, posts
+
+    @classmethod
+    def _n_col_opens(cls, code: int = 3) -> int:  # lib.rs:57-61
+        dist = float(_lib.load().lcpc_sdig_dist(code))
+        return int(math.ceil(-cls.LAMBDA / math.log2(1.0 - dist / 3.0)))
+
+    @classmethod
+    def _n_degree_tests(cls, fid: int, n_cols: int) -> int:  # lib.rs:64-66
+        return n_degree_tests(cls.LAMBDA, n_cols, FIELD_NUM_BITS[fid] - 1)
+
+    @classmethod
+    def _n_per_row_for_len(cls, fid: int, length: int, code: int = 3, ml: bool = False) -> int:
+        """lib.rs:69-123: new / new_ml / _new_from_np1."""
+        n_col_opens = cls._n_col_opens(code)
+        lncf = float(n_col_opens * length)
+        ndt = float(cls._n_degree_tests(fid, int(math.ceil(math.sqrt(lncf))) * 2))
+        np1 = int(math.ceil(math.sqrt(lncf / ndt)))
+        if ml:
+            np1 = next_pow2(np1)
+        np1 = min(np1, length)
+        nr1 = (length + np1 - 1) // np1
+        nd1 = cls._n_degree_tests(fid, np1 * 2)
+        np2 = np1 // 2
+        nr2 = (length + np2 - 1) // np2
+        nd2 = cls._n_degree_tests(fid, np2 * 2)
+        sz1 = n_col_opens * nr1 + (1 + nd1) * np1
+        sz2 = n_col_opens * nr2 + (1 + nd2) * np2
+        return np1 if sz1 < sz2 else np2
+
+    @classmethod
+    def new(cls, fid: int, length: int, seed: int, code: int = 3, ctx: Optional[Context] = None) -> "SdigEncoding":
+        """SdigEncodingS::new(len, seed) (lib.rs:93-100)."""
+        return cls.new_from_dims(fid, cls._n_per_row_for_len(fid, length, code), None, seed, code, ctx)
+
+    @classmethod
+    def new_ml(cls, fid: int, n_vars: int, seed: int, code: int = 3, ctx: Optional[Context] = None) -> "SdigEncoding":
+        """lib.rs:104-113."""
+        return cls.new_from_dims(fid, cls._n_per_row_for_len(fid, 1 << n_vars, code, ml=True), None, seed, code, ctx)
+
+    @classmethod
+    def new_from_dims(cls, fid: int, n_per_row: int, n_cols: Optional[int], seed: int, code: int = 3,
+                      ctx: Optional[Context] = None) -> "SdigEncoding":
+        """lib.rs:126-137."""
+        pre, post = cls.generate(fid, n_per_row, seed, code)
+        enc = cls(fid, pre, post, n_col_opens=cls._n_col_opens(code), ctx=ctx)
+        if n_cols is not None and n_cols != enc.n_cols:
+            raise AssertionError("assertion failed: n_cols == codeword_length(&precodes, &postcodes)")
+        return enc
+
     def dims_ok(self, n_per_row: int, n_cols: int) -> bool:  # :160-167
         return n_per_row < n_cols and n_per_row == self.n_per_row and n_cols == self.n_cols
 
@@ -333,6 +440,12 @@ class LcEvalProof:
 
     def get_n_per_row(self) -> int:
         return self.p_eval.shape[0]
+
+    def verify(self, root: bytes, outer_tensor: np.ndarray, inner_tensor: np.ndarray, enc: "_Encoding",
+               tr: "Transcript") -> np.ndarray:
+        """LcEvalProof::verify (lib.rs:547-556 -> :862-982): returns the evaluation (1, LIMBS) or raises
+        VerifierError with the reference's variant name."""
+        return verify(root, outer_tensor, inner_tensor, self, enc, tr)
 
 
 class LcCommit:
@@ -429,6 +542,10 @@ class LcCommit:
         _prover_call(_lib.load().lcpc_fold_host(self._h, 1 if encoded else 0, _ptr(tensors), tensors.shape[0], _ptr(out)))
         return out
 
+    def prove(self, outer_tensor: np.ndarray, enc: "_Encoding", tr: "Transcript") -> LcEvalProof:
+        """LcCommit::prove (lib.rs:319-326 -> :1034-1123)."""
+        return prove(self, outer_tensor, enc, tr)
+
     def open_columns(self, cols: Sequence[int], with_path: bool = True) -> List[LcColumn]:
         L = self.enc.limbs
         idx = np.ascontiguousarray(np.asarray(cols, dtype=np.uint64))
@@ -476,3 +593,54 @@ def collapse_columns(comm: LcCommit, tensor: np.ndarray) -> np.ndarray:
     if t.shape[0] != comm.n_rows:
         raise ProverError("OuterTensor", "bad outer tensor size")
     return comm.fold(t[None])[0]
+
+
+def prove(comm: LcCommit, outer_tensor: np.ndarray, enc: _Encoding, tr: Transcript) -> LcEvalProof:
+    """lib.rs:1034-1123.  check_comm (:1045) is structural here: the handle cannot be malformed."""
+    L = enc.limbs
+    if not enc.dims_ok(comm.n_per_row, comm.n_cols):
+        raise ProverError("Commit", "bad dimensions for commitment")
+    outer = _elems(outer_tensor, L)
+    n_dt, n_open = enc.get_n_degree_tests(), enc.get_n_col_opens()
+    depth = log2(comm.n_cols)
+    p_eval = np.empty((comm.n_per_row, L), dtype=np.uint64)
+    p_random = np.empty((n_dt, comm.n_per_row, L), dtype=np.uint64)
+    cols = np.empty((n_open, comm.n_rows, L), dtype=np.uint64)
+    paths = np.empty((n_open, depth, 32), dtype=np.uint8)
+    _prover_call(_lib.load().lcpc_prove(comm._h, _ptr(outer), outer.shape[0], n_dt, n_open, tr._h, _ptr(p_eval),
+                                        _ptr(p_random), None, _ptr(cols), _ptr(paths)))
+    return LcEvalProof(comm.n_cols, p_eval, [p_random[i] for i in range(n_dt)],
+                       [LcColumn(cols[i], paths[i]) for i in range(n_open)])
+
+
+def verify(root: bytes, outer_tensor: np.ndarray, inner_tensor: np.ndarray, proof: LcEvalProof, enc: _Encoding,
+           tr: Transcript) -> np.ndarray:
+    """lib.rs:862-982."""
+    from ._lib import VERIFIER_ERRORS
+
+    L = enc.limbs
+    outer, inner = _elems(outer_tensor, L), _elems(inner_tensor, L)
+    n_columns = len(proof.columns)
+    n_rows = proof.columns[0].col.shape[0] if n_columns else 0
+    path_len = proof.columns[0].path.shape[0] if n_columns else 0
+    for c in proof.columns:  # ragged proofs cannot be passed flat; the reference fails the affected column
+        if c.col.shape[0] != n_rows:
+            raise VerifierError("ColumnEval", "column eval invalid")
+        if c.path.shape[0] != path_len:
+            raise VerifierError("ColumnPath", "column path invalid")
+    columns = np.ascontiguousarray(np.stack([c.col for c in proof.columns])) if n_columns else np.empty((0, 0, L), np.uint64)
+    paths = np.ascontiguousarray(np.stack([c.path for c in proof.columns])) if n_columns else np.empty((0, 0, 32), np.uint8)
+    p_eval = _elems(proof.p_eval, L)
+    n_pr = len(proof.p_random_vec)
+    p_random = (np.ascontiguousarray(np.stack([_elems(v, L) for v in proof.p_random_vec]))
+                if n_pr else np.empty((0, p_eval.shape[0], L), np.uint64))
+    rootb = np.frombuffer(root, dtype=np.uint8).copy()
+    res = np.empty((1, L), dtype=np.uint64)
+    rc = _lib.load().lcpc_verify(enc.plan, _ptr(rootb), _ptr(outer), outer.shape[0], _ptr(inner), inner.shape[0],
+                                 proof.n_cols, _ptr(p_eval), p_eval.shape[0], _ptr(p_random), n_pr, _ptr(columns), n_rows,
+                                 _ptr(paths), path_len, n_columns, enc.get_n_col_opens(), enc.get_n_degree_tests(),
+                                 tr._h, _ptr(res))
+    if rc in VERIFIER_ERRORS:
+        raise VerifierError(VERIFIER_ERRORS[rc], _lib.load().lcpc_last_error().decode())
+    check(rc)
+    return res
