@@ -151,6 +151,7 @@ def run_reference(args, rank: int, world: int) -> None:
     from oracle import lcpc_oracle as O
 
     O.build()
+    O.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = O.max_threads()
     n_rows = ROWS_PER_GPU * max(1, args.gpus)
     # bounded sample: at most 512 rows of the same width per step (throughput per coefficient does
@@ -357,6 +358,7 @@ def main() -> None:
         from oracle import lcpc_oracle as O
 
         O.build()
+        O.set_threads(os.cpu_count() or 1)
         oenc = O.LigeroEncoding(FID, N_PER_ROW, N_COLS)
         sample_rows = ROWS_PER_GPU * (world if world <= 2 else 1)
         if world == 1 or world == 2:
