@@ -58,6 +58,85 @@ __host__ __device__ constexpr FieldConsts field_consts(int fid) {
     }
 }
 
+// ---- 63-bit field fast path ----------------------------------------------------------
+// p = 0x46d07600_00000001: low word 1, high word P_HI.  The Montgomery product is computed
+// column-wise with 32x32+64 -> 64 multiply-adds (IMAD.WIDE) only, so that carries propagate
+// inside the FMA pipe instead of through IADD3/ISETP/SEL chains on the ALU pipe (which is
+// what bound the first version of the NTT kernels, profiles/r01a_summary.md).
+// Multipliers that ptxas cannot see through (read from the constant bank): `mad.wide.u32 d, x, 1,
+// acc` would be strength-reduced to an IADD3/IADD3.X carry chain on the ALU pipe, and a literal
+// modulus word would be split into IMAD + IMAD.HI + 3-input IADD3; opaque, they stay single
+// IMAD.WIDE instructions whose 64-bit accumulate carries inside the FMA pipe.
+static __constant__ uint32_t LCPC_ONE = 1u;
+static __constant__ uint32_t LCPC_FT63_Q = 0xb92f8a00u;   // 2^32 - P_HI
+static __constant__ uint32_t LCPC_NEG1 = 0xffffffffu;
+
+namespace ft63 {
+constexpr uint64_t P = 0x46d0760000000001ull;
+constexpr uint32_t P_HI = 0x46d07600u;
+constexpr uint64_t REDC_C = ((uint64_t)P_HI << 32) + 1;  // added to columns 1 and 2 up front
+
+__device__ __forceinline__ uint64_t wmul(uint32_t a, uint32_t b) {
+    uint64_t d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t wmad(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+__device__ __forceinline__ uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+__device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+
+// x in [0, 2p) -> x mod p
+__device__ __forceinline__ uint64_t csub(uint64_t x) {
+    const uint64_t t = x - P;
+    return (int64_t)t < 0 ? x : t;  // x < p  <=>  x - p wraps to >= 2^64 - p > 2^63
+}
+
+// One Montgomery digit (2^-32) of the value  w + acc * 2^32  (w a 32-bit word, acc the 64 bits above
+// it, REDC_C already included in acc): with m = 2^32 - w (also for w = 0) the low word of
+// w + m*p is exactly 2^32, so the quotient is acc' = acc_orig + 1 + m*P_HI = acc + w*Q - w*2^32
+// (mod 2^64; the true value fits).  One IMAD.WIDE + one 32-bit IMAD, no carry flags.
+__device__ __forceinline__ uint64_t redc_digit(uint32_t w, uint64_t acc) {
+    const uint64_t u = wmad(w, LCPC_FT63_Q, acc);
+    return pack(lo32(u), hi32(u) + w * LCPC_NEG1);
+}
+
+// Montgomery reduction of col0 + (col1 - C)*2^32 + (col2 - C)*2^64 with C = REDC_C pre-added to
+// columns 1 and 2; columns are sums of 32x32 products, not carry-normalised.  Result in [0, p)
+// for inputs that are products of reduced elements.
+__device__ __forceinline__ uint64_t redc_cols(uint64_t col0, uint64_t col1, uint64_t col2) {
+    const uint32_t one = LCPC_ONE;
+    col1 = wmad(hi32(col0), one, col1);
+    const uint64_t u = redc_digit(lo32(col0), col1);
+    col2 = wmad(hi32(u), one, col2);
+    const uint64_t v = redc_digit(lo32(u), col2);
+    return csub(v);
+}
+
+// a*b*2^-64 mod p, a, b < p
+__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
+    const uint32_t a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    return redc_cols(wmul(a0, b0), wmad(a1, b0, wmad(a0, b1, REDC_C)), wmad(a1, b1, REDC_C));
+}
+// a*2^-64 mod p
+__device__ __forceinline__ uint64_t to_canon(uint64_t a) {
+    return redc_cols((uint64_t)lo32(a), (uint64_t)hi32(a) + REDC_C, REDC_C);
+}
+__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return csub(a + b); }
+__device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) {
+    const uint64_t d = a - b;
+    return a < b ? d + P : d;
+}
+}  // namespace ft63
+
 // Compile-time field description: P(i) etc. are constexpr calls that fold to
 // immediates inside fully unrolled loops.
 template <int FID>
@@ -176,17 +255,16 @@ struct Field {
         return r;
     }
 
+    // difference that is only consumed as the first operand of mul() (hook for lazy reduction)
+    __device__ __forceinline__ static E sub_for_mul(const E &a, const E &b) {
+        return sub(a, b);
+    }
+
     // Montgomery product a*b*R^-1 mod p, fully reduced.
     __device__ __forceinline__ static E mul(const E &a, const E &b) {
         E r;
         if constexpr (LIMBS == 1) {
-            uint64_t lo = a.v[0] * b.v[0];
-            uint64_t hi = __umul64hi(a.v[0], b.v[0]);
-            uint64_t m = lo * INV();
-            uint64_t mp_hi = __umul64hi(m, P(0));
-            // lo + low64(m*p) == 0 mod 2^64: carry out iff lo != 0
-            uint64_t t = hi + mp_hi + (lo != 0);
-            r.v[0] = t >= P(0) ? t - P(0) : t;
+            r.v[0] = ft63::mul(a.v[0], b.v[0]);
         } else {
             // coarsely integrated operand scanning over 64-bit limbs
             uint64_t t[LIMBS + 2];
@@ -229,10 +307,7 @@ struct Field {
     __device__ __forceinline__ static E to_canon(const E &a) {
         if constexpr (LIMBS == 1) {
             E r;
-            uint64_t lo = a.v[0];
-            uint64_t m = lo * INV();
-            uint64_t t = __umul64hi(m, P(0)) + (lo != 0);
-            r.v[0] = t >= P(0) ? t - P(0) : t;
+            r.v[0] = ft63::to_canon(a.v[0]);
             return r;
         } else {
             E o = zero();

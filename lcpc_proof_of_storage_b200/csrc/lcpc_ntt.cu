@@ -84,9 +84,8 @@ __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], c
             if ((j & gap) == 0) {
                 E a = x[j], b = x[j + gap];
                 x[j] = F::add(a, b);
-                E d = F::sub(a, b);
                 const int e16 = ((j & (gap - 1)) << t) << (4 - R);  // exponent of w16
-                x[j + gap] = (e16 == 0) ? d : F::mul(d, tw.w[e16]);
+                x[j + gap] = (e16 == 0) ? F::sub(a, b) : F::mul(F::sub_for_mul(a, b), tw.w[e16]);
             }
         }
     }
@@ -95,7 +94,7 @@ __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], c
 // ------------------------------------------------------------------ strided pass
 
 template <int FID, int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 1)
 k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows,
               int log_sub, const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
     using F = Field<FID>;
@@ -114,12 +113,17 @@ k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t
             x[m] = idx < src_valid ? ld_fe<L>(src + (row * src_stride + idx) * L) : F::zero();
         }
         radix_dif<FID, R>(x, stw);
+        {
+            E t[1 << R];
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+        }
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
             const size_t idx = base + ((size_t)m << log_n2);
-            E v = x[m];
-            if (m != 0) v = F::mul(v, ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
-            st_fe<L>(dst + (row * n + idx) * L, v);
+            st_fe<L>(dst + (row * n + idx) * L, x[m]);
         }
     }
 }
@@ -128,7 +132,7 @@ k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t
 
 __device__ __forceinline__ size_t sm_phys(size_t i) { return i + (i >> 4); }
 
-template <int FID, int R>
+template <int FID, int R, bool TW>
 __device__ __forceinline__ void block_substep(uint64_t *sm, size_t plane, int LB, int log_sub,
                                               const uint64_t *__restrict__ tw, const SmallTw<FID> &stw) {
     using F = Field<FID>;
@@ -147,19 +151,32 @@ __device__ __forceinline__ void block_substep(uint64_t *sm, size_t plane, int LB
             for (int l = 0; l < L; l++) x[m].v[l] = sm[l * plane + p];
         }
         radix_dif<FID, R>(x, stw);
+        if constexpr (TW) {
+            // all pass twiddles of this group in flight together (one exposed L1/L2 latency, not 2^R - 1)
+            E t[1 << R];
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+        }
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
-            E v = x[m];
-            if (m != 0 && log_n2 > 0) v = F::mul(v, ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
             const size_t p = sm_phys(base + ((size_t)m << log_n2));
 #pragma unroll
-            for (int l = 0; l < L; l++) sm[l * plane + p] = v.v[l];
+            for (int l = 0; l < L; l++) sm[l * plane + p] = x[m].v[l];
         }
     }
 }
 
+template <int FID, int R>
+__device__ __forceinline__ void block_substep_any(uint64_t *sm, size_t plane, int LB, int log_sub,
+                                                  const uint64_t *__restrict__ tw, const SmallTw<FID> &stw) {
+    if (log_sub - R > 0) block_substep<FID, R, true>(sm, plane, LB, log_sub, tw, stw);
+    else block_substep<FID, R, false>(sm, plane, LB, log_sub, tw, stw);
+}
+
 template <int FID, int RMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 1)
 k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows, int LB,
             const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
     using F = Field<FID>;
@@ -184,13 +201,13 @@ k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *
             const int R = log_sub < RMAX ? log_sub : RMAX;
             const uint64_t *t = tw + tw_off * L;
             if (R == 4) {
-                if constexpr (RMAX >= 4) block_substep<FID, 4>(sm, plane, LB, log_sub, t, stw);
+                if constexpr (RMAX >= 4) block_substep_any<FID, 4>(sm, plane, LB, log_sub, t, stw);
             } else if (R == 3) {
-                block_substep<FID, 3>(sm, plane, LB, log_sub, t, stw);
+                block_substep_any<FID, 3>(sm, plane, LB, log_sub, t, stw);
             } else if (R == 2) {
-                block_substep<FID, 2>(sm, plane, LB, log_sub, t, stw);
+                block_substep_any<FID, 2>(sm, plane, LB, log_sub, t, stw);
             } else {
-                block_substep<FID, 1>(sm, plane, LB, log_sub, t, stw);
+                block_substep_any<FID, 1>(sm, plane, LB, log_sub, t, stw);
             }
             if (log_sub - R > 0) tw_off += (size_t)1 << log_sub;
             log_sub -= R;
