@@ -98,6 +98,9 @@ void ctx_unref(lcpc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (auto e : ctx->events) cudaEventDestroy(e);
     delete ctx->timer;
     delete ctx;
 }
@@ -145,6 +148,61 @@ int32_t commit_finish(lcpc_plan *plan, lcpc_commit *c, uint64_t *coeffs_out, uin
         CU(cudaMemcpyAsync(comm_out, c->d_comm, c->n_rows * c->n_cols * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (hashes_out)
         CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+// Host commit with the three stages overlapped over row chunks: H2D of coefficient rows (stream
+// s_in), encode on the compute stream, D2H of encoded rows (stream s_out).  Column hashing needs
+// every row, so it runs once after the last chunk is encoded, while earlier chunks are still
+// draining over PCIe.  Bit-identical to the unchunked path: rows are independent.
+int32_t commit_host_pipelined(lcpc_plan *plan, lcpc_commit *c, const uint64_t *h_coeffs, size_t n_coeffs,
+                              uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out) {
+    lcpc_ctx *ctx = plan->ctx;
+    const int L = limbs_of(plan->fid);
+    const size_t wbytes = (size_t)L * sizeof(uint64_t);
+    const size_t n_rows = c->n_rows, npr = c->n_per_row, n_cols = c->n_cols;
+    if (!ctx->s_in) CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    CU(cudaMallocAsync((void **)&c->d_coeffs, n_rows * npr * wbytes, ctx->stream));
+    CU(cudaMallocAsync((void **)&c->d_comm, n_rows * n_cols * wbytes, ctx->stream));
+    CU(cudaMallocAsync((void **)&c->d_hashes, (2 * c->np2 - 1) * 32, ctx->stream));
+    cudaEvent_t ready = ctx->event(0);
+    CU(cudaEventRecord(ready, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->s_in, ready, 0));
+    CU(cudaStreamWaitEvent(ctx->s_out, ready, 0));
+    size_t n_chunks = n_rows < 8 ? n_rows : 8;
+    const size_t rows_per = (n_rows + n_chunks - 1) / n_chunks;
+    n_chunks = (n_rows + rows_per - 1) / rows_per;
+    for (size_t k = 0; k < n_chunks; k++) {
+        const size_t r0 = k * rows_per, nr = r0 + rows_per <= n_rows ? rows_per : n_rows - r0;
+        const size_t e0 = r0 * npr, e1 = (r0 + nr) * npr;  // element range of this chunk's coefficient rows
+        const size_t have = n_coeffs > e0 ? (n_coeffs < e1 ? n_coeffs - e0 : e1 - e0) : 0;
+        if (have)
+            CU(cudaMemcpyAsync(c->d_coeffs + e0 * L, h_coeffs + e0 * L, have * wbytes, cudaMemcpyHostToDevice, ctx->s_in));
+        if (have < e1 - e0)  // lib.rs:665-674: zero fill of the ragged tail
+            CU(cudaMemsetAsync(c->d_coeffs + (e0 + have) * L, 0, (e1 - e0 - have) * wbytes, ctx->s_in));
+        cudaEvent_t in_done = ctx->event(1 + 2 * k), enc_done = ctx->event(2 + 2 * k);
+        CU(cudaEventRecord(in_done, ctx->s_in));
+        CU(cudaStreamWaitEvent(ctx->stream, in_done, 0));
+        int32_t rc = encode_dev(plan, c->d_coeffs + e0 * L, nr, c->d_comm + r0 * n_cols * L);
+        if (rc != LCPC_OK) return rc;
+        CU(cudaEventRecord(enc_done, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->s_out, enc_done, 0));
+        if (comm_out)
+            CU(cudaMemcpyAsync(comm_out + r0 * n_cols * L, c->d_comm + r0 * n_cols * L, nr * n_cols * wbytes,
+                               cudaMemcpyDeviceToHost, ctx->s_out));
+        if (coeffs_out)
+            CU(cudaMemcpyAsync(coeffs_out + e0 * L, c->d_coeffs + e0 * L, (e1 - e0) * wbytes, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    int32_t rc = merkleize_dev(ctx, plan->fid, c->d_comm, n_rows, n_cols, c->np2, c->d_hashes);
+    if (rc != LCPC_OK) return rc;
+    if (hashes_out)
+        CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    // everything is joined on the compute stream before returning
+    cudaEvent_t out_done = ctx->event(1 + 2 * n_chunks);
+    CU(cudaEventRecord(out_done, ctx->s_out));
+    CU(cudaStreamWaitEvent(ctx->stream, out_done, 0));
     CU(cudaStreamSynchronize(ctx->stream));
     return LCPC_OK;
 }
@@ -409,6 +467,9 @@ int32_t lcpc_commit_host(lcpc_plan *plan, const uint64_t *coeffs, size_t n_coeff
     const size_t wbytes = (size_t)limbs_of(plan->fid) * sizeof(uint64_t);
     auto body = [&]() -> int32_t {
         const size_t padded = c->n_rows * c->n_per_row;
+        // large commits: overlap PCIe in, kernels and PCIe out over row chunks
+        if (c->n_rows >= 8 && c->n_rows * c->n_cols * wbytes >= ((size_t)8 << 20))
+            return commit_host_pipelined(plan, c, coeffs, n_coeffs, coeffs_out, comm_out, hashes_out);
         CU(cudaMallocAsync((void **)&c->d_coeffs, padded * wbytes, ctx->stream));
         CU(cudaMemcpyAsync(c->d_coeffs, coeffs, n_coeffs * wbytes, cudaMemcpyHostToDevice, ctx->stream));
         if (padded > n_coeffs)  // lib.rs:665-674: the last row is zero-filled

@@ -48,7 +48,19 @@ struct lcpc_ctx {
     std::string timing_report;
     std::mutex mu;
     std::atomic<int> refs{1};  // the creator + every live plan
+    // copy engines for the pipelined host commit: H2D and D2H run on their own streams so that
+    // both PCIe directions and the kernels overlap
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> events;
     lcpc::Launch lc() { return lcpc::Launch{stream, &launches, timer}; }
+    cudaEvent_t event(size_t i) {
+        while (events.size() <= i) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            events.push_back(e);
+        }
+        return events[i];
+    }
 };
 
 struct lcpc_plan {

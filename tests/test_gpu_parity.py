@@ -81,6 +81,10 @@ COMMIT_CASES = [
     (2, 90 * 16, 16, 32),
     (3, 5000, 100, 256),
     (3, 70 * 64, 64, 128),
+    # large enough for the chunk-pipelined host path (>= 8 rows and >= 8 MiB encoded), ragged tail
+    (0, 300 * 2048 - 777, 2048, 4096),
+    (0, 9 * 65536 - 1, 65536, 131072),
+    (3, 75 * 2048 - 5, 2048, 4096),
 ]
 
 
