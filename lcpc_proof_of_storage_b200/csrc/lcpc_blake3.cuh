@@ -42,15 +42,25 @@ __host__ __device__ constexpr Schedule make_schedule() {
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
+// c + d on the FMA pipe (IMAD with a multiplier of 1 read from the constant bank, which ptxas
+// cannot strength-reduce back to an IADD3): the G function is otherwise 100 % ALU-pipe work
+// (3-input adds, xors, funnel shifts, byte permutes), and that pipe is what bounds the kernel.
+static __constant__ uint32_t LCPC_B3_ONE = 1u;
+__device__ __forceinline__ uint32_t add_fma(uint32_t c, uint32_t d, uint32_t one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(d), "r"(one), "r"(c));
+    return r;
+}
+
 #define LCPC_B3_G(a, b, c, d, mx, my) \
     do {                              \
-        a = a + b + (mx);             \
+        a = add_fma(add_fma(a, b, one), (mx), one); \
         d = __byte_perm(d ^ a, 0, 0x1032); \
-        c = c + d;                    \
+        c = add_fma(c, d, one);       \
         b = rotr(b ^ c, 12);          \
-        a = a + b + (my);             \
+        a = add_fma(add_fma(a, b, one), (my), one); \
         d = __byte_perm(d ^ a, 0, 0x0321); \
-        c = c + d;                    \
+        c = add_fma(c, d, one);       \
         b = rotr(b ^ c, 7);           \
     } while (0)
 
@@ -58,6 +68,7 @@ __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshi
 __device__ __forceinline__ void compress(uint32_t cv[8], const uint32_t m[16], uint64_t counter,
                                          uint32_t block_len, uint32_t flags) {
     constexpr Schedule SC = make_schedule();
+    const uint32_t one = LCPC_B3_ONE;
     uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = cv[3], s4 = cv[4], s5 = cv[5], s6 = cv[6], s7 = cv[7];
     uint32_t s8 = LCPC_B3_IV0, s9 = LCPC_B3_IV1, s10 = LCPC_B3_IV2, s11 = LCPC_B3_IV3;
     uint32_t s12 = (uint32_t)counter, s13 = (uint32_t)(counter >> 32), s14 = block_len, s15 = flags;

@@ -82,8 +82,43 @@ __device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t 
     }
 }
 
+// Raw (Montgomery) elements of BLAKE3 block `B` for fields whose elements do not straddle blocks
+// (LIMBS 1, 2, 4): rows outside [0, n_rows) -- the 32-byte zero prefix and the tail -- read as zero.
+template <int FID>
+struct BlockElems {
+    static constexpr int L = Field<FID>::LIMBS;
+    static constexpr int WPE = 2 * L;
+    static constexpr bool WHOLE = (16 % WPE == 0);
+    static constexpr int EPB = WHOLE ? 16 / WPE : 1;
+    static constexpr int K = 8 / WPE;  // prefix length in elements
+    typename Field<FID>::E e[EPB];
+
+    __device__ __forceinline__ void load(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t col,
+                                         uint64_t B) {
+#pragma unroll
+        for (int i = 0; i < EPB; i++) {
+            const int64_t row = (int64_t)(B * EPB + i) - K;
+            e[i] = (row >= 0 && (uint64_t)row < n_rows) ? ld_fe<L>(mat + ((size_t)row * row_stride + col) * L)
+                                                        : Field<FID>::zero();
+        }
+    }
+    // canonical little-endian words of the block (the de-Montgomery reduction of zero is zero)
+    __device__ __forceinline__ void words(uint32_t m[16]) const {
+#pragma unroll
+        for (int i = 0; i < EPB; i++) {
+            const typename Field<FID>::E c = Field<FID>::to_canon(e[i]);
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                m[i * WPE + 2 * l] = (uint32_t)c.v[l];
+                m[i * WPE + 2 * l + 1] = (uint32_t)(c.v[l] >> 32);
+            }
+        }
+    }
+};
+
 // One thread per (column, chunk): chaining value of that chunk, or the leaf itself when
-// the whole message is a single chunk.
+// the whole message is a single chunk.  The loads of block b+1 are issued before block b is
+// compressed, so the L2/HBM latency hides behind ~900 ALU instructions.
 template <int FID>
 __global__ void __launch_bounds__(128)
 k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
@@ -96,9 +131,16 @@ k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride
         const uint32_t nb = (uint32_t)((chunk_bytes + b3::BLOCK_BYTES - 1) / b3::BLOCK_BYTES);
         uint32_t cv[8];
         b3::set_iv(cv);
+        BlockElems<FID> cur, nxt;
+        if constexpr (BlockElems<FID>::WHOLE) cur.load(mat, n_rows, row_stride, col, c * 16);
         for (uint32_t b = 0; b < nb; b++) {
             uint32_t m[16];
-            load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b);
+            if constexpr (BlockElems<FID>::WHOLE) {
+                if (b + 1 < nb) nxt.load(mat, n_rows, row_stride, col, c * 16 + b + 1);
+                cur.words(m);
+            } else {
+                load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b);
+            }
             uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
             uint32_t len = b3::BLOCK_BYTES;
             if (b + 1 == nb) {
@@ -107,6 +149,7 @@ k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride
                 len = (uint32_t)(chunk_bytes - (uint64_t)b * b3::BLOCK_BYTES);
             }
             b3::compress(cv, m, n_chunks == 1 ? 0 : c, len, flags);
+            if constexpr (BlockElems<FID>::WHOLE) cur = nxt;
         }
         uint4 *o = reinterpret_cast<uint4 *>(out + (c * n_cols + j) * 8);
         o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
