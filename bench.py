@@ -381,7 +381,9 @@ def main() -> None:
         "dtype": "u64 (63-bit prime field, Montgomery)", "data": "synthetic",
         "config": {"workload": workload_name(world), "field": "Ft63", "n_rows": n_rows_total, "n_per_row": N_PER_ROW,
                    "n_cols": N_COLS, "digest": "BLAKE3", "l2": "inputs larger than L2 (128 MiB in, 256 MiB out per GPU)",
-                   "parallelism": "single GPU" if world == 1 else f"row shards x{world} + NCCL all-to-all + subtree roots"},
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"row shards x{world}; " + ("encode kernel stores into peer column blocks over NVLink (symmetric memory)"
+                                                   if sc.fused else "NCCL all-to-all") + "; per-rank Merkle subtrees, roots all-gathered")},
         "algorithmic_GBps": step_gbs,
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
         "root": gpu_root,

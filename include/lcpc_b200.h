@@ -255,6 +255,15 @@ double lcpc_sdig_dist(int32_t code);
 /* rows [0, n_rows) of the padded coefficient matrix -> encoded rows.  d_coeffs has
  * row stride n_per_row, d_comm row stride n_cols.  d_coeffs may alias nothing in d_comm. */
 int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);
+/* Fused encode + re-shard for the one-process-per-GPU path (Ligero plans): like lcpc_dev_encode,
+ * but the last pass of the transform stores every row block directly into the column-block matrix
+ * of the rank that hashes those columns: peer_blocks[g] is rank g's [n_rows_total][n_cols/n_peers]
+ * row-major matrix (this rank's own buffer or a peer-mapped pointer reached over NVLink), rows
+ * row0 .. row0+n_rows of it are written.  d_scratch: n_rows*n_cols elements of local scratch for the
+ * leading passes (may be NULL when the transform is a single pass).  The caller synchronises the
+ * ranks before anyone reads its matrix. */
+int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t row0,
+                                uint64_t *d_scratch, uint64_t *const *peer_blocks, size_t n_peers);
 /* hash_columns (lib.rs:736-775) on a column window: leaves[j] for j in [0, n_cols) of a
  * matrix with `n_rows` rows whose row stride is `row_stride` elements, starting at d_mat. */
 int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows,

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "lcpc_sdig_gen_level": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),
     "lcpc_sdig_dist": (C.c_double, [C.c_int32]),
     "lcpc_dev_encode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lcpc_dev_encode_scatter": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p,
+                                            C.POINTER(C.c_void_p), C.c_size_t]),
     "lcpc_dev_hash_columns": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_merkle_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "lcpc_dev_fold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,

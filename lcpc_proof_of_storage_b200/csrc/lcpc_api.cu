@@ -685,6 +685,32 @@ int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows
     return encode_dev(plan, d_coeffs, n_rows, d_comm);
 }
 
+int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t row0,
+                                uint64_t *d_scratch, uint64_t *const *peer_blocks, size_t n_peers) {
+    if (!plan || !d_coeffs || !peer_blocks) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (plan->kind != 0) return fail(LCPC_ERR_INVALID_ARG, "the fused encode + re-shard is defined for Ligero plans");
+    if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || plan->n_cols % n_peers)
+        return fail(LCPC_ERR_DIMS, "n_peers must be a power of two <= 16 dividing n_cols");
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(plan->ctx->mu);
+    lcpc_ctx *ctx = plan->ctx;
+    CU(cudaSetDevice(ctx->device));
+    ScatterDst sc{};
+    size_t cb = plan->n_cols / n_peers;
+    sc.log_cb = 0;
+    while (((size_t)1 << sc.log_cb) < cb) sc.log_cb++;
+    sc.row0 = row0;
+    for (size_t i = 0; i < n_peers; i++) {
+        if (!peer_blocks[i]) return fail(LCPC_ERR_INVALID_ARG, "null peer pointer");
+        sc.base[i] = peer_blocks[i];
+    }
+    if (plan->ntt.passes.size() > 1 && !d_scratch) return fail(LCPC_ERR_INVALID_ARG, "scratch needed for multi-pass transforms");
+    cudaError_t e = ntt_encode(plan->ntt, d_coeffs, plan->n_per_row, plan->n_per_row, d_scratch, n_rows, ctx->lc(), &sc);
+    if (e == cudaErrorInvalidValue) return fail(LCPC_ERR_DIMS, "column blocks narrower than the transform's shared-memory block");
+    CU(e);
+    return LCPC_OK;
+}
+
 int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
                               size_t n_cols, uint8_t *d_leaves) {
     if (!ctx || !d_mat || !d_leaves) return fail(LCPC_ERR_INVALID_ARG, "null argument");

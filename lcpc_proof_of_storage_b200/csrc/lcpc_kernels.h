@@ -58,11 +58,21 @@ struct NttPlan {
 cudaError_t ntt_plan_build(NttPlan &plan, int fid, int log_n, const uint64_t *root_mont, const Launch &lc);
 void ntt_plan_free(NttPlan &plan);
 
+// Destination of a fused encode + re-shard (one process per GPU): the final pass of the transform
+// stores each row block straight into the column-block matrix of the rank that will hash those
+// columns -- local HBM for this rank's own block, peer HBM over NVLink for the others.  Rank g owns
+// columns [g << log_cb, (g+1) << log_cb); its matrix is [n_rows_total][1 << log_cb] row-major.
+struct ScatterDst {
+    uint64_t *base[16];
+    int log_cb;
+    uint64_t row0;  // global index of this rank's first row
+};
+
 // n_rows independent transforms.  src rows have stride src_stride and src_valid leading
 // valid elements (the rest of each row reads as zero); dst rows have stride n.
 // src == dst (with src_stride == n) is the in-place case.
 cudaError_t ntt_encode(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
-                       uint64_t *dst, size_t n_rows, const Launch &lc);
+                       uint64_t *dst, size_t n_rows, const Launch &lc, const ScatterDst *scatter = nullptr);
 
 // Column hashing.  d_col_idx == nullptr hashes columns [0, n_cols); otherwise column
 // d_col_idx[j] for j < n_cols.  d_cv_scratch needs hash_scratch_bytes().

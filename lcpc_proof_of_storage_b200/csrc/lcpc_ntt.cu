@@ -175,10 +175,11 @@ __device__ __forceinline__ void block_substep_any(uint64_t *sm, size_t plane, in
     else block_substep<FID, R, false>(sm, plane, LB, log_sub, tw, stw);
 }
 
-template <int FID, int RMAX>
+template <int FID, int RMAX, bool SCATTER>
 __global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 1)
 k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows, int LB,
-            const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
+            const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw,
+            const __grid_constant__ ScatterDst sc) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
@@ -218,7 +219,14 @@ k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *
             const size_t p = sm_phys(i);
 #pragma unroll
             for (int l = 0; l < L; l++) v.v[l] = sm[l * plane + p];
-            st_fe<L>(dst + (row * n + col0 + i) * L, v);
+            if constexpr (SCATTER) {
+                // whole block lands in one rank's column-block matrix (1 << log_cb >= 1 << LB)
+                uint64_t *base = sc.base[col0 >> sc.log_cb];
+                const size_t off = ((sc.row0 + row) << sc.log_cb) + (col0 & (((size_t)1 << sc.log_cb) - 1)) + i;
+                st_fe<L>(base + off * L, v);
+            } else {
+                st_fe<L>(dst + (row * n + col0 + i) * L, v);
+            }
         }
         __syncthreads();
     }
@@ -318,7 +326,7 @@ static cudaError_t plan_build_t(NttPlan &plan, int log_n, const uint64_t *root_m
 
 template <int FID>
 static cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
-                            uint64_t *dst, size_t n_rows, const Launch &lc) {
+                            uint64_t *dst, size_t n_rows, const Launch &lc, const ScatterDst *scatter) {
     using F = Field<FID>;
     constexpr int L = F::LIMBS;
     constexpr int RMAX = L <= 2 ? 4 : 3;
@@ -360,8 +368,14 @@ static cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src
             size_t thr = NB >> RMAX;
             thr = thr < 32 ? 32 : (thr > 256 ? 256 : thr);
             dim3 grid((unsigned)(n >> LB), gy);
-            lc.begin("k_ntt_block");
-            k_ntt_block<FID, RMAX><<<grid, (unsigned)thr, smem, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, LB, tw, stw);
+            if (scatter) {
+                if (LB > scatter->log_cb) return cudaErrorInvalidValue;
+                lc.begin("k_ntt_block_scatter");
+                k_ntt_block<FID, RMAX, true><<<grid, (unsigned)thr, smem, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, LB, tw, stw, *scatter);
+            } else {
+                lc.begin("k_ntt_block");
+                k_ntt_block<FID, RMAX, false><<<grid, (unsigned)thr, smem, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, LB, tw, stw, ScatterDst{});
+            }
         }
         lc.end();
         first = false;
@@ -390,8 +404,8 @@ void ntt_plan_free(NttPlan &plan) {
 }
 
 cudaError_t ntt_encode(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
-                       uint64_t *dst, size_t n_rows, const Launch &lc) {
-#define CALL(F) encode_t<F>(plan, src, src_stride, src_valid, dst, n_rows, lc)
+                       uint64_t *dst, size_t n_rows, const Launch &lc, const ScatterDst *scatter) {
+#define CALL(F) encode_t<F>(plan, src, src_stride, src_valid, dst, n_rows, lc, scatter)
     LCPC_FIELD_SWITCH(plan.fid, CALL)
 #undef CALL
 }

@@ -49,6 +49,13 @@ class GpuOps:
             _lib.check(self.lib.lcpc_dev_encode(self.enc.plan, coeffs.data_ptr(), n_rows, comm.data_ptr()))
         return comm
 
+    def encode_scatter(self, coeffs: torch.Tensor, n_rows: int, row0: int, scratch: torch.Tensor, peer_ptrs) -> None:
+        """Fused encode + re-shard: the transform's last pass stores each row block straight into the
+        owning rank's column-block matrix (peer HBM over NVLink), see lcpc_dev_encode_scatter."""
+        if n_rows:
+            _lib.check(self.lib.lcpc_dev_encode_scatter(self.enc.plan, coeffs.data_ptr(), n_rows, row0,
+                                                        scratch.data_ptr(), peer_ptrs, len(peer_ptrs)))
+
     def hash_columns(self, mat: torch.Tensor, n_rows: int, row_stride: int, n_cols: int, out: torch.Tensor) -> None:
         _lib.check(self.lib.lcpc_dev_hash_columns(self.enc.ctx.handle, self.fid, mat.data_ptr(), n_rows, row_stride,
                                                   n_cols, out.data_ptr()))
@@ -79,7 +86,7 @@ class ShardedLigeroCommitter:
     the top of the tree and the root.
     """
 
-    def __init__(self, enc, n_rows_total: int, group=None, ops=None):
+    def __init__(self, enc, n_rows_total: int, group=None, ops=None, fused: Optional[bool] = None):
         self.enc = enc
         self.group = group
         self.world = dist.get_world_size(group)
@@ -101,6 +108,31 @@ class ShardedLigeroCommitter:
         self.comm_cols: Optional[torch.Tensor] = None   # [n_rows_total, cb, L]: my column block, all rows
         self.subtree: Optional[torch.Tensor] = None     # [(2*cb-1)*32] uint8
         self.top: Optional[torch.Tensor] = None         # rank 0: [(2*world-1)*32] uint8
+        # Fused path (GPU back end, world > 1, power-of-two n_cols): the column-block matrix lives in
+        # symmetric memory, every rank's encode kernel writes its rows into all peers' matrices over
+        # NVLink, and no separate pack / all-to-all pass exists.  fused=None tries it and falls back
+        # to NCCL all_to_all_single when peer mapping is not available.
+        self._symm = self._hdl = self._peer_ptrs = self._scratch = None
+        want = fused if fused is not None else (isinstance(self.ops, GpuOps) and self.world > 1)
+        if want and isinstance(self.ops, GpuOps) and self.world > 1 and self.np2 == self.n_cols and self.world <= 16:
+            try:
+                import ctypes as C
+
+                import torch.distributed._symmetric_memory as symm_mem
+
+                dev = torch.device("cuda", enc.ctx.device)
+                self._symm = symm_mem.empty(self.n_rows * self.cb * self.L, dtype=torch.int64, device=dev)
+                self._hdl = symm_mem.rendezvous(self._symm, group if group is not None else dist.group.WORLD)
+                self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in self._hdl.buffer_ptrs])
+                self._scratch = torch.empty(max(1, self.rows_local) * self.n_cols * self.L, dtype=torch.int64, device=dev)
+            except Exception:
+                if fused:
+                    raise
+                self._symm = self._hdl = self._peer_ptrs = self._scratch = None
+
+    @property
+    def fused(self) -> bool:
+        return self._hdl is not None
 
     # ------------------------------------------------------------------ commit
     def commit(self, coeffs_local: torch.Tensor) -> None:
@@ -108,6 +140,13 @@ class ShardedLigeroCommitter:
         assert coeffs_local.numel() == self.rows_local * self.n_per_row * L
         dev = coeffs_local.device
         self.coeffs_local = coeffs_local
+        if self.fused:
+            self._hdl.barrier(channel=0)  # every rank is done reading the previous matrix
+            self.ops.encode_scatter(coeffs_local, self.rows_local, self.row0, self._scratch, self._peer_ptrs)
+            self._hdl.barrier(channel=1)  # every rank's rows have landed
+            self.comm_cols = self._symm
+            self._finish_tree(dev)
+            return
         comm = self.ops.encode(coeffs_local, self.rows_local)  # [rows_local, n_cols, L]
         # pack: one contiguous slab per destination rank = that rank's column block of my rows
         if self.np2 != self.n_cols:
@@ -125,22 +164,28 @@ class ShardedLigeroCommitter:
         else:
             recv = send.view(-1)
         self.comm_cols = recv  # row-major [n_rows_total, cb, L] because row blocks arrive in rank order
-        # leaves of my column block + my subtree
-        self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
+        self._finish_tree(dev)
+
+    def _finish_tree(self, dev) -> None:
+        cb, W = self.cb, self.world
+        recv = self.comm_cols
+        # leaves of my column block + my subtree (padding leaves are never written: they stay zero)
+        if self.subtree is None or self.subtree.device != dev:
+            self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
+            self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
+            self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
         if self.cols_local:
             self.ops.hash_columns(recv, self.n_rows, cb, self.cols_local, self.subtree)
         self.ops.merkle_tree(self.subtree, cb)
-        # only the subtree roots travel
-        my_root = self.subtree[-32:].contiguous()
+        # only the subtree roots travel (32 bytes per rank); rank 0 joins them
+        my_root = self.subtree[-32:]
         if W > 1:
-            gathered = [torch.empty(32, dtype=torch.uint8, device=dev) for _ in range(W)] if self.rank == 0 else None
-            dist.gather(my_root, gathered, dst=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+            dist.all_gather_into_tensor(self._roots, my_root, group=self.group)
             if self.rank == 0:
-                self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
-                self.top[:W * 32] = torch.cat(gathered)
+                self.top[:W * 32] = self._roots
                 self.ops.merkle_tree(self.top, W)
         else:
-            self.top = my_root.clone()
+            self.top[:32] = my_root
 
     def root(self) -> bytes:
         """LcCommit::get_root on rank 0."""

@@ -1,0 +1,79 @@
+"""The one-process-per-GPU commit on real GPUs (needs >= 2 devices; the single-GPU round-end run
+skips it): NCCL all-to-all path and the fused encode + peer-store path, both against the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, fused, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import lcpc_proof_of_storage_b200 as P
+        from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter, row_partition
+        from oracle import lcpc_oracle as O
+
+        fid, n_rows, n_per_row, n_cols = 0, 37, 4096, 8192
+        n = n_rows * n_per_row - 11
+        coeffs = np.zeros((n_rows * n_per_row, 1), dtype=np.uint64)
+        coeffs[:n] = O.random_field_elements(fid, 5, n)
+        ctx = P.Context(rank, stream=torch.cuda.current_stream().cuda_stream)
+        enc = P.LigeroEncoding(fid, n_per_row, n_cols, ctx=ctx)
+        sc = ShardedLigeroCommitter(enc, n_rows, None, fused=fused)
+        assert sc.fused == fused
+        r0, cnt = row_partition(n_rows, world)[rank]
+        local = torch.from_numpy(coeffs.reshape(n_rows, n_per_row)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
+        for _ in range(3):  # repeated commits reuse the symmetric buffer
+            sc.commit(local)
+        hashes = sc.gather_hashes()
+        tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, 1)
+        folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda())
+        cols = [0, n_cols - 1, 4096, 4095]
+        opened = sc.open_columns(cols)
+        if rank == 0:
+            exp = O.commit(coeffs[:n], O.LigeroEncoding(fid, n_per_row, n_cols))
+            ok = sc.root() == exp.get_root()
+            ok &= np.array_equal(hashes.cpu().numpy().reshape(-1, 32), exp.hashes)
+            f = folded.cpu().numpy().view(np.uint64).reshape(2, n_per_row, 1)
+            for t in range(2):
+                ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+            for c, col in zip(cols, opened):
+                e = O.open_column(exp, c)
+                ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_sharded_commit_two_gpus(fused):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, fused, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
