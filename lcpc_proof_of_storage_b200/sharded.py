@@ -121,9 +121,15 @@ class ShardedLigeroCommitter:
                 import torch.distributed._symmetric_memory as symm_mem
 
                 dev = torch.device("cuda", enc.ctx.device)
-                self._symm = symm_mem.empty(self.n_rows * self.cb * self.L, dtype=torch.int64, device=dev)
+                # two matrices used alternately: a rank may start writing commit k+1 into its peers while
+                # they still hash commit k, so one barrier per commit (after the encode) is enough
+                per = self.n_rows * self.cb * self.L
+                self._symm = symm_mem.empty(2 * per, dtype=torch.int64, device=dev)
                 self._hdl = symm_mem.rendezvous(self._symm, group if group is not None else dist.group.WORLD)
-                self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in self._hdl.buffer_ptrs])
+                self._peer_ptrs = [(C.c_void_p * self.world)(*[int(p) + half * per * 8 for p in self._hdl.buffer_ptrs])
+                                   for half in range(2)]
+                self._halves = [self._symm[:per], self._symm[per:]]
+                self._flip = 0
                 self._scratch = torch.empty(max(1, self.rows_local) * self.n_cols * self.L, dtype=torch.int64, device=dev)
             except Exception:
                 if fused:
@@ -141,10 +147,11 @@ class ShardedLigeroCommitter:
         dev = coeffs_local.device
         self.coeffs_local = coeffs_local
         if self.fused:
-            self._hdl.barrier(channel=0)  # every rank is done reading the previous matrix
-            self.ops.encode_scatter(coeffs_local, self.rows_local, self.row0, self._scratch, self._peer_ptrs)
-            self._hdl.barrier(channel=1)  # every rank's rows have landed
-            self.comm_cols = self._symm
+            half = self._flip
+            self._flip ^= 1
+            self.ops.encode_scatter(coeffs_local, self.rows_local, self.row0, self._scratch, self._peer_ptrs[half])
+            self._hdl.barrier(channel=half)  # every rank's rows have landed (and commit k-1 is fully hashed everywhere)
+            self.comm_cols = self._halves[half]
             self._finish_tree(dev)
             return
         comm = self.ops.encode(coeffs_local, self.rows_local)  # [rows_local, n_cols, L]
