@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "lcpc_mont32.cuh"
+
 namespace lcpc {
 
 enum FieldId : int { FT63 = 0, FT127 = 1, FT191 = 2, FT255 = 3, N_FIELDS = 4 };
@@ -150,6 +152,24 @@ struct Field {
     __host__ __device__ static constexpr uint64_t INV() { return field_consts(FID).inv; }
     __host__ __device__ static constexpr uint64_t RMODP(int i) { return field_consts(FID).r[i]; }
 
+    // 32-bit word i of the modulus (folds to an immediate)
+    struct PWord {
+        __host__ __device__ constexpr uint32_t operator()(int i) const { return (uint32_t)(P(i >> 1) >> (32 * (i & 1))); }
+    };
+    __device__ __forceinline__ static void split(uint32_t (&w)[2 * LIMBS], const E &a) {
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) {
+            w[2 * i] = (uint32_t)a.v[i];
+            w[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
+        }
+    }
+    __device__ __forceinline__ static E join(const uint32_t (&w)[2 * LIMBS]) {
+        E r;
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) r.v[i] = ((uint64_t)w[2 * i + 1] << 32) | w[2 * i];
+        return r;
+    }
+
     __device__ __forceinline__ static E zero() {
         E r;
 #pragma unroll
@@ -207,18 +227,11 @@ struct Field {
             uint64_t s = a.v[0] + b.v[0];  // < 2^64: both < p < 2^63
             r.v[0] = s >= P(0) ? s - P(0) : s;
         } else {
-            uint64_t carry = 0;
-#pragma unroll
-            for (int i = 0; i < LIMBS; i++) {
-                uint64_t s = a.v[i] + b.v[i];
-                uint64_t c1 = s < a.v[i];
-                uint64_t s2 = s + carry;
-                uint64_t c2 = s2 < s;
-                r.v[i] = s2;
-                carry = c1 | c2;
-            }
-            // top bit of every modulus is clear (2p < R): no carry out
-            if (geq_p(r.v)) sub_p(r.v);
+            uint32_t x[2 * LIMBS], y[2 * LIMBS], z[2 * LIMBS];
+            split(x, a);
+            split(y, b);
+            m32::add_mod<2 * LIMBS>(z, x, y, PWord{});
+            r = join(z);
         }
         return r;
     }
@@ -229,28 +242,11 @@ struct Field {
             uint64_t d = a.v[0] - b.v[0];
             r.v[0] = a.v[0] < b.v[0] ? d + P(0) : d;
         } else {
-            uint64_t borrow = 0;
-#pragma unroll
-            for (int i = 0; i < LIMBS; i++) {
-                uint64_t d = a.v[i] - b.v[i];
-                uint64_t b1 = a.v[i] < b.v[i];
-                uint64_t d2 = d - borrow;
-                uint64_t b2 = d < borrow;
-                r.v[i] = d2;
-                borrow = b1 | b2;
-            }
-            if (borrow) {
-                uint64_t carry = 0;
-#pragma unroll
-                for (int i = 0; i < LIMBS; i++) {
-                    uint64_t s = r.v[i] + P(i);
-                    uint64_t c1 = s < r.v[i];
-                    uint64_t s2 = s + carry;
-                    uint64_t c2 = s2 < s;
-                    r.v[i] = s2;
-                    carry = c1 | c2;
-                }
-            }
+            uint32_t x[2 * LIMBS], y[2 * LIMBS], z[2 * LIMBS];
+            split(x, a);
+            split(y, b);
+            m32::sub_mod<2 * LIMBS>(z, x, y, PWord{});
+            r = join(z);
         }
         return r;
     }
@@ -266,39 +262,11 @@ struct Field {
         if constexpr (LIMBS == 1) {
             r.v[0] = ft63::mul(a.v[0], b.v[0]);
         } else {
-            // coarsely integrated operand scanning over 64-bit limbs
-            uint64_t t[LIMBS + 2];
-#pragma unroll
-            for (int i = 0; i < LIMBS + 2; i++) t[i] = 0;
-#pragma unroll
-            for (int i = 0; i < LIMBS; i++) {
-                unsigned __int128 c = 0;
-#pragma unroll
-                for (int j = 0; j < LIMBS; j++) {
-                    c += (unsigned __int128)a.v[j] * b.v[i] + t[j];
-                    t[j] = (uint64_t)c;
-                    c >>= 64;
-                }
-                c += t[LIMBS];
-                t[LIMBS] = (uint64_t)c;
-                t[LIMBS + 1] = (uint64_t)(c >> 64);
-                uint64_t m = t[0] * INV();
-                c = (unsigned __int128)m * P(0) + t[0];
-                c >>= 64;
-#pragma unroll
-                for (int j = 1; j < LIMBS; j++) {
-                    c += (unsigned __int128)m * P(j) + t[j];
-                    t[j - 1] = (uint64_t)c;
-                    c >>= 64;
-                }
-                c += t[LIMBS];
-                t[LIMBS - 1] = (uint64_t)c;
-                t[LIMBS] = t[LIMBS + 1] + (uint64_t)(c >> 64);
-            }
-            // a, b < p < R/2  =>  t < 2p < R: t[LIMBS] == 0
-            if (geq_p(t)) sub_p(t);
-#pragma unroll
-            for (int i = 0; i < LIMBS; i++) r.v[i] = t[i];
+            uint32_t x[2 * LIMBS], y[2 * LIMBS], z[2 * LIMBS];
+            split(x, a);
+            split(y, b);
+            m32::mont_mul<2 * LIMBS>(z, x, y, PWord{});
+            r = join(z);
         }
         return r;
     }
@@ -310,9 +278,10 @@ struct Field {
             r.v[0] = ft63::to_canon(a.v[0]);
             return r;
         } else {
-            E o = zero();
-            o.v[0] = 1;
-            return mul(a, o);
+            uint32_t x[2 * LIMBS], z[2 * LIMBS];
+            split(x, a);
+            m32::mont_redc<2 * LIMBS>(z, x, PWord{});
+            return join(z);
         }
     }
 

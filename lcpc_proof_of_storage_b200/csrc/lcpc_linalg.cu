@@ -273,45 +273,91 @@ cudaError_t pack_bytes7(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elem
 
 // ------------------------------------------------------------------ Brakedown
 
-// y[b][i] = sum_k data[k] * x[b][colidx[k]] over CSR row i, for every matrix row b of the batch
+// The expander levels run on a TRANSPOSED working copy xT[codeword index][matrix row] (leading
+// dimension bp = matrix rows rounded up to the lane-group size): every gathered operand
+// x[col_k][b .. b+GS) is then one contiguous run, the non-zero a[i,k] is loaded once per lane group
+// instead of once per matrix row, and the output run is contiguous too.  A lane group of GS = 8, 16 or
+// 32 lanes owns one output index i; a warp covers 32/GS of them.
 template <int FID>
 __global__ void __launch_bounds__(128)
-k_spmv_batch(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint64_t *__restrict__ data,
-             size_t m_rows, const uint64_t *x_base, size_t x_stride, uint64_t *y_base, size_t y_stride, size_t batch) {
+k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint64_t *__restrict__ data,
+         size_t m_rows, const uint64_t *xT, uint64_t *yT, size_t bp, int log_gs) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int gs = 1 << log_gs;
+    const int lane = threadIdx.x & 31, sub = lane >> log_gs, bl = lane & (gs - 1);
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t i = warp * (32 >> log_gs) + sub;
     if (i >= m_rows) return;
     const uint32_t k0 = rowptr[i], k1 = rowptr[i + 1];
-    for (size_t b = blockIdx.y; b < batch; b += gridDim.y) {
+    for (size_t b = (size_t)blockIdx.y * gs + bl; b < bp; b += (size_t)gridDim.y * gs) {
         E acc = F::zero();
         for (uint32_t k = k0; k < k1; k++) {
             const E a = ld_fe<L>(data + (size_t)k * L);
-            const E x = ld_fe<L>(x_base + (b * x_stride + colidx[k]) * L);
+            const E x = ld_fe<L>(xT + ((size_t)colidx[k] * bp + b) * L);
             acc = F::add(acc, F::mul(a, x));
         }
-        st_fe<L>(y_base + (b * y_stride + i) * L, acc);
+        st_fe<L>(yT + (i * bp + b) * L, acc);
     }
 }
 
-// xo[b][r] = sum_j xi[b][j] * (r+1)^j by Horner (encode.rs:97-109)
+// xoT[r][b] = sum_j xiT[j][b] * (r+1)^j by Horner (encode.rs:97-109), transposed layout
 template <int FID>
-__global__ void k_reed_solomon(const uint64_t *__restrict__ xi, size_t xi_stride, size_t n_in, uint64_t *xo,
-                               size_t xo_stride, size_t n_out, size_t batch) {
+__global__ void k_reed_solomon_t(const uint64_t *__restrict__ xiT, size_t n_in, uint64_t *xoT, size_t n_out, size_t bp) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= batch * n_out) return;
-    const size_t b = t / n_out, r = t % n_out;
-    // x = (r+1) in Montgomery form = sum of (r+1) ones
-    E x = F::zero();
+    if (t >= bp * n_out) return;
+    const size_t r = t / bp, b = t % bp;
+    E x = F::zero();  // (r+1) in Montgomery form = sum of (r+1) ones
     const E one = F::one();
     for (size_t i = 0; i <= r; i++) x = F::add(x, one);
     E acc = F::zero();
-    for (size_t j = n_in; j-- > 0;) acc = F::add(F::mul(acc, x), ld_fe<L>(xi + (b * xi_stride + j) * L));
-    st_fe<L>(xo + (b * xo_stride + r) * L, acc);
+    for (size_t jj = n_in; jj-- > 0;) acc = F::add(F::mul(acc, x), ld_fe<L>(xiT + (jj * bp + b) * L));
+    st_fe<L>(xoT + (r * bp + b) * L, acc);
+}
+
+// dst[c][r] = src[r][c] for r < n_r, c < n_c (32x32 element tiles through shared memory); rows
+// r in [n_r, dst_ld) of dst are written as zero when zero_pad is set.
+template <int L>
+__global__ void __launch_bounds__(256)
+k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src_ld, uint64_t *__restrict__ dst,
+            size_t dst_ld, int zero_pad) {
+    __shared__ uint64_t tile[L][32][33];
+    const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int rr = ty; rr < 32; rr += 8) {
+        const size_t r = r0 + rr, c = c0 + tx;
+        Fe<L> v;
+#pragma unroll
+        for (int l = 0; l < L; l++) v.v[l] = 0;
+        if (r < n_r && c < n_c) v = ld_fe<L>(src + (r * src_ld + c) * L);
+#pragma unroll
+        for (int l = 0; l < L; l++) tile[l][rr][tx] = v.v[l];
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 32; cc += 8) {
+        const size_t c = c0 + cc, r = r0 + tx;
+        if (c < n_c && (r < n_r || (zero_pad && r < dst_ld))) {
+            Fe<L> v;
+#pragma unroll
+            for (int l = 0; l < L; l++) v.v[l] = tile[l][tx][cc];
+            st_fe<L>(dst + (c * dst_ld + r) * L, v);
+        }
+    }
+}
+
+template <int L>
+static void transpose_launch(const uint64_t *src, size_t n_r, size_t n_c, size_t src_ld, uint64_t *dst, size_t dst_ld,
+                             int zero_pad, const Launch &lc) {
+    if (n_r == 0 || n_c == 0) return;
+    const size_t rows_cov = zero_pad ? dst_ld : n_r;
+    dim3 grid((unsigned)((n_c + 31) / 32), (unsigned)((rows_cov + 31) / 32));
+    lc.begin("k_transpose");
+    k_transpose<L><<<grid, 256, 0, lc.s>>>(src, n_r, n_c, src_ld, dst, dst_ld, zero_pad);
+    lc.end();
 }
 
 template <int L>
@@ -343,8 +389,24 @@ cudaError_t widen_rows(int fid, const uint64_t *d_coeffs, size_t n_per_row, uint
     return cudaGetLastError();
 }
 
+// lane-group size (log2) that wastes the fewest padded lanes for this many matrix rows
+static int sdig_log_gs(size_t n_rows) {
+    int best = 5;
+    size_t best_bp = (n_rows + 31) / 32 * 32;
+    for (int lg = 4; lg >= 3; lg--) {
+        size_t g = (size_t)1 << lg, bp = (n_rows + g - 1) / g * g;
+        if (bp < best_bp) { best_bp = bp; best = lg; }
+    }
+    return best;
+}
+static size_t sdig_bp(size_t n_rows) {
+    size_t g = (size_t)1 << sdig_log_gs(n_rows);
+    return (n_rows + g - 1) / g * g;
+}
+
+// transposed working copy: n_cols codeword rows + the (unstored) output of the last precode
 size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows) {
-    return plan.pre.empty() ? 0 : n_rows * plan.pre.back().rows;
+    return plan.pre.empty() ? 0 : (plan.n_cols + plan.pre.back().rows) * sdig_bp(n_rows);
 }
 
 template <int FID>
@@ -353,44 +415,50 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t 
     constexpr int L = Field<FID>::LIMBS;
     const size_t nl = plan.pre.size();
     if (nl == 0 || n_rows == 0) return cudaSuccess;
-    const size_t stride = plan.n_cols;
-    const unsigned gy = (unsigned)(n_rows < 65535 ? n_rows : 65535);
-    auto spmv = [&](const DevCsr &m, const uint64_t *x, size_t xs, uint64_t *y, size_t ys) {
+    const size_t n_cols = plan.n_cols, npr = plan.n_per_row;
+    const int log_gs = sdig_log_gs(n_rows);
+    const size_t bp = sdig_bp(n_rows), gs = (size_t)1 << log_gs;
+    uint64_t *xT = d_tmp;                        // [n_cols][bp]
+    uint64_t *tT = d_tmp + n_cols * bp * L;      // [rows of the last precode][bp]
+    // message columns -> transposed copy (padded lanes zero, so every derived lane stays zero)
+    transpose_launch<L>(d_comm, n_rows, npr, n_cols, xT, bp, 1, lc);
+    auto spmv = [&](const DevCsr &m, size_t x_off, uint64_t *y) {
         if (m.rows == 0) return;
-        dim3 grid((unsigned)((m.rows + 127) / 128), gy);
-        lc.begin("k_spmv_batch");
-        k_spmv_batch<FID><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, x, xs, y, ys, n_rows);
+        const size_t rows_per_cta = 4 * (32 >> log_gs);
+        const size_t groups = bp / gs;
+        dim3 grid((unsigned)((m.rows + rows_per_cta - 1) / rows_per_cta), (unsigned)(groups < 65535 ? groups : 65535));
+        lc.begin("k_spmv_t");
+        k_spmv_t<FID><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, xT + x_off * bp * L, y, bp, log_gs);
         lc.end();
     };
     // encode.rs:46-58 precodes all the way down
     size_t in_start = 0;
     for (size_t l = 0; l + 1 < nl; l++) {
         const size_t in_end = in_start + plan.pre[l].cols;
-        spmv(plan.pre[l], d_comm + in_start * L, stride, d_comm + in_end * L, stride);
+        spmv(plan.pre[l], in_start, xT + in_end * bp * L);
         in_start = in_end;
     }
-    // encode.rs:61-74 base case
+    // encode.rs:61-74 base case: last precode into the temporary, Reed-Solomon of that
     const DevCsr &lp = plan.pre[nl - 1];
     const size_t in_end = in_start + lp.cols;
-    spmv(lp, d_comm + in_start * L, stride, d_tmp, lp.rows);
+    spmv(lp, in_start, tT);
     const size_t n_rs = plan.post[nl - 1].cols;
-    {
-        const size_t total = n_rows * n_rs;
-        if (total) {
-            lc.begin("k_reed_solomon");
-            k_reed_solomon<FID><<<(unsigned)((total + 127) / 128), 128, 0, lc.s>>>(d_tmp, lp.rows, lp.rows,
-                                                                                 d_comm + in_end * L, stride, n_rs, n_rows);
-            lc.end();
-        }
+    if (n_rs) {
+        const size_t total = bp * n_rs;
+        lc.begin("k_reed_solomon_t");
+        k_reed_solomon_t<FID><<<(unsigned)((total + 127) / 128), 128, 0, lc.s>>>(tT, lp.rows, xT + in_end * bp * L, n_rs, bp);
+        lc.end();
     }
     in_start = in_end + lp.rows;
     size_t out_start = in_end + n_rs;
     // encode.rs:76-90 postcodes back up
     for (size_t l = nl; l-- > 0;) {
         in_start -= plan.pre[l].rows;
-        spmv(plan.post[l], d_comm + in_start * L, stride, d_comm + out_start * L, stride);
+        spmv(plan.post[l], in_start, xT + out_start * bp * L);
         out_start += plan.post[l].rows;
     }
+    // computed part of the codeword back to the row-major matrix (the message columns are in place)
+    transpose_launch<L>(xT + npr * bp * L, n_cols - npr, n_rows, bp, d_comm + npr * L, n_cols, 0, lc);
     return cudaGetLastError();
 }
 

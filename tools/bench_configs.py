@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench): the other BASELINE.json configurations on one
+B200, device-resident, CUDA-event timed, with per-kernel timings.  Prints one JSON line per case.
+
+    python tools/bench_configs.py [case ...]      cases: ligero63_20 ligero63_24 ligero63_28 ligero255_24
+                                                         brakedown63_24 brakedown255_24 pos_1g fold63_24 prove63_24
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import lcpc_proof_of_storage_b200 as P
+from lcpc_proof_of_storage_b200 import _lib
+
+lib = _lib.load()
+stream = torch.cuda.current_stream()
+ctx = P.Context(0, stream=stream.cuda_stream)
+MOD = {0: 5102708120182849537,
+       1: 146823888364060453008360742206866194433,
+       3: 46242760681095663677370860714659204618859642560429202607213929836750194081793}
+
+
+def rand_elems(fid, n, seed=1):
+    """Uniform-ish reduced elements: random limbs with the top limb cut below the modulus' top limb."""
+    L = P.FIELD_LIMBS[fid]
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 63, size=(n, L), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, L), dtype=np.uint64)
+    top = MOD[fid] >> (64 * (L - 1))
+    a[:, L - 1] %= np.uint64(top)
+    return a
+
+
+def timed(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ctx.kernel_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    kt = ctx.kernel_timing_report()
+    ctx.kernel_timing(False)
+    return e0.elapsed_time(e1) / steps, {k: round(v[1] / steps, 4) for k, v in kt.items()}
+
+
+def commit_case(name, enc, n, steps=10):
+    fid, L = enc.fid, P.FIELD_LIMBS[enc.fid]
+    n_rows, npr, n_cols = enc.get_dims(n)
+    np2 = P.next_pow2(n_cols)
+    coeffs = torch.from_numpy(rand_elems(fid, n_rows * npr).view(np.int64).reshape(-1)).cuda()
+    comm = torch.empty(n_rows * n_cols * L, dtype=torch.int64, device="cuda")
+    hashes = torch.zeros((2 * np2 - 1) * 32, dtype=torch.uint8, device="cuda")
+
+    def step():
+        _lib.check(lib.lcpc_dev_encode(enc.plan, coeffs.data_ptr(), n_rows, comm.data_ptr()))
+        _lib.check(lib.lcpc_dev_hash_columns(ctx.handle, fid, comm.data_ptr(), n_rows, n_cols, n_cols, hashes.data_ptr()))
+        _lib.check(lib.lcpc_dev_merkle_tree(ctx.handle, hashes.data_ptr(), np2))
+
+    ms, kt = timed(step, steps)
+    alg = n * 8 * L + n_rows * n_cols * 8 * L + (2 * np2 - 1) * 32
+    print(json.dumps({"case": name, "field": P.FIELD_NAMES[fid], "n_coeffs": n, "shape": [n_rows, npr, n_cols],
+                      "ms_per_commit": round(ms, 4), "coeffs_per_s": n / ms * 1e3, "algorithmic_GBps": alg / ms / 1e6,
+                      "kernels_ms": kt}), flush=True)
+    return coeffs, comm, hashes
+
+
+def main():
+    cases = sys.argv[1:] or ["ligero63_20", "ligero63_24", "ligero63_28", "ligero255_24", "brakedown63_24",
+                             "brakedown255_24", "fold63_24"]
+    for case in cases:
+        if case.startswith("ligero"):
+            fid = 0 if case.startswith("ligero63") else 3
+            n = 1 << int(case.split("_")[1])
+            enc = P.LigeroEncoding.new(fid, n, ctx=ctx)
+            commit_case(case, enc, n, steps=10 if n <= (1 << 24) else 3)
+        elif case.startswith("brakedown"):
+            fid = 0 if case.startswith("brakedown63") else 3
+            n = 1 << int(case.split("_")[1])
+            t0 = time.time()
+            enc = P.SdigEncoding.new(fid, n, seed=0, ctx=ctx)
+            gen_s = time.time() - t0
+            print(json.dumps({"case": case + "_matgen", "host_seconds": round(gen_s, 2), "n_per_row": enc.n_per_row,
+                              "n_cols": enc.n_cols, "levels": len(enc.precodes)}), flush=True)
+            commit_case(case, enc, n, steps=5)
+        elif case == "fold63_24":
+            fid, n = 0, 1 << 24
+            enc = P.LigeroEncoding.new(fid, n, ctx=ctx)
+            n_rows, npr, n_cols = enc.get_dims(n)
+            coeffs = torch.from_numpy(rand_elems(fid, n).view(np.int64).reshape(-1)).cuda()
+            for nt in (1, 4):
+                tens = torch.from_numpy(rand_elems(fid, nt * n_rows, 3).view(np.int64).reshape(-1)).cuda()
+                out = torch.empty(nt * npr, dtype=torch.int64, device="cuda")
+
+                def step():
+                    _lib.check(lib.lcpc_dev_fold(ctx.handle, fid, coeffs.data_ptr(), n_rows, npr, npr, tens.data_ptr(), nt,
+                                                 out.data_ptr()))
+
+                ms, kt = timed(step, 20)
+                print(json.dumps({"case": f"fold63_24_x{nt}", "ms": round(ms, 4), "GBps_matrix_read": n * 8 / ms / 1e6,
+                                  "kernels_ms": kt}), flush=True)
+        elif case == "pos_1g":
+            n_bytes = 1 << 30
+            data = torch.randint(0, 256, (n_bytes,), dtype=torch.uint8, device="cuda")
+            n = (n_bytes + 6) // 7
+            enc = P.LigeroEncoding(0, 32768, 65536, ctx=ctx)
+            n_rows = (n + 32767) // 32768
+            elems = torch.zeros(n_rows * 32768, dtype=torch.int64, device="cuda")
+            comm = torch.empty(n_rows * 65536, dtype=torch.int64, device="cuda")
+            hashes = torch.zeros((2 * 65536 - 1) * 32, dtype=torch.uint8, device="cuda")
+
+            def step():
+                _lib.check(lib.lcpc_dev_pack_bytes7(ctx.handle, data.data_ptr(), n_bytes, elems.data_ptr()))
+                _lib.check(lib.lcpc_dev_encode(enc.plan, elems.data_ptr(), n_rows, comm.data_ptr()))
+                _lib.check(lib.lcpc_dev_hash_columns(ctx.handle, 0, comm.data_ptr(), n_rows, 65536, 65536, hashes.data_ptr()))
+                _lib.check(lib.lcpc_dev_merkle_tree(ctx.handle, hashes.data_ptr(), 65536))
+
+            ms, kt = timed(step, 5)
+            print(json.dumps({"case": "pos_1GiB_file", "n_rows": n_rows, "ms": round(ms, 3), "file_GBps": n_bytes / ms / 1e6,
+                              "kernels_ms": kt}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
