@@ -94,7 +94,7 @@ __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], c
 // ------------------------------------------------------------------ strided pass
 
 template <int FID, int R>
-__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 1)
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 2)
 k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows,
               int log_sub, const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
     using F = Field<FID>;
@@ -113,12 +113,15 @@ k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t
             x[m] = idx < src_valid ? ld_fe<L>(src + (row * src_stride + idx) * L) : F::zero();
         }
         radix_dif<FID, R>(x, stw);
-        {
+        if constexpr (L == 1) {
             E t[1 << R];
 #pragma unroll
             for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
 #pragma unroll
             for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+        } else {
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
         }
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
@@ -152,12 +155,18 @@ __device__ __forceinline__ void block_substep(uint64_t *sm, size_t plane, int LB
         }
         radix_dif<FID, R>(x, stw);
         if constexpr (TW) {
-            // all pass twiddles of this group in flight together (one exposed L1/L2 latency, not 2^R - 1)
-            E t[1 << R];
+            if constexpr (L == 1) {
+                // all pass twiddles of this group in flight together (one exposed L1/L2 latency, not 2^R - 1)
+                E t[1 << R];
 #pragma unroll
-            for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
+                for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
 #pragma unroll
-            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+                for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+            } else {
+                // wide elements: keep one twiddle live at a time (register pressure decides occupancy here)
+#pragma unroll
+                for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
+            }
         }
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
@@ -176,7 +185,7 @@ __device__ __forceinline__ void block_substep_any(uint64_t *sm, size_t plane, in
 }
 
 template <int FID, int RMAX, bool SCATTER>
-__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 1)
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 2)
 k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows, int LB,
             const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw,
             const __grid_constant__ ScatterDst sc) {
