@@ -234,6 +234,21 @@ int32_t lcpc_verify(lcpc_plan *plan, const uint8_t root[LCPC_DIGEST_BYTES], cons
                     size_t n_columns, size_t n_col_opens, size_t n_degree_tests, lcpc_transcript *tr,
                     uint64_t *result_out);
 
+/* ---- proof-of-storage helpers -------------------------------------------------------- */
+
+/* get_column_indicies_from_random_seed (proof-of-storage/src/networking/client.rs:443-456):
+ * ChaCha8Rng::seed_from_u64(seed), then IteratorRandom::choose_multiple of `amount` indices out
+ * of 0..max_index (without replacement).  Host-side.  *n_out = min(amount, max_index). */
+int32_t lcpc_pos_choose_columns(uint64_t seed, size_t amount, size_t max_index, uint64_t *out, size_t *n_out);
+
+/* The client's retrievability check on received columns (lcpc_online.rs:275-281, 370-398,
+ * 439-452): leaves_out[i] = hash_column_to_digest(column i) (nullable), and when `paths` is given,
+ * ok_out[i] = verify_column_path(column i, col_idx[i], root) (lcpc-2d/src/lib.rs:985-1012).
+ * columns: n x n_rows elements, column-contiguous as in LcColumn.col; paths: n x path_len digests. */
+int32_t lcpc_verify_columns_host(lcpc_ctx *ctx, int32_t field, const uint64_t *columns, size_t n_rows,
+                                 const uint8_t *paths, size_t path_len, const uint64_t *col_idx, size_t n,
+                                 const uint8_t root[LCPC_DIGEST_BYTES], uint8_t *leaves_out, uint32_t *ok_out);
+
 /* ---- Brakedown code generation (host-side) ------------------------------------------ */
 
 /* matgen::get_dims (lcpc-brakedown-pc/src/matgen.rs:56-111) for SdigCode<code> (1..6,

@@ -84,6 +84,9 @@ _SIGNATURES = {
     "lcpc_verify": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                 C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "lcpc_pos_choose_columns": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_size_t, C.c_void_p, szp]),
+    "lcpc_verify_columns_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcpc_sdig_get_dims": (C.c_int32, [C.c_int32, C.c_uint64, C.c_int32, u64p, u64p, C.c_int32, C.POINTER(C.c_int32)]),
     "lcpc_sdig_gen_level": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),
     "lcpc_sdig_dist": (C.c_double, [C.c_int32]),

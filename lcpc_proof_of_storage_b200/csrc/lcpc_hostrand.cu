@@ -154,7 +154,7 @@ void ChaCha20Rng::refill() {
         x[a] += x[b]; x[d] = rol32(x[d] ^ x[a], 8);
         x[c] += x[d]; x[b] = rol32(x[b] ^ x[c], 7);
     };
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < rounds_ / 2; i++) {
         qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
         qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
     }
@@ -163,15 +163,16 @@ void ChaCha20Rng::refill() {
     idx_ = 0;
 }
 
-ChaCha20Rng ChaCha20Rng::from_seed(const uint8_t seed[32]) {
+ChaCha20Rng ChaCha20Rng::from_seed(const uint8_t seed[32], int rounds) {
     ChaCha20Rng r;
+    r.rounds_ = rounds;
     for (int i = 0; i < 8; i++)
         r.key_[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) |
                     ((uint32_t)seed[4 * i + 3] << 24);
     return r;
 }
 
-ChaCha20Rng ChaCha20Rng::seed_from_u64(uint64_t state) {
+ChaCha20Rng ChaCha20Rng::seed_from_u64(uint64_t state, int rounds) {
     uint8_t seed[32];
     for (int i = 0; i < 8; i++) {
         state = state * 6364136223846793005ull + 11634580027462260723ull;
@@ -180,7 +181,7 @@ ChaCha20Rng ChaCha20Rng::seed_from_u64(uint64_t state) {
         const uint32_t v = (xs >> rot) | (xs << ((32 - rot) & 31));
         for (int b = 0; b < 4; b++) seed[4 * i + b] = (uint8_t)(v >> (8 * b));
     }
-    return from_seed(seed);
+    return from_seed(seed, rounds);
 }
 
 uint32_t ChaCha20Rng::next_u32() {
@@ -200,6 +201,26 @@ uint64_t ChaCha20Rng::uniform(uint64_t n) {
     for (;;) {
         const unsigned __int128 m = (unsigned __int128)next_u64() * n;
         if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+    }
+}
+
+uint32_t ChaCha20Rng::gen_range_u32(uint32_t n) {
+    // UniformInt<u32>::sample_single_inclusive(0, n-1): range = n, zone = (range << lz) - 1
+    const uint32_t zone = (n << __builtin_clz(n)) - 1;
+    for (;;) {
+        const uint64_t m = (uint64_t)next_u32() * n;
+        if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+    }
+}
+
+void choose_multiple_indices(ChaCha20Rng &rng, uint64_t amount, uint64_t max_index, std::vector<uint64_t> &out) {
+    out.clear();
+    for (uint64_t i = 0; i < amount && i < max_index; i++) out.push_back(i);
+    if (out.size() < amount) return;  // iterator exhausted: everything is chosen
+    for (uint64_t i = 0; amount + i < max_index; i++) {
+        const uint64_t ubound = i + 1 + amount;
+        const uint64_t k = ubound <= 0xffffffffull ? rng.gen_range_u32((uint32_t)ubound) : rng.uniform(ubound);
+        if (k < amount) out[k] = amount + i;
     }
 }
 

@@ -38,27 +38,36 @@ private:
 };
 
 // ---- rand_chacha 0.3 ChaCha20Rng ----------------------------------------------------
+// rand_chacha 0.3 ChaChaXRng; the round count distinguishes ChaCha20Rng (prove / verify / matgen)
+// from ChaCha8Rng (proof-of-storage column choice, networking/client.rs:448).
 class ChaCha20Rng {
 public:
-    static ChaCha20Rng from_seed(const uint8_t seed[32]);
-    static ChaCha20Rng seed_from_u64(uint64_t state);  // rand_core 0.6 PCG32 expansion
+    static ChaCha20Rng from_seed(const uint8_t seed[32], int rounds = 20);
+    static ChaCha20Rng seed_from_u64(uint64_t state, int rounds = 20);  // rand_core 0.6 PCG32 expansion
     void set_stream(uint64_t stream) { stream_ = stream; }  // before the first draw (matgen.rs:43-44)
     uint32_t next_u32();
     uint64_t next_u64();
     // rand 0.8 Uniform::new(0usize, n).sample(rng), 64-bit target
     uint64_t uniform(uint64_t n);
+    // rand 0.8 rng.gen_range(0..n) for u32 (UniformInt::sample_single: leading-zeros zone)
+    uint32_t gen_range_u32(uint32_t n);
 
 private:
     uint32_t key_[8];
     uint64_t counter_ = 0, stream_ = 0;
     uint32_t buf_[16];
     int idx_ = 16;
+    int rounds_ = 20;
     void refill();
 };
 
 // ff_derive `Field::random`: LIMBS x next_u64, top limb masked to NUM_BITS, rejected if >= p;
 // the accepted limbs are the Montgomery residue.
 void field_random(int fid, ChaCha20Rng &rng, uint64_t *out);
+
+// rand 0.8 IteratorRandom::choose_multiple over 0..max (reservoir sampling; gen_index draws u32 when
+// the bound fits): proof-of-storage get_column_indicies_from_random_seed (networking/client.rs:443-456)
+void choose_multiple_indices(ChaCha20Rng &rng, uint64_t amount, uint64_t max_index, std::vector<uint64_t> &out);
 
 // ---- lcpc-brakedown-pc code generation -------------------------------------------------
 struct SdigDims {

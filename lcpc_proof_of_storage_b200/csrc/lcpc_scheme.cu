@@ -103,6 +103,56 @@ int32_t lcpc_random_columns(const uint8_t key[32], uint64_t n_cols, uint64_t *ou
     return LCPC_OK;
 }
 
+// ---- proof-of-storage helpers -------------------------------------------------------------
+
+int32_t lcpc_pos_choose_columns(uint64_t seed, size_t amount, size_t max_index, uint64_t *out, size_t *n_out) {
+    if ((!out && amount) || !n_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    host::ChaCha20Rng rng = host::ChaCha20Rng::seed_from_u64(seed, 8);  // ChaCha8Rng (networking/client.rs:448)
+    std::vector<uint64_t> cols;
+    host::choose_multiple_indices(rng, amount, max_index, cols);
+    for (size_t i = 0; i < cols.size(); i++) out[i] = cols[i];
+    *n_out = cols.size();
+    return LCPC_OK;
+}
+
+int32_t lcpc_verify_columns_host(lcpc_ctx *ctx, int32_t field, const uint64_t *columns, size_t n_rows, const uint8_t *paths,
+                                 size_t path_len, const uint64_t *col_idx, size_t n, const uint8_t root[LCPC_DIGEST_BYTES],
+                                 uint8_t *leaves_out, uint32_t *ok_out) {
+    if (!ctx || (!columns && n && n_rows) || (!col_idx && n && paths)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    if (paths && (!root || !ok_out)) return fail(LCPC_ERR_INVALID_ARG, "paths given without root / ok_out");
+    if (n == 0) return LCPC_OK;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t wbytes = (size_t)limbs_of(field) * 8;
+    DevBuf d_cols, d_leafidx, d_leaves, d_hs, d_paths, d_idx, d_root, d_ok;
+    CU(d_cols.alloc(n * n_rows * wbytes, ctx->stream));
+    CU(d_leafidx.alloc(n * 8, ctx->stream));
+    CU(d_leaves.alloc(n * 32, ctx->stream));
+    CU(d_hs.alloc(hash_scratch_bytes(field, n_rows, n), ctx->stream));
+    CU(cudaMemcpyAsync(d_cols.p, columns, n * n_rows * wbytes, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint64_t> leafidx(n);
+    for (size_t i = 0; i < n; i++) leafidx[i] = i * n_rows;  // column i is contiguous: a stride-1 "matrix"
+    CU(cudaMemcpyAsync(d_leafidx.p, leafidx.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(hash_columns(field, d_cols.as<uint64_t>(), n_rows, 1, n, d_leafidx.as<uint64_t>(), d_leaves.as<uint8_t>(),
+                    d_hs.as<uint8_t>(), ctx->lc()));
+    if (leaves_out) CU(cudaMemcpyAsync(leaves_out, d_leaves.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (paths) {
+        CU(d_paths.alloc(n * path_len * 32, ctx->stream));
+        CU(d_idx.alloc(n * 8, ctx->stream));
+        CU(d_root.alloc(32, ctx->stream));
+        CU(d_ok.alloc(n * 4, ctx->stream));
+        if (path_len) CU(cudaMemcpyAsync(d_paths.p, paths, n * path_len * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_idx.p, col_idx, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_root.p, root, 32, cudaMemcpyHostToDevice, ctx->stream));
+        CU(verify_paths(d_leaves.as<uint8_t>(), d_paths.as<uint8_t>(), (int)path_len, d_idx.as<uint64_t>(), n,
+                        d_root.as<uint8_t>(), d_ok.as<uint32_t>(), ctx->lc()));
+        CU(cudaMemcpyAsync(ok_out, d_ok.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
 // ---- Brakedown code generation ---------------------------------------------------------
 
 int32_t lcpc_sdig_get_dims(int32_t code, uint64_t n_per_row, int32_t field, uint64_t *pre_dims, uint64_t *post_dims,

@@ -707,3 +707,24 @@ def random_field_elements(fid: int, seed: int, n: int) -> np.ndarray:
         for l in range(L):
             raw[i, l] = (v >> (64 * l)) & ((1 << 64) - 1)
     return raw
+
+
+def pos_choose_columns(seed: int, amount: int, max_index: int) -> List[int]:
+    """proof-of-storage get_column_indicies_from_random_seed (networking/client.rs:443-456):
+    ChaCha8Rng::seed_from_u64 + IteratorRandom::choose_multiple over 0..max_index."""
+    out = np.zeros(max(1, amount), dtype=np.uint64)
+    lib().orc_pos_choose_columns.restype = C.c_size_t
+    n = lib().orc_pos_choose_columns(C.c_uint64(seed), C.c_size_t(amount), C.c_size_t(max_index), _p64(out))
+    return [int(x) for x in out[:n]]
+
+
+def pack_bytes7(data: bytes) -> np.ndarray:
+    """DataField::from_byte_vec for WriteableFt63 (fields/data_field.rs:38-46, writable_ft63.rs:35-40)."""
+    n = (len(data) + 6) // 7
+    buf = np.zeros(n * 7, dtype=np.uint8)
+    buf[:len(data)] = np.frombuffer(data, dtype=np.uint8)
+    b = buf.reshape(n, 7).astype(np.uint64)
+    out = np.zeros(n, dtype=np.uint64)
+    for k in range(7):
+        out |= b[:, k] << np.uint64(8 * k)
+    return out.reshape(n, 1)

@@ -23,7 +23,8 @@ static void chacha_block(orc_chacha_rng *r) {
     in[14] = (uint32_t)r->stream;
     in[15] = (uint32_t)(r->stream >> 32);
     memcpy(x, in, sizeof x);
-    for (int i = 0; i < 10; i++) {
+    int dr = (r->rounds ? r->rounds : 20) / 2;
+    for (int i = 0; i < dr; i++) {
         QR(x[0], x[4], x[8], x[12]);
         QR(x[1], x[5], x[9], x[13]);
         QR(x[2], x[6], x[10], x[14]);
@@ -45,6 +46,7 @@ void orc_chacha_from_seed(orc_chacha_rng *r, const uint8_t seed[32]) {
     r->counter = 0;
     r->stream = 0;
     r->idx = 16;
+    r->rounds = 20;
 }
 
 /* rand_core 0.6 SeedableRng::seed_from_u64 default: PCG32 fills the seed 4 bytes at a time */
@@ -90,6 +92,29 @@ uint64_t orc_uniform_usize(orc_chacha_rng *r, uint64_t n) {
         uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
         if (lo <= zone) return hi;
     }
+}
+
+uint32_t orc_gen_range_u32(orc_chacha_rng *r, uint32_t n) {
+    uint32_t zone = (n << __builtin_clz(n)) - 1;
+    for (;;) {
+        uint64_t m = (uint64_t)orc_chacha_next_u32(r) * n;
+        if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+    }
+}
+
+size_t orc_pos_choose_columns(uint64_t seed, size_t amount, size_t max_index, uint64_t *out) {
+    orc_chacha_rng rng;
+    orc_chacha_seed_from_u64(&rng, seed);
+    rng.rounds = 8;
+    size_t n = 0;
+    for (size_t i = 0; i < amount && i < max_index; i++) out[n++] = i; /* reservoir.extend(take(amount)) */
+    if (n < amount) return n;
+    for (size_t i = 0; amount + i < max_index; i++) { /* gen_index(rng, i + 1 + amount) */
+        uint64_t ub = i + 1 + amount;
+        uint64_t k = ub <= 0xffffffffull ? orc_gen_range_u32(&rng, (uint32_t)ub) : orc_uniform_usize(&rng, ub);
+        if (k < amount) out[k] = amount + i;
+    }
+    return n;
 }
 
 /* ---------------- Keccak-f[1600] ---------------- */

@@ -26,6 +26,7 @@ typedef struct {
     uint64_t stream;  /* 64-bit stream id     (state words 14,15) */
     uint32_t buf[16];
     int idx;          /* next unread word in buf; 16 = empty      */
+    int rounds;       /* 20 = ChaCha20Rng, 8 = ChaCha8Rng; 0 is read as 20 */
 } orc_chacha_rng;
 
 void orc_chacha_from_seed(orc_chacha_rng *r, const uint8_t seed[32]);
@@ -35,6 +36,11 @@ uint32_t orc_chacha_next_u32(orc_chacha_rng *r);
 uint64_t orc_chacha_next_u64(orc_chacha_rng *r);
 /* rand 0.8 Uniform::new(0, n).sample(rng) for usize on a 64-bit target */
 uint64_t orc_uniform_usize(orc_chacha_rng *r, uint64_t n);
+/* rand 0.8 rng.gen_range(0..n) for u32 (UniformInt::sample_single) */
+uint32_t orc_gen_range_u32(orc_chacha_rng *r, uint32_t n);
+/* ChaCha8Rng::seed_from_u64(seed) + IteratorRandom::choose_multiple over 0..max_index
+ * (proof-of-storage/src/networking/client.rs:443-456); returns the number of indices written */
+size_t orc_pos_choose_columns(uint64_t seed, size_t amount, size_t max_index, uint64_t *out);
 
 void orc_keccak_f1600(uint64_t st[25]);
 

@@ -143,7 +143,7 @@ def test_keccak_f1600_via_sha3(oracle):
 
 class _Rng(C.Structure):
     _fields_ = [("key", C.c_uint32 * 8), ("counter", C.c_uint64), ("stream", C.c_uint64),
-                ("buf", C.c_uint32 * 16), ("idx", C.c_int)]
+                ("buf", C.c_uint32 * 16), ("idx", C.c_int), ("rounds", C.c_int)]
 
 
 @pytest.mark.parametrize("stream", [0, 1, 5])
