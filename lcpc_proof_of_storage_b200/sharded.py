@@ -56,6 +56,13 @@ class GpuOps:
             _lib.check(self.lib.lcpc_dev_encode_scatter(self.enc.plan, coeffs.data_ptr(), n_rows, row0,
                                                         scratch.data_ptr(), peer_ptrs, len(peer_ptrs)))
 
+    def pack_bytes7(self, data: torch.Tensor, n_elems_padded: int) -> torch.Tensor:
+        """WriteableFt63::from_data_bytes over this rank's slice of the file; the tail is zero elements."""
+        out = torch.zeros(n_elems_padded, dtype=torch.int64, device=self.device)
+        if data.numel():
+            _lib.check(self.lib.lcpc_dev_pack_bytes7(self.enc.ctx.handle, data.data_ptr(), data.numel(), out.data_ptr()))
+        return out
+
     def hash_columns(self, mat: torch.Tensor, n_rows: int, row_stride: int, n_cols: int, out: torch.Tensor) -> None:
         _lib.check(self.lib.lcpc_dev_hash_columns(self.enc.ctx.handle, self.fid, mat.data_ptr(), n_rows, row_stride,
                                                   n_cols, out.data_ptr()))
@@ -194,6 +201,19 @@ class ShardedLigeroCommitter:
         else:
             self.top[:32] = my_root
 
+    # ------------------------------------------------------------------ proof-of-storage bytes
+    def byte_range(self, n_bytes_total: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        """[start, end) of the file bytes that make up this rank's rows (7 bytes per element)."""
+        r0, cnt = self.rows[self.rank if rank is None else rank]
+        lo = min(n_bytes_total, r0 * self.n_per_row * 7)
+        hi = min(n_bytes_total, (r0 + cnt) * self.n_per_row * 7)
+        return lo, hi
+
+    def commit_bytes(self, local_bytes: torch.Tensor) -> None:
+        """proof-of-storage commit of a file sharded by row blocks: 7-byte packing on the device, then commit."""
+        assert self.L == 1 and local_bytes.dtype == torch.uint8
+        self.commit(self.ops.pack_bytes7(local_bytes, self.rows_local * self.n_per_row))
+
     def root(self) -> bytes:
         """LcCommit::get_root on rank 0."""
         assert self.rank == 0 and self.top is not None
@@ -238,38 +258,64 @@ class ShardedLigeroCommitter:
 
     # ------------------------------------------------------------------ open
     def open_columns(self, cols: Sequence[int]) -> Optional[List[LcColumn]]:
-        """open_column for each index; the column values come from the rank owning that column
-        block, the path from the gathered tree.  Result on rank 0 (None elsewhere)."""
+        """open_column (lcpc-2d/src/lib.rs:818-855) for each index.  The owner of a column block sends
+        the column values together with the part of the Merkle path that lies inside its subtree;
+        rank 0 appends the siblings above the subtree roots.  Result on rank 0 (None elsewhere)."""
         import numpy as np
 
-        L, cb = self.L, self.cb
+        L, cb, W = self.L, self.cb, self.world
         for c in cols:
             if not 0 <= c < self.n_cols:
                 from .lcpc2d import ProverError
 
                 raise ProverError("ColumnNumber", "bad column number")
-        mine = [c for c in cols if c // cb == self.rank]
-        m3 = self.comm_cols.view(self.n_rows, cb, L)
-        vals = torch.stack([m3[:, c - self.col0] for c in mine]) if mine else torch.empty(0, self.n_rows, L, dtype=torch.int64,
-                                                                                             device=self.comm_cols.device)
-        gathered = [None] * self.world
-        dist.all_gather_object(gathered, (mine, vals.cpu().numpy().view(np.uint64)), group=self.group)
-        hashes = self.gather_hashes()
-        if self.rank != 0:
-            return None
-        h = hashes.cpu().numpy().reshape(-1, 32)
-        by_col = {}
-        for cols_q, vals_q in gathered:
-            for c, v in zip(cols_q, vals_q):
-                by_col[c] = v
-        out = []
+        dev = self.comm_cols.device
         depth = log2(self.n_cols)
-        for c in cols:
-            path, off, n, idx = [], 0, self.np2, c
-            for _ in range(depth):
-                path.append(h[off + (idx ^ 1)])
+        depth_sub = min(depth, log2(cb))  # path levels inside a subtree
+        owners = [c // cb for c in cols]
+        mine = [c for c, o in zip(cols, owners) if o == self.rank]
+
+        def my_payload():
+            idx = torch.tensor([c - self.col0 for c in mine], dtype=torch.long, device=dev)
+            m3 = self.comm_cols.view(self.n_rows, cb, L)
+            vals = m3.index_select(1, idx).transpose(0, 1).contiguous().view(len(mine), -1)  # [k, n_rows*L]
+            sub = self.subtree.view(-1, 32)
+            parts, off, n, node = [], 0, cb, idx.clone()
+            for _ in range(depth_sub):
+                parts.append(sub.index_select(0, off + (node ^ 1)))
                 off += n
                 n //= 2
-                idx >>= 1
-            out.append(LcColumn(by_col[c], np.stack(path) if path else np.empty((0, 32), np.uint8)))
+                node = node >> 1
+            paths = torch.stack(parts, dim=1).reshape(len(mine), -1) if parts else torch.empty(len(mine), 0, dtype=torch.uint8, device=dev)
+            # one int64 buffer per rank: values, then the path bytes (32-byte digests = 4 words each)
+            return torch.cat([vals, paths.contiguous().view(torch.int64).view(len(mine), -1)], dim=1).contiguous()
+
+        width = self.n_rows * L + depth_sub * 4
+        payload = my_payload() if mine else torch.empty(0, width, dtype=torch.int64, device=dev)
+        counts = [sum(1 for o in owners if o == q) for q in range(W)]
+        if self.rank == 0:
+            bufs = [payload] + [torch.empty(counts[q], width, dtype=torch.int64, device=dev) for q in range(1, W)]
+            ops = [dist.P2POp(dist.irecv, bufs[q], q, group=self.group) for q in range(1, W) if counts[q]]
+        else:
+            bufs, ops = None, ([dist.P2POp(dist.isend, payload, 0, group=self.group)] if mine else [])
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if self.rank != 0:
+            return None
+        host = [b.cpu().numpy() for b in bufs]
+        top = self.top.cpu().numpy().reshape(-1, 32)
+        out, seen = [], [0] * W
+        for c, q in zip(cols, owners):
+            row = host[q][seen[q]]
+            seen[q] += 1
+            col = row[:self.n_rows * L].view(np.uint64).reshape(self.n_rows, L)
+            path = [row[self.n_rows * L:].view(np.uint8).reshape(depth_sub, 32)] if depth_sub else []
+            off, n, node = 0, W, q
+            for _ in range(depth - depth_sub):  # siblings among / above the subtree roots
+                path.append(top[off + (node ^ 1)][None])
+                off += n
+                n //= 2
+                node >>= 1
+            out.append(LcColumn(col, np.concatenate(path) if path else np.empty((0, 32), np.uint8)))
         return out

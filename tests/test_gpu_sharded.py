@@ -35,8 +35,18 @@ def _worker(rank, world, port, fused, q):
         assert sc.fused == fused
         r0, cnt = row_partition(n_rows, world)[rank]
         local = torch.from_numpy(coeffs.reshape(n_rows, n_per_row)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
-        for _ in range(3):  # repeated commits reuse the symmetric buffer
+        for _ in range(3):  # repeated commits reuse the symmetric buffers
             sc.commit(local)
+        root_elems = sc.root() if rank == 0 else None
+        # the same commitment from file bytes (each element < 2^56, so packing 7-byte groups reproduces it)
+        file_bytes = (coeffs[:n].reshape(-1) & np.uint64((1 << 56) - 1)).view(np.uint8).reshape(-1, 8)[:, :7].reshape(-1)
+        lo, hi = sc.byte_range(file_bytes.shape[0])
+        sc2 = ShardedLigeroCommitter(enc, n_rows, None, fused=fused)
+        sc2.commit_bytes(torch.from_numpy(file_bytes[lo:hi].copy()).cuda())
+        if rank == 0:
+            exp2 = O.commit(O.pack_bytes7(file_bytes.tobytes()), O.LigeroEncoding(fid, n_per_row, n_cols))
+            assert sc2.root() == exp2.get_root()
+        sc.commit(local)
         hashes = sc.gather_hashes()
         tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, 1)
         folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda())
