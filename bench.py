@@ -132,12 +132,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload
+# (profiles/r01b_summary.md); None for kernels that were not captured
+NCU_DRAM_TRAFFIC = {"k_ntt_strided": 134_775_808 + 214_266_624, "k_ntt_block": 268_606_976 + 209_246_464,
+                    "k_hash_chunks": 268_456_448 + 9_687_040}
+
+
 # per-kernel compulsory HBM bytes for one launch at this workload (DESIGN.md "Kernels")
 def kernel_algorithmic_bytes(name: str, n_rows: int) -> int:
     enc = n_rows * N_COLS * 8
     return {
         "k_ntt_strided": n_rows * N_PER_ROW * 8 + enc,  # reads the coefficients, writes the widened rows
         "k_ntt_block": 2 * enc,                          # in place over the encoded matrix
+        "k_ntt_block_scatter": 2 * enc,                  # same pass, stores go to the owning ranks' column blocks
         "k_hash_chunks": enc + ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32,
         "k_hash_merge": ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32 + N_COLS * 32,
         "k_merkle_levels": 2 * N_COLS * 32,
@@ -312,6 +319,28 @@ def main() -> None:
                "d2h_bytes_per_step": ROWS_PER_GPU * N_COLS * 8 + (2 * np2 - 1) * 32, "ms_per_step": 1e3 * dt / e2e_steps,
                "steps": e2e_steps, "api": "lcpc_commit_host (pinned host coeffs in; LcCommit.comm + LcCommit.hashes out)"}
         assert bytes(h_hashes[-32:].numpy()).hex() == gpu_root, "e2e root differs from the device-resident root"
+        # informational: the same host call keeping the commitment resident in HBM (what a server that answers
+        # openings / folds from the handle needs): coefficients in, 32-byte root out
+        keep = C.c_void_p()
+        root_buf = torch.empty(32, dtype=torch.uint8).pin_memory()
+
+        def resident_step():
+            _lib.check(lib.lcpc_commit_host(enc.plan, h_coeffs.data_ptr(), n_local, None, None, None, C.byref(keep)))
+            _lib.check(lib.lcpc_commit_root(keep, root_buf.data_ptr()))
+            lib.lcpc_commit_free(keep)
+
+        for _ in range(2):
+            resident_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            resident_step()
+        torch.cuda.synchronize()
+        dt2 = time.perf_counter() - t0
+        e2e["resident_handle"] = {"value": n_local * e2e_steps / dt2, "ms_per_step": 1e3 * dt2 / e2e_steps,
+                                  "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": 32,
+                                  "api": "lcpc_commit_host(keep=handle) + lcpc_commit_root"}
+        assert bytes(root_buf.numpy()).hex() == gpu_root
     else:
         # sharded end to end: pinned host rows in, root (32 B) out on rank 0
         barrier()
@@ -345,7 +374,9 @@ def main() -> None:
         alg = kernel_algorithmic_bytes(name, ROWS_PER_GPU if world == 1 else ROWS_PER_GPU)
         ach = alg / (per_launch_ms * 1e-3) / 1e9 if alg else None
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / peak) if ach else None,
+                    "traffic": NCU_DRAM_TRAFFIC.get(name.replace("_scatter", "")) if world == 1 else None,
+                    "traffic_source": "ncu --set full, profiles/r01b_summary.md", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                     "share_of_step": total_ms / ms_total,
                     "kernels_ms_per_step": {k: v[1] / steps for k, v in kt.items()},

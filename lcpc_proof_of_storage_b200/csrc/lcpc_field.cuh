@@ -76,7 +76,7 @@ static __constant__ uint32_t LCPC_NEG1 = 0xffffffffu;
 namespace ft63 {
 constexpr uint64_t P = 0x46d0760000000001ull;
 constexpr uint32_t P_HI = 0x46d07600u;
-constexpr uint64_t REDC_C = ((uint64_t)P_HI << 32) + 1;  // added to columns 1 and 2 up front
+constexpr uint64_t NEG_P = 0 - P;                         // 2^64 - p
 
 __device__ __forceinline__ uint64_t wmul(uint32_t a, uint32_t b) {
     uint64_t d;
@@ -96,47 +96,44 @@ __device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) {
     return d;
 }
 
-// x in [0, 2p) -> x mod p
-__device__ __forceinline__ uint64_t csub(uint64_t x) {
-    const uint64_t t = x - P;
-    return (int64_t)t < 0 ? x : t;  // x < p  <=>  x - p wraps to >= 2^64 - p > 2^63
+// v in [-p, p) as a two's-complement 64-bit value -> v mod p in [0, p).  p < 2^63, so the sign bit of the
+// high word alone decides.  Callers fold the "- p" into work they do anyway (a + b + NEG_P is one
+// three-input carry chain; the Montgomery reduction leaves v - p for free), and the correction itself is
+// SHF + IADD3 on the ALU pipe and one IMAD.X (sign * P_HI + hi + carry) on the FMA pipe: 2 ALU slots
+// where compare + select needs 5.  The integer ALU pipe is what bounds the NTT (profiles/r01b_summary.md).
+__device__ __forceinline__ uint64_t fix(uint64_t v) {
+    uint32_t lo = lo32(v), hi = hi32(v);
+    asm("{ .reg .u32 m; shr.u32 m, %1, 31; add.cc.u32 %0, %0, m; madc.lo.u32 %1, m, 0x46d07600, %1; }" : "+r"(lo), "+r"(hi));
+    return pack(lo, hi);
 }
 
 // One Montgomery digit (2^-32) of the value  w + acc * 2^32  (w a 32-bit word, acc the 64 bits above
-// it, REDC_C already included in acc): with m = 2^32 - w (also for w = 0) the low word of
-// w + m*p is exactly 2^32, so the quotient is acc' = acc_orig + 1 + m*P_HI = acc + w*Q - w*2^32
-// (mod 2^64; the true value fits).  One IMAD.WIDE + one 32-bit IMAD, no carry flags.
+// it, P already included in acc): with m = 2^32 - w (also for w = 0) the low word of w + m*p is exactly
+// 2^32, so the quotient is acc' = acc_orig + 1 + m*P_HI = acc + w*Q - w*2^32 (mod 2^64; the true value
+// fits), Q = 2^32 - P_HI, and "+ 1 + 2^32*P_HI" is "+ P".  No carry flags, no compare.
 __device__ __forceinline__ uint64_t redc_digit(uint32_t w, uint64_t acc) {
-    const uint64_t u = wmad(w, LCPC_FT63_Q, acc);
-    return pack(lo32(u), hi32(u) + w * LCPC_NEG1);
+    const uint64_t u = acc + wmul(w, LCPC_FT63_Q);
+    return pack(lo32(u), hi32(u) - w);
 }
 
-// Montgomery reduction of col0 + (col1 - C)*2^32 + (col2 - C)*2^64 with C = REDC_C pre-added to
-// columns 1 and 2; columns are sums of 32x32 products, not carry-normalised.  Result in [0, p)
-// for inputs that are products of reduced elements.
-__device__ __forceinline__ uint64_t redc_cols(uint64_t col0, uint64_t col1, uint64_t col2) {
-    const uint32_t one = LCPC_ONE;
-    col1 = wmad(hi32(col0), one, col1);
-    const uint64_t u = redc_digit(lo32(col0), col1);
-    col2 = wmad(hi32(u), one, col2);
-    const uint64_t v = redc_digit(lo32(u), col2);
-    return csub(v);
+// Montgomery reduction of p00 + col1*2^32 + p11*2^64 (sums of 32x32 products, not carry-normalised;
+// col1 < 2.9 * 2^62).  The second digit's "+ P" is left out, so the digit chain ends on v - p in [-p, p)
+// and fix() finishes.  Result in [0, p).
+__device__ __forceinline__ uint64_t redc_cols(uint64_t p00, uint64_t col1, uint64_t p11) {
+    const uint64_t u = redc_digit(lo32(p00), col1 + P + hi32(p00));
+    const uint64_t v = redc_digit(lo32(u), p11 + hi32(u));
+    return fix(v);
 }
 
 // a*b*2^-64 mod p, a, b < p
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
     const uint32_t a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
-    return redc_cols(wmul(a0, b0), wmad(a1, b0, wmad(a0, b1, REDC_C)), wmad(a1, b1, REDC_C));
+    return redc_cols(wmul(a0, b0), wmul(a0, b1) + wmul(a1, b0), wmul(a1, b1));
 }
 // a*2^-64 mod p
-__device__ __forceinline__ uint64_t to_canon(uint64_t a) {
-    return redc_cols((uint64_t)lo32(a), (uint64_t)hi32(a) + REDC_C, REDC_C);
-}
-__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return csub(a + b); }
-__device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) {
-    const uint64_t d = a - b;
-    return a < b ? d + P : d;
-}
+__device__ __forceinline__ uint64_t to_canon(uint64_t a) { return redc_cols((uint64_t)lo32(a), (uint64_t)hi32(a), 0); }
+__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return fix(a + b + NEG_P); }
+__device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return fix(a - b); }
 }  // namespace ft63
 
 // Compile-time field description: P(i) etc. are constexpr calls that fold to
@@ -224,8 +221,7 @@ struct Field {
     __device__ __forceinline__ static E add(const E &a, const E &b) {
         E r;
         if constexpr (LIMBS == 1) {
-            uint64_t s = a.v[0] + b.v[0];  // < 2^64: both < p < 2^63
-            r.v[0] = s >= P(0) ? s - P(0) : s;
+            r.v[0] = ft63::add(a.v[0], b.v[0]);
         } else {
             uint32_t x[2 * LIMBS], y[2 * LIMBS], z[2 * LIMBS];
             split(x, a);
@@ -239,8 +235,7 @@ struct Field {
     __device__ __forceinline__ static E sub(const E &a, const E &b) {
         E r;
         if constexpr (LIMBS == 1) {
-            uint64_t d = a.v[0] - b.v[0];
-            r.v[0] = a.v[0] < b.v[0] ? d + P(0) : d;
+            r.v[0] = ft63::sub(a.v[0], b.v[0]);
         } else {
             uint32_t x[2 * LIMBS], y[2 * LIMBS], z[2 * LIMBS];
             split(x, a);
