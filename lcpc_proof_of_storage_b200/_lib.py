@@ -126,7 +126,8 @@ def load():
         return _lib
     from . import build as _build
 
-    path = _build.build()
+    # LCPC_B200_LIB: load another build of the same library (kernel experiments); still no fallback
+    path = os.environ.get("LCPC_B200_LIB") or _build.build()
     lib = C.CDLL(path)
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(lib, name)

@@ -20,6 +20,10 @@
 #include "lcpc_field.cuh"
 #include "lcpc_kernels.h"
 
+#ifndef LCPC_NTT_CTAS1
+#define LCPC_NTT_CTAS1 3  // resident 256-thread CTAs per SM for the one-limb field (register budget 80)
+#endif
+
 namespace lcpc {
 
 template <int FID>
@@ -94,7 +98,7 @@ __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], c
 // ------------------------------------------------------------------ strided pass
 
 template <int FID, int R>
-__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 2)
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? LCPC_NTT_CTAS1 : 2)
 k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows,
               int log_sub, const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
     using F = Field<FID>;
@@ -133,25 +137,36 @@ k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t
 
 // ------------------------------------------------------------------ shared-memory block pass
 
-__device__ __forceinline__ size_t sm_phys(size_t i) { return i + (i >> 4); }
+// shared-memory indices are 32-bit on purpose: 64-bit index arithmetic doubles the SHF/IADD3 count on the
+// ALU pipe, which is the pipe that bounds these kernels
+__device__ __forceinline__ unsigned sm_phys(unsigned i) { return i + (i >> 4); }
 
-template <int FID, int R, bool TW>
-__device__ __forceinline__ void block_substep(uint64_t *sm, size_t plane, int LB, int log_sub,
-                                              const uint64_t *__restrict__ tw, const SmallTw<FID> &stw) {
+// GSRC: the sub-step takes its inputs straight from global memory (the first sub-step of a block: adjacent
+// threads own adjacent elements, so the loads are full lines and the staging copy into shared memory, one
+// STS + LDS per element and a barrier, is skipped); elements at or beyond `valid` read as zero.
+template <int FID, int R, bool TW, bool GSRC>
+__device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                              const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
+                                              const uint64_t *__restrict__ gsrc, unsigned valid) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
     const int log_n2 = log_sub - R;
-    const size_t groups = ((size_t)1 << LB) >> R;
-    for (size_t g = threadIdx.x; g < groups; g += blockDim.x) {
-        const size_t hi = g >> log_n2, lo = g & (((size_t)1 << log_n2) - 1);
-        const size_t base = (hi << log_sub) + lo;
+    const unsigned groups = (1u << LB) >> R;
+    for (unsigned g = threadIdx.x; g < groups; g += blockDim.x) {
+        const unsigned hi = g >> log_n2, lo = g & ((1u << log_n2) - 1);
+        const unsigned base = (hi << log_sub) + lo;
         E x[1 << R];
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
-            const size_t p = sm_phys(base + ((size_t)m << log_n2));
+            const unsigned i = base + ((unsigned)m << log_n2);
+            if constexpr (GSRC) {
+                x[m] = i < valid ? ld_fe<L>(gsrc + (size_t)i * L) : F::zero();
+            } else {
+                const unsigned p = sm_phys(i);
 #pragma unroll
-            for (int l = 0; l < L; l++) x[m].v[l] = sm[l * plane + p];
+                for (int l = 0; l < L; l++) x[m].v[l] = sm[l * plane + p];
+            }
         }
         radix_dif<FID, R>(x, stw);
         if constexpr (TW) {
@@ -159,33 +174,49 @@ __device__ __forceinline__ void block_substep(uint64_t *sm, size_t plane, int LB
                 // all pass twiddles of this group in flight together (one exposed L1/L2 latency, not 2^R - 1)
                 E t[1 << R];
 #pragma unroll
-                for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
+                for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((unsigned)m << log_n2) + lo) * L);
 #pragma unroll
                 for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
             } else {
                 // wide elements: keep one twiddle live at a time (register pressure decides occupancy here)
 #pragma unroll
-                for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
+                for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (size_t)(((unsigned)m << log_n2) + lo) * L));
             }
         }
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
-            const size_t p = sm_phys(base + ((size_t)m << log_n2));
+            const unsigned p = sm_phys(base + ((unsigned)m << log_n2));
 #pragma unroll
             for (int l = 0; l < L; l++) sm[l * plane + p] = x[m].v[l];
         }
     }
 }
 
-template <int FID, int R>
-__device__ __forceinline__ void block_substep_any(uint64_t *sm, size_t plane, int LB, int log_sub,
-                                                  const uint64_t *__restrict__ tw, const SmallTw<FID> &stw) {
-    if (log_sub - R > 0) block_substep<FID, R, true>(sm, plane, LB, log_sub, tw, stw);
-    else block_substep<FID, R, false>(sm, plane, LB, log_sub, tw, stw);
+template <int FID, int R, bool GSRC>
+__device__ __forceinline__ void block_substep_any(uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                                  const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
+                                                  const uint64_t *__restrict__ gsrc, unsigned valid) {
+    if (log_sub - R > 0) block_substep<FID, R, true, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    else block_substep<FID, R, false, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+}
+
+template <int FID, int RMAX, bool GSRC>
+__device__ __forceinline__ void block_substep_r(int R, uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                                const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
+                                                const uint64_t *__restrict__ gsrc, unsigned valid) {
+    if (R == 4) {
+        if constexpr (RMAX >= 4) block_substep_any<FID, 4, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    } else if (R == 3) {
+        block_substep_any<FID, 3, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    } else if (R == 2) {
+        block_substep_any<FID, 2, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    } else {
+        block_substep_any<FID, 1, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    }
 }
 
 template <int FID, int RMAX, bool SCATTER>
-__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? 3 : 2)
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? LCPC_NTT_CTAS1 : 2)
 k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows, int LB,
             const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw,
             const __grid_constant__ ScatterDst sc) {
@@ -193,39 +224,27 @@ k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *
     using E = typename F::E;
     constexpr int L = F::LIMBS;
     extern __shared__ uint64_t sm[];
-    const size_t NB = (size_t)1 << LB;
-    const size_t plane = NB + (NB >> 4) + 1;
+    const unsigned NB = 1u << LB;
+    const unsigned plane = NB + (NB >> 4) + 1;
     const size_t col0 = (size_t)blockIdx.x << LB;
+    const unsigned valid = src_valid > col0 ? (unsigned)(src_valid - col0 < NB ? src_valid - col0 : NB) : 0u;
     for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
-        for (size_t i = threadIdx.x; i < NB; i += blockDim.x) {
-            const size_t idx = col0 + i;
-            E v = idx < src_valid ? ld_fe<L>(src + (row * src_stride + idx) * L) : F::zero();
-            const size_t p = sm_phys(i);
-#pragma unroll
-            for (int l = 0; l < L; l++) sm[l * plane + p] = v.v[l];
-        }
-        __syncthreads();
         int log_sub = LB;
         size_t tw_off = 0;
+        bool first = true;
         while (log_sub > 0) {
             const int R = log_sub < RMAX ? log_sub : RMAX;
             const uint64_t *t = tw + tw_off * L;
-            if (R == 4) {
-                if constexpr (RMAX >= 4) block_substep_any<FID, 4>(sm, plane, LB, log_sub, t, stw);
-            } else if (R == 3) {
-                block_substep_any<FID, 3>(sm, plane, LB, log_sub, t, stw);
-            } else if (R == 2) {
-                block_substep_any<FID, 2>(sm, plane, LB, log_sub, t, stw);
-            } else {
-                block_substep_any<FID, 1>(sm, plane, LB, log_sub, t, stw);
-            }
+            if (first) block_substep_r<FID, RMAX, true>(R, sm, plane, LB, log_sub, t, stw, src + (row * src_stride + col0) * L, valid);
+            else block_substep_r<FID, RMAX, false>(R, sm, plane, LB, log_sub, t, stw, nullptr, 0u);
+            first = false;
             if (log_sub - R > 0) tw_off += (size_t)1 << log_sub;
             log_sub -= R;
             __syncthreads();
         }
-        for (size_t i = threadIdx.x; i < NB; i += blockDim.x) {
+        for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) {
             E v;
-            const size_t p = sm_phys(i);
+            const unsigned p = sm_phys(i);
 #pragma unroll
             for (int l = 0; l < L; l++) v.v[l] = sm[l * plane + p];
             if constexpr (SCATTER) {
