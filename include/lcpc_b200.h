@@ -298,6 +298,43 @@ int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_
 /* 7-byte packing (WriteableFt63::from_data_bytes): n_elems = ceil(n_bytes/7) limbs written. */
 int32_t lcpc_dev_pack_bytes7(lcpc_ctx *ctx, const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems);
 
+/* ---------------------------------------------------------------------------------------------
+ * Streaming commit -- proof-of-storage's EncodedFileWriter + ColumnDigestAccumulator
+ * (src/lcpc_online/encoded_file_writer.rs:33-508, column_digest_accumulator.rs:17-118,
+ * row_generator_iter.rs): rows arrive in order, are encoded block by block, folded into the column
+ * digests one BLAKE3 chunk at a time and (optionally) appended to the column-major encoded file.
+ * Device memory is O(block_rows * n_cols); the file never has to fit in HBM.
+ *
+ *   max_rows           upper bound on the rows that will be pushed (sizes the chaining-value store:
+ *                      32 bytes per column per KiB of column)
+ *   block_rows         rows encoded per step; 0 picks about 256 MiB of encoded rows
+ *   sink               nullable host image of the encoded file (e.g. an mmap of the .porenc file):
+ *                      element (r, c) is written as its canonical to_repr bytes at
+ *                      sink[(c*sink_row_capacity + r) * 8*LIMBS] (encoded_file_writer.rs:327-349,
+ *                      fields/data_field.rs:62-70); sink_row_capacity = the writer's row_capacity
+ * push_elems / push_bytes take whole rows (n_per_row elements, or 7*n_per_row file bytes for the 63-bit
+ * field, data_field.rs:38-46); only the final push may end inside a row, which is zero padded
+ * (LCPC_ERR_DIMS if a later push follows).  finish hashes the last chunk, merges the chunk chaining
+ * values into the leaves and builds the tree; hashes_out receives (2*np2-1)*32 bytes = the .portree
+ * image (merkle_tree.rs:61-86).  The result equals lcpc_commit_host / lcpc_commit_bytes_host on the
+ * concatenated input (row_generator_iter.rs:286-364 tests this for the reference). */
+typedef struct lcpc_stream lcpc_stream;
+int32_t lcpc_stream_begin(lcpc_plan *plan, size_t max_rows, size_t block_rows, uint8_t *sink,
+                          size_t sink_row_capacity, lcpc_stream **out);
+int32_t lcpc_stream_push_elems_host(lcpc_stream *s, const uint64_t *elems, size_t n_elems);
+int32_t lcpc_stream_push_bytes_host(lcpc_stream *s, const uint8_t *bytes, size_t n_bytes);
+int32_t lcpc_stream_finish(lcpc_stream *s, uint8_t *hashes_out, size_t *n_rows_out);
+void lcpc_stream_free(lcpc_stream *s);
+
+/* Row edit on a device-resident commitment -- FileHandler::edit_bytes -> reencode_row ->
+ * recalculate_merkle_tree (src/lcpc_online/file_handler.rs:279-402, 474-481).  Replaces coefficient rows
+ * [row0, row0 + n_rows) (coeff_rows: n_rows * n_per_row elements, zero padded by the caller), re-encodes
+ * exactly those rows, re-hashes only the BLAKE3 chunks of the column leaves that contain them, and
+ * rebuilds the tree.  comm_rows_out (nullable) receives the n_rows re-encoded rows, hashes_out (nullable)
+ * the whole tree.  LCPC_ERR_DIMS when the range leaves the committed rows. */
+int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
+                                     uint64_t *comm_rows_out, uint8_t *hashes_out);
+
 /* number of kernels this library has launched on this context since creation */
 uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx);
 /* Per-kernel device timing: when enabled, every launch on this context is bracketed by

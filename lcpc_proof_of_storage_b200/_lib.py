@@ -55,6 +55,12 @@ _SIGNATURES = {
     "lcpc_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "lcpc_ctx_kernel_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
     "lcpc_ctx_kernel_timing_report": (C.c_char_p, [C.c_void_p]),
+    "lcpc_stream_begin": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, vpp]),
+    "lcpc_stream_push_elems_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "lcpc_stream_push_bytes_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "lcpc_stream_finish": (C.c_int32, [C.c_void_p, C.c_void_p, szp]),
+    "lcpc_stream_free": (None, [C.c_void_p]),
+    "lcpc_commit_update_rows_host": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcpc_plan_ligero": (C.c_int32, [C.c_void_p, C.c_int32, C.c_size_t, C.c_size_t, u64p, vpp]),
     "lcpc_plan_brakedown": (C.c_int32, [C.c_void_p, C.c_int32, C.c_size_t, C.c_size_t, C.c_size_t,
                                         C.POINTER(LcpcCsc), C.POINTER(LcpcCsc), vpp]),

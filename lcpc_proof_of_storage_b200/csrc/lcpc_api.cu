@@ -80,13 +80,23 @@ int32_t upload_csr(const lcpc_csc &a, int L, DevCsr &out) {
     return LCPC_OK;
 }
 
+// d_cvs_keep: where the chunk chaining values go when the caller keeps them (a commit handle); a
+// stream-ordered scratch buffer otherwise
 int32_t merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_rows, size_t n_cols, size_t np2,
-                      uint8_t *d_hashes) {
+                      uint8_t *d_hashes, uint8_t **d_cvs_keep = nullptr) {
     // padding leaves n_cols..np2 stay all-zero (lib.rs:685-695)
     if (np2 > n_cols) CU(cudaMemsetAsync(d_hashes + n_cols * 32, 0, (np2 - n_cols) * 32, ctx->stream));
     DevBuf scratch;
-    CU(scratch.alloc(hash_scratch_bytes(fid, n_rows, n_cols), ctx->stream));
-    CU(hash_columns(fid, d_comm, n_rows, n_cols, n_cols, nullptr, d_hashes, scratch.as<uint8_t>(), ctx->lc()));
+    uint8_t *cvs = nullptr;
+    const size_t cv_bytes = hash_scratch_bytes(fid, n_rows, n_cols);
+    if (d_cvs_keep && cv_bytes) {
+        CU(cudaMallocAsync((void **)d_cvs_keep, cv_bytes, ctx->stream));
+        cvs = *d_cvs_keep;
+    } else {
+        CU(scratch.alloc(cv_bytes, ctx->stream));
+        cvs = scratch.as<uint8_t>();
+    }
+    CU(hash_columns(fid, d_comm, n_rows, n_cols, n_cols, nullptr, d_hashes, cvs, ctx->lc()));
     CU(merkle_tree(d_hashes, np2, ctx->lc()));
     return LCPC_OK;
 }
@@ -125,6 +135,7 @@ void commit_release(lcpc_commit *c) {
         if (c->d_coeffs) cudaFreeAsync(c->d_coeffs, s);
         if (c->d_comm) cudaFreeAsync(c->d_comm, s);
         if (c->d_hashes) cudaFreeAsync(c->d_hashes, s);
+        if (c->d_cvs) cudaFreeAsync(c->d_cvs, s);
     }
     lcpc_plan *plan = c->plan;
     delete c;
@@ -140,7 +151,7 @@ int32_t commit_finish(lcpc_plan *plan, lcpc_commit *c, uint64_t *coeffs_out, uin
     CU(cudaMallocAsync((void **)&c->d_hashes, (2 * c->np2 - 1) * 32, ctx->stream));
     int32_t rc = encode_dev(plan, c->d_coeffs, c->n_rows, c->d_comm);
     if (rc != LCPC_OK) return rc;
-    rc = merkleize_dev(ctx, plan->fid, c->d_comm, c->n_rows, c->n_cols, c->np2, c->d_hashes);
+    rc = merkleize_dev(ctx, plan->fid, c->d_comm, c->n_rows, c->n_cols, c->np2, c->d_hashes, &c->d_cvs);
     if (rc != LCPC_OK) return rc;
     if (coeffs_out)
         CU(cudaMemcpyAsync(coeffs_out, c->d_coeffs, c->n_rows * c->n_per_row * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -195,7 +206,7 @@ int32_t commit_host_pipelined(lcpc_plan *plan, lcpc_commit *c, const uint64_t *h
         if (coeffs_out)
             CU(cudaMemcpyAsync(coeffs_out + e0 * L, c->d_coeffs + e0 * L, (e1 - e0) * wbytes, cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    int32_t rc = merkleize_dev(ctx, plan->fid, c->d_comm, n_rows, n_cols, c->np2, c->d_hashes);
+    int32_t rc = merkleize_dev(ctx, plan->fid, c->d_comm, n_rows, n_cols, c->np2, c->d_hashes, &c->d_cvs);
     if (rc != LCPC_OK) return rc;
     if (hashes_out)
         CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));

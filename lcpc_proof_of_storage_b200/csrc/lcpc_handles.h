@@ -80,6 +80,9 @@ struct lcpc_commit {
     uint64_t *d_coeffs = nullptr;
     uint64_t *d_comm = nullptr;
     uint8_t *d_hashes = nullptr;
+    // BLAKE3 chunk chaining values of every column, [chunk][column][32 B] (null when a leaf is a single chunk):
+    // kept so that a row edit re-hashes only the chunks it touches (lcpc_commit_update_rows_host)
+    uint8_t *d_cvs = nullptr;
     std::mutex mu;
 };
 

@@ -24,7 +24,7 @@ namespace lcpc {
 // for column `col`.  Stream = 8 zero words, then 2L words per row.
 template <int FID>
 __device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t *__restrict__ mat, size_t n_rows,
-                                                 size_t row_stride, size_t col, uint64_t B) {
+                                                 size_t row_stride, size_t col, uint64_t B, int64_t row_base) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
@@ -43,7 +43,7 @@ __device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t 
         for (int e = 0; e < EPB; e++) {
             const int64_t row = (int64_t)(ve0 + e) - K;
             E c = F::zero();
-            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)row * row_stride + col) * L));
+            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L));
 #pragma unroll
             for (int l = 0; l < L; l++) {
                 m[e * WPE + 2 * l] = (uint32_t)c.v[l];
@@ -58,7 +58,7 @@ __device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t 
         for (int e = 0; e < NE; e++) {
             const int64_t row = (int64_t)(ve0 + e) - K;
             E c = F::zero();
-            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)row * row_stride + col) * L));
+            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L));
 #pragma unroll
             for (int l = 0; l < L; l++) {
                 w[e * WPE + 2 * l] = (uint32_t)c.v[l];
@@ -94,11 +94,11 @@ struct BlockElems {
     typename Field<FID>::E e[EPB];
 
     __device__ __forceinline__ void load(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t col,
-                                         uint64_t B) {
+                                         uint64_t B, int64_t row_base) {
 #pragma unroll
         for (int i = 0; i < EPB; i++) {
             const int64_t row = (int64_t)(B * EPB + i) - K;
-            e[i] = (row >= 0 && (uint64_t)row < n_rows) ? ld_fe<L>(mat + ((size_t)row * row_stride + col) * L)
+            e[i] = (row >= 0 && (uint64_t)row < n_rows) ? ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L)
                                                         : Field<FID>::zero();
         }
     }
@@ -119,27 +119,31 @@ struct BlockElems {
 // One thread per (column, chunk): chaining value of that chunk, or the leaf itself when
 // the whole message is a single chunk.  The loads of block b+1 are issued before block b is
 // compressed, so the L2/HBM latency hides behind ~900 ALU instructions.
+// `mat` may be a window of the matrix: its first row is global row `row_base`, rows in [0, n_rows) are
+// valid (the rest of the byte stream reads as zero), and only chunks [chunk0, chunk_end) are computed
+// (streaming commits hash chunks as their rows arrive; row edits re-hash only the chunks they touch).
 template <int FID>
 __global__ void __launch_bounds__(128)
 k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
-              const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks, uint32_t *__restrict__ out) {
+              const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks, uint32_t *__restrict__ out,
+              int64_t row_base, uint64_t chunk0, uint64_t chunk_end) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_cols) return;
     const size_t col = col_idx ? (size_t)col_idx[j] : j;
-    for (uint64_t c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+    for (uint64_t c = chunk0 + blockIdx.y; c < chunk_end; c += gridDim.y) {
         const uint64_t chunk_bytes = (c + 1 == n_chunks) ? total_bytes - c * b3::CHUNK_BYTES : b3::CHUNK_BYTES;
         const uint32_t nb = (uint32_t)((chunk_bytes + b3::BLOCK_BYTES - 1) / b3::BLOCK_BYTES);
         uint32_t cv[8];
         b3::set_iv(cv);
         BlockElems<FID> cur, nxt;
-        if constexpr (BlockElems<FID>::WHOLE) cur.load(mat, n_rows, row_stride, col, c * 16);
+        if constexpr (BlockElems<FID>::WHOLE) cur.load(mat, n_rows, row_stride, col, c * 16, row_base);
         for (uint32_t b = 0; b < nb; b++) {
             uint32_t m[16];
             if constexpr (BlockElems<FID>::WHOLE) {
-                if (b + 1 < nb) nxt.load(mat, n_rows, row_stride, col, c * 16 + b + 1);
+                if (b + 1 < nb) nxt.load(mat, n_rows, row_stride, col, c * 16 + b + 1, row_base);
                 cur.words(m);
             } else {
-                load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b);
+                load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b, row_base);
             }
             uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
             uint32_t len = b3::BLOCK_BYTES;
@@ -211,7 +215,7 @@ static cudaError_t hash_columns_t(const uint64_t *d_mat, size_t n_rows, size_t r
     const unsigned gy = (unsigned)(nc < 65535 ? nc : 65535);
     uint32_t *out = nc == 1 ? reinterpret_cast<uint32_t *>(d_leaves) : reinterpret_cast<uint32_t *>(d_cv_scratch);
     lc.begin("k_hash_chunks");
-    k_hash_chunks<FID><<<dim3(gx, gy), 128, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_col_idx, total, nc, out);
+    k_hash_chunks<FID><<<dim3(gx, gy), 128, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_col_idx, total, nc, out, 0, 0, nc);
     lc.end();
     if (nc > 1) {
         lc.begin("k_hash_merge");
@@ -219,6 +223,101 @@ static cudaError_t hash_columns_t(const uint64_t *d_mat, size_t n_rows, size_t r
                                         reinterpret_cast<uint32_t *>(d_leaves));
         lc.end();
     }
+    return cudaGetLastError();
+}
+
+template <int FID>
+static cudaError_t hash_chunk_range_t(const uint64_t *d_mat, int64_t row_base, size_t n_rows_valid, size_t row_stride,
+                                      size_t n_cols, uint64_t chunk0, uint64_t chunk_end, uint64_t total_bytes,
+                                      uint64_t n_chunks_total, uint8_t *d_cvs, const Launch &lc) {
+    if (n_cols == 0 || chunk_end <= chunk0) return cudaSuccess;
+    const unsigned gx = (unsigned)((n_cols + 127) / 128);
+    const uint64_t todo = chunk_end - chunk0;
+    const unsigned gy = (unsigned)(todo < 65535 ? todo : 65535);
+    lc.begin("k_hash_chunks");
+    k_hash_chunks<FID><<<dim3(gx, gy), 128, 0, lc.s>>>(d_mat, n_rows_valid, row_stride, n_cols, nullptr, total_bytes,
+                                                    n_chunks_total, reinterpret_cast<uint32_t *>(d_cvs), row_base, chunk0,
+                                                    chunk_end);
+    lc.end();
+    return cudaGetLastError();
+}
+
+cudaError_t hash_chunk_range(int fid, const uint64_t *d_mat, int64_t row_base, size_t n_rows_valid, size_t row_stride,
+                             size_t n_cols, uint64_t chunk0, uint64_t chunk_end, uint64_t total_bytes,
+                             uint64_t n_chunks_total, uint8_t *d_cvs, const Launch &lc) {
+#define LCPC_HCR(F) hash_chunk_range_t<F>(d_mat, row_base, n_rows_valid, row_stride, n_cols, chunk0, chunk_end, total_bytes, n_chunks_total, d_cvs, lc)
+    switch (fid) {
+    case FT63: return LCPC_HCR(FT63);
+    case FT127: return LCPC_HCR(FT127);
+    case FT191: return LCPC_HCR(FT191);
+    case FT255: return LCPC_HCR(FT255);
+    default: return cudaErrorInvalidValue;
+    }
+#undef LCPC_HCR
+}
+
+cudaError_t hash_merge(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves, const Launch &lc) {
+    if (n_cols == 0) return cudaSuccess;
+    if (n_chunks <= 1) {  // a single chunk is its own (ROOT-flagged) leaf
+        if (d_cvs != d_leaves) return cudaMemcpyAsync(d_leaves, d_cvs, n_cols * 32, cudaMemcpyDeviceToDevice, lc.s);
+        return cudaSuccess;
+    }
+    lc.begin("k_hash_merge");
+    k_hash_merge<<<(unsigned)((n_cols + 127) / 128), 128, 0, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, n_chunks,
+                                                                  reinterpret_cast<uint32_t *>(d_leaves));
+    lc.end();
+    return cudaGetLastError();
+}
+
+uint64_t hash_leaf_bytes(int fid, size_t n_rows) { return leaf_bytes(fid, n_rows); }
+uint64_t hash_leaf_chunks(int fid, size_t n_rows) { return leaf_chunks(fid, n_rows); }
+
+// ------------------------------------------------------------------ column-major emit
+
+// out[c][r] = canonical little-endian repr of mat[r][c]: the layout of proof-of-storage's encoded file
+// (lcpc_online/encoded_file_writer.rs:327-349: column c at byte c*row_capacity*w, row r at +r*w;
+// fields/data_field.rs:62-70: to_repr bytes).  32 x 32 element tiles through shared memory so that both the
+// row-major loads and the column-major stores are full lines.
+template <int FID>
+__global__ void __launch_bounds__(256) k_emit_colmajor(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride,
+                                                       size_t n_cols, uint64_t *__restrict__ out, size_t out_col_stride) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    __shared__ uint64_t tile[L][32][33];
+    const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t r = r0 + ty + 8 * k, c = c0 + tx;
+        typename F::E v = F::zero();
+        if (r < n_rows && c < n_cols) v = F::to_canon(ld_fe<L>(mat + (r * row_stride + c) * L));
+#pragma unroll
+        for (int l = 0; l < L; l++) tile[l][ty + 8 * k][tx] = v.v[l];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < n_rows && c < n_cols) {
+#pragma unroll
+            for (int l = 0; l < L; l++) out[(c * out_col_stride + r) * L + l] = tile[l][tx][ty + 8 * k];
+        }
+    }
+}
+
+cudaError_t emit_colmajor(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t *d_out,
+                          size_t out_col_stride, const Launch &lc) {
+    if (n_rows == 0 || n_cols == 0) return cudaSuccess;
+    const dim3 grid((unsigned)((n_cols + 31) / 32), (unsigned)((n_rows + 31) / 32));
+    lc.begin("k_emit_colmajor");
+    switch (fid) {
+    case FT63: k_emit_colmajor<FT63><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
+    case FT127: k_emit_colmajor<FT127><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
+    case FT191: k_emit_colmajor<FT191><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
+    case FT255: k_emit_colmajor<FT255><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
+    default: return cudaErrorInvalidValue;
+    }
+    lc.end();
     return cudaGetLastError();
 }
 

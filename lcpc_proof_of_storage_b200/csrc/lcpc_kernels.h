@@ -80,6 +80,23 @@ size_t hash_scratch_bytes(int fid, size_t n_rows, size_t n_cols);
 cudaError_t hash_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols,
                          const uint64_t *d_col_idx, uint8_t *d_leaves, uint8_t *d_cv_scratch, const Launch &lc);
 
+// Pieces of hash_columns for streaming commits and row edits.  The leaf of a column is the BLAKE3 tree over
+// its 1 KiB chunks; chunk chaining values live in d_cvs as [chunk][column][32 bytes].  hash_chunk_range
+// computes chunks [chunk0, chunk_end) from a row window of the matrix (d_mat's first row is global row
+// row_base; global rows >= n_rows_valid read as zero); total_bytes / n_chunks_total describe the whole
+// leaf and matter only for the final chunk (length, ROOT flag when it is the only one) -- pass
+// UINT64_MAX for both while more rows are still to come.  hash_merge folds the chaining values.
+uint64_t hash_leaf_bytes(int fid, size_t n_rows);
+uint64_t hash_leaf_chunks(int fid, size_t n_rows);
+cudaError_t hash_chunk_range(int fid, const uint64_t *d_mat, int64_t row_base, size_t n_rows_valid, size_t row_stride,
+                             size_t n_cols, uint64_t chunk0, uint64_t chunk_end, uint64_t total_bytes,
+                             uint64_t n_chunks_total, uint8_t *d_cvs, const Launch &lc);
+cudaError_t hash_merge(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves, const Launch &lc);
+
+// d_out[c * out_col_stride + r] = canonical repr of d_mat[r][c] (proof-of-storage's column-major encoded file)
+cudaError_t emit_colmajor(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t *d_out,
+                          size_t out_col_stride, const Launch &lc);
+
 cudaError_t merkle_tree(uint8_t *d_hashes, size_t n_leaves, const Launch &lc);
 
 // out[t][j] = sum_r tensors[t][r] * mat[r][j].  d_scratch needs fold_scratch_bytes().

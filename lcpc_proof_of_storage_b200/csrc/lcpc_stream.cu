@@ -1,0 +1,293 @@
+// Streaming commit and in-place row edits: the proof-of-storage file path beyond one resident matrix.
+//
+// lcpc_stream_* stands in for proof-of-storage's EncodedFileWriter + ColumnDigestAccumulator
+// (src/lcpc_online/encoded_file_writer.rs:33-508, column_digest_accumulator.rs:17-118): rows arrive in order,
+// each is encoded, folded into every column's running digest and appended to a column-major encoded file.
+// The reference keeps one BLAKE3 hasher per column and feeds it 8 bytes per row; here a block of rows is
+// encoded at once and the column digests advance one BLAKE3 *chunk* (1 KiB = 128 rows of Ft63) at a time:
+// chunk chaining values are independent, so a chunk is hashed as soon as one byte beyond it exists and its
+// rows can be dropped.  Device memory is O(block_rows * n_cols), not O(file).
+//
+// lcpc_commit_update_rows_host stands in for FileHandler::edit_bytes -> reencode_row ->
+// recalculate_merkle_tree (src/lcpc_online/file_handler.rs:279-402, 474-481): the edited rows are re-encoded
+// and only the chunks of the column leaves that contain them are re-hashed (the reference re-reads and
+// re-hashes every column from disk).
+#include <algorithm>
+#include <thread>
+
+#include "lcpc_handles.h"
+
+using namespace lcpc;
+using namespace lcpc::abi;
+
+struct lcpc_stream {
+    lcpc_plan *plan = nullptr;
+    int fid = 0, L = 1;
+    size_t n_per_row = 0, n_cols = 0, np2 = 0, wbytes = 8;
+    size_t max_rows = 0, block_rows = 0, pend_cap = 0;
+    uint64_t *d_in = nullptr;       // block_rows x n_per_row coefficient staging
+    uint8_t *d_bytes = nullptr;     // block_rows x n_per_row x 7 raw file bytes (63-bit field only)
+    uint64_t *d_pend[2] = {nullptr, nullptr};  // encoded rows not yet consumed by the column digests
+    int cur = 0;
+    size_t pend_rows = 0, pend_base = 0;
+    uint8_t *d_cvs = nullptr;       // [chunk][column][32]
+    uint64_t chunks_cap = 0, chunks_done = 0;
+    uint8_t *d_hashes = nullptr;
+    uint64_t *d_col = nullptr;      // [n_cols][block_rows] canonical reprs (column-major emit)
+    uint8_t *h_col = nullptr;       // pinned mirror of d_col
+    uint8_t *sink = nullptr;        // host image of the encoded file (may be an mmap), column c at c*sink_cap*w
+    size_t sink_cap = 0;
+    size_t rows_total = 0, elems_total = 0;
+    bool ragged = false, finished = false;
+    std::mutex mu;
+};
+
+namespace {
+
+void stream_release(lcpc_stream *s) {
+    if (!s) return;
+    lcpc_plan *plan = s->plan;
+    if (plan) {
+        cudaStream_t st = plan->ctx->stream;
+        cudaSetDevice(plan->ctx->device);
+        cudaStreamSynchronize(st);
+        for (void *p : {(void *)s->d_in, (void *)s->d_bytes, (void *)s->d_pend[0], (void *)s->d_pend[1], (void *)s->d_cvs,
+                        (void *)s->d_hashes, (void *)s->d_col})
+            if (p) cudaFree(p);
+        if (s->h_col) cudaFreeHost(s->h_col);
+    }
+    delete s;
+    if (plan) lcpc_plan_destroy(plan);  // drops the stream's reference (handles are reference counted)
+}
+
+// rows [row0, row0 + nr) of the column-major block in h_col -> the sink image
+void scatter_to_sink(lcpc_stream *s, size_t row0, size_t nr) {
+    const size_t w = s->wbytes, n_cols = s->n_cols;
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned nt = n_cols * nr * w < (1u << 20) ? 1u : hw;
+    auto work = [&](unsigned t) {
+        for (size_t c = t; c < n_cols; c += nt)
+            memcpy(s->sink + (c * s->sink_cap + row0) * w, s->h_col + c * nr * w, nr * w);
+    };
+    if (nt == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+}
+
+// one block of rows is in d_in (padded with zeros): encode, emit, advance the digests
+int32_t process_block(lcpc_stream *s, size_t nr) {
+    lcpc_plan *plan = s->plan;
+    lcpc_ctx *ctx = plan->ctx;
+    const int L = s->L;
+    const size_t n_cols = s->n_cols, w = s->wbytes;
+    if (s->rows_total + nr > s->max_rows) return fail(LCPC_ERR_TOO_BIG, "stream: more rows than max_rows");
+    uint64_t *pend = s->d_pend[s->cur];
+    uint64_t *dst = pend + s->pend_rows * n_cols * L;
+    int32_t rc = encode_dev(plan, s->d_in, nr, dst);
+    if (rc != LCPC_OK) return rc;
+    if (s->sink) {
+        if (s->rows_total + nr > s->sink_cap) return fail(LCPC_ERR_TOO_BIG, "stream: sink row capacity exceeded");
+        CU(emit_colmajor(s->fid, dst, nr, n_cols, n_cols, s->d_col, nr, ctx->lc()));
+        CU(cudaMemcpyAsync(s->h_col, s->d_col, n_cols * nr * w, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    s->pend_rows += nr;
+    s->rows_total += nr;
+    // chunks that are complete and certainly not the last one: 1024*(c+1) < bytes so far
+    const uint64_t bytes = 32 + (uint64_t)s->rows_total * w;
+    const uint64_t chunk_end = (bytes - 1) / 1024;
+    if (chunk_end > s->chunks_done) {
+        if (chunk_end > s->chunks_cap) return fail(LCPC_ERR_TOO_BIG, "stream: chunk store exceeded");
+        CU(hash_chunk_range(s->fid, pend, (int64_t)s->pend_base, s->rows_total, n_cols, n_cols, s->chunks_done, chunk_end,
+                            UINT64_MAX, UINT64_MAX, s->d_cvs, ctx->lc()));
+        s->chunks_done = chunk_end;
+        // rows below the first byte of the next chunk are finished with
+        const uint64_t first_byte = 1024 * chunk_end;
+        const size_t new_base = first_byte > 32 ? (size_t)((first_byte - 32) / w) : 0;
+        const size_t keep = s->rows_total - new_base;
+        if (keep)
+            CU(cudaMemcpyAsync(s->d_pend[s->cur ^ 1], pend + (new_base - s->pend_base) * n_cols * L, keep * n_cols * w,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+        s->cur ^= 1;
+        s->pend_base = new_base;
+        s->pend_rows = keep;
+    }
+    if (s->sink) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        scatter_to_sink(s, s->rows_total - nr, nr);
+    }
+    return LCPC_OK;
+}
+
+int32_t push_common(lcpc_stream *s, const void *data, size_t n_units, bool bytes) {
+    if (!s || (!data && n_units)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    lcpc_plan *plan = s->plan;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g0(s->mu);
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    if (s->finished) return fail(LCPC_ERR_INVALID_ARG, "stream: already finished");
+    if (n_units == 0) return LCPC_OK;
+    if (s->ragged) return fail(LCPC_ERR_DIMS, "stream: only the final push may end inside a row");
+    if (bytes && s->fid != FT63) return fail(LCPC_ERR_INVALID_ARG, "byte packing is defined for the 63-bit field only");
+    CU(cudaSetDevice(ctx->device));
+    const size_t unit_per_row = bytes ? s->n_per_row * 7 : s->n_per_row;  // bytes or elements in a full row
+    const size_t usize = bytes ? 1 : s->wbytes;
+    // all or nothing: a push that would overflow the stream is rejected before any of it is consumed
+    if (s->rows_total + (n_units + unit_per_row - 1) / unit_per_row > s->max_rows)
+        return fail(LCPC_ERR_TOO_BIG, "stream: more rows than max_rows");
+    size_t off = 0;
+    while (off < n_units) {
+        const size_t take = std::min(n_units - off, s->block_rows * unit_per_row);
+        const size_t nr = (take + unit_per_row - 1) / unit_per_row;
+        const size_t n_elems = bytes ? (take + 6) / 7 : take;
+        if (take % unit_per_row) s->ragged = true;
+        const uint8_t *src = static_cast<const uint8_t *>(data) + off * usize;
+        if (bytes) {
+            CU(cudaMemcpyAsync(s->d_bytes, src, take, cudaMemcpyHostToDevice, ctx->stream));
+            CU(pack_bytes7(s->d_bytes, take, s->d_in, ctx->lc()));
+        } else {
+            CU(cudaMemcpyAsync(s->d_in, src, take * usize, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (n_elems < nr * s->n_per_row)  // zero fill of the last row (lib.rs:665-674; data_field.rs:38-46)
+            CU(cudaMemsetAsync(s->d_in + n_elems * s->L, 0, (nr * s->n_per_row - n_elems) * s->wbytes, ctx->stream));
+        int32_t rc = process_block(s, nr);
+        if (rc != LCPC_OK) return rc;
+        // the staging buffers are reused by the next block: pageable-source copies above are synchronous with
+        // respect to the host, pinned ones are not
+        CU(cudaStreamSynchronize(ctx->stream));
+        s->elems_total += n_elems;
+        off += take;
+    }
+    return LCPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lcpc_stream_begin(lcpc_plan *plan, size_t max_rows, size_t block_rows, uint8_t *sink, size_t sink_row_capacity,
+                          lcpc_stream **out) {
+    if (!plan || !out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (max_rows == 0) return fail(LCPC_ERR_DIMS, "stream: max_rows must be positive");
+    if (sink && sink_row_capacity < 1) return fail(LCPC_ERR_DIMS, "stream: sink row capacity must be positive");
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    lcpc_stream *s = new (std::nothrow) lcpc_stream;
+    if (!s) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    s->plan = plan;
+    plan->refs.fetch_add(1);
+    s->fid = plan->fid;
+    s->L = limbs_of(plan->fid);
+    s->wbytes = (size_t)s->L * 8;
+    s->n_per_row = plan->n_per_row;
+    s->n_cols = plan->n_cols;
+    s->np2 = next_pow2(plan->n_cols);
+    s->max_rows = max_rows;
+    if (block_rows == 0) {  // about 256 MiB of encoded rows per block
+        block_rows = std::max<size_t>(1, ((size_t)256 << 20) / (s->n_cols * s->wbytes));
+    }
+    s->block_rows = std::min(block_rows, max_rows);
+    s->pend_cap = s->block_rows + 1024 / s->wbytes + 4;
+    s->chunks_cap = hash_leaf_chunks(s->fid, max_rows);
+    s->sink = sink;
+    s->sink_cap = sink_row_capacity;
+    auto body = [&]() -> int32_t {
+        CU(cudaMalloc((void **)&s->d_in, s->block_rows * s->n_per_row * s->wbytes));
+        if (s->fid == FT63) CU(cudaMalloc((void **)&s->d_bytes, s->block_rows * s->n_per_row * 7 + 8));
+        for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&s->d_pend[i], s->pend_cap * s->n_cols * s->wbytes));
+        CU(cudaMalloc((void **)&s->d_cvs, (size_t)s->chunks_cap * s->n_cols * 32));
+        CU(cudaMalloc((void **)&s->d_hashes, (2 * s->np2 - 1) * 32));
+        if (sink) {
+            CU(cudaMalloc((void **)&s->d_col, s->block_rows * s->n_cols * s->wbytes));
+            CU(cudaMallocHost((void **)&s->h_col, s->block_rows * s->n_cols * s->wbytes));
+        }
+        return LCPC_OK;
+    };
+    int32_t rc = s->np2 ? body() : fail(LCPC_ERR_TOO_BIG, "n_cols is too large for this encoding");
+    if (rc != LCPC_OK) {
+        stream_release(s);
+        return rc;
+    }
+    *out = s;
+    return LCPC_OK;
+}
+
+int32_t lcpc_stream_push_elems_host(lcpc_stream *s, const uint64_t *elems, size_t n_elems) {
+    return push_common(s, elems, n_elems, false);
+}
+
+int32_t lcpc_stream_push_bytes_host(lcpc_stream *s, const uint8_t *bytes, size_t n_bytes) {
+    return push_common(s, bytes, n_bytes, true);
+}
+
+int32_t lcpc_stream_finish(lcpc_stream *s, uint8_t *hashes_out, size_t *n_rows_out) {
+    if (!s) return fail(LCPC_ERR_INVALID_ARG, "null stream");
+    lcpc_plan *plan = s->plan;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g0(s->mu);
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (s->rows_total == 0) return fail(LCPC_ERR_DIMS, "cannot commit to zero coefficients");
+    if (!s->finished) {
+        const uint64_t total = hash_leaf_bytes(s->fid, s->rows_total), nc = hash_leaf_chunks(s->fid, s->rows_total);
+        CU(hash_chunk_range(s->fid, s->d_pend[s->cur], (int64_t)s->pend_base, s->rows_total, s->n_cols, s->n_cols,
+                            s->chunks_done, nc, total, nc, s->d_cvs, ctx->lc()));
+        s->chunks_done = nc;
+        if (s->np2 > s->n_cols) CU(cudaMemsetAsync(s->d_hashes + s->n_cols * 32, 0, (s->np2 - s->n_cols) * 32, ctx->stream));
+        CU(hash_merge(s->d_cvs, s->n_cols, nc, s->d_hashes, ctx->lc()));
+        CU(merkle_tree(s->d_hashes, s->np2, ctx->lc()));
+        s->finished = true;
+    }
+    if (hashes_out) CU(cudaMemcpyAsync(hashes_out, s->d_hashes, (2 * s->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_rows_out) *n_rows_out = s->rows_total;
+    return LCPC_OK;
+}
+
+void lcpc_stream_free(lcpc_stream *s) { stream_release(s); }
+
+int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
+                                     uint64_t *comm_rows_out, uint8_t *hashes_out) {
+    if (!c || !coeff_rows) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (n_rows == 0 || row0 + n_rows > c->n_rows || row0 + n_rows < row0) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
+    lcpc_plan *plan = c->plan;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g0(c->mu);
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const int L = limbs_of(plan->fid);
+    const size_t w = (size_t)L * 8, npr = c->n_per_row, n_cols = c->n_cols;
+    uint64_t *d_rows = c->d_coeffs + row0 * npr * L;
+    uint64_t *d_enc = c->d_comm + row0 * n_cols * L;
+    CU(cudaMemcpyAsync(d_rows, coeff_rows, n_rows * npr * w, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = encode_dev(plan, d_rows, n_rows, d_enc);
+    if (rc != LCPC_OK) return rc;
+    const uint64_t total = hash_leaf_bytes(plan->fid, c->n_rows), nc = hash_leaf_chunks(plan->fid, c->n_rows);
+    if (nc <= 1 || !c->d_cvs) {
+        DevBuf scratch;
+        CU(scratch.alloc(hash_scratch_bytes(plan->fid, c->n_rows, n_cols), ctx->stream));
+        CU(hash_columns(plan->fid, c->d_comm, c->n_rows, n_cols, n_cols, nullptr, c->d_hashes, scratch.as<uint8_t>(), ctx->lc()));
+    } else {
+        const uint64_t c_lo = (32 + (uint64_t)row0 * w) / 1024;
+        const uint64_t c_hi = (32 + (uint64_t)(row0 + n_rows) * w - 1) / 1024 + 1;
+        CU(hash_chunk_range(plan->fid, c->d_comm, 0, c->n_rows, n_cols, n_cols, c_lo, std::min(c_hi, nc), total, nc, c->d_cvs,
+                            ctx->lc()));
+        CU(hash_merge(c->d_cvs, n_cols, nc, c->d_hashes, ctx->lc()));
+    }
+    CU(merkle_tree(c->d_hashes, c->np2, ctx->lc()));
+    if (comm_rows_out) CU(cudaMemcpyAsync(comm_rows_out, d_enc, n_rows * n_cols * w, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hashes_out) CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+}  // extern "C"

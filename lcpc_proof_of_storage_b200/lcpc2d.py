@@ -532,6 +532,25 @@ class LcCommit:
         check(_lib.load().lcpc_commit_root(self._h, _ptr(out)))
         return out.tobytes()
 
+    def update_rows(self, row0: int, coeff_rows: np.ndarray) -> np.ndarray:
+        """Replace coefficient rows [row0, row0 + k) and bring the commitment up to date: only those rows are
+        re-encoded and only the BLAKE3 chunks of the column leaves that contain them are re-hashed
+        (proof-of-storage FileHandler::edit_bytes -> reencode_row -> recalculate_merkle_tree,
+        lcpc_online/file_handler.rs:279-402, 474-481).  Returns the new flat tree."""
+        L = self.enc.limbs
+        rows = np.ascontiguousarray(coeff_rows, dtype=np.uint64).reshape(-1, self.n_per_row, L)
+        k = rows.shape[0]
+        np2 = next_pow2(self.n_cols)
+        hashes = np.empty((2 * np2 - 1, 32), dtype=np.uint8)
+        comm_rows = np.empty((k, self.n_cols, L), dtype=np.uint64)
+        _prover_call(_lib.load().lcpc_commit_update_rows_host(self._h, row0, k, _ptr(rows), _ptr(comm_rows), _ptr(hashes)))
+        if self._coeffs is not None:
+            self._coeffs[row0:row0 + k] = rows
+        if self._comm is not None:
+            self._comm[row0:row0 + k] = comm_rows
+        self._hashes = hashes
+        return hashes
+
     # -- folds / openings ----------------------------------------------------------------
     def fold(self, tensors: np.ndarray, encoded: bool = False) -> np.ndarray:
         """collapse_columns for a batch of tensors: (n_tensors, n_rows, L) -> (n_tensors, width, L)."""
