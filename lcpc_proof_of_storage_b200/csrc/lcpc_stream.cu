@@ -25,16 +25,21 @@ struct lcpc_stream {
     int fid = 0, L = 1;
     size_t n_per_row = 0, n_cols = 0, np2 = 0, wbytes = 8;
     size_t max_rows = 0, block_rows = 0, pend_cap = 0;
-    uint64_t *d_in = nullptr;       // block_rows x n_per_row coefficient staging
-    uint8_t *d_bytes = nullptr;     // block_rows x n_per_row x 7 raw file bytes (63-bit field only)
+    // staging is double buffered: the H2D copy of block k+1 (copy stream) overlaps the encode + hash of block k
+    uint64_t *d_in[2] = {nullptr, nullptr};    // block_rows x n_per_row coefficients
+    uint8_t *d_bytes[2] = {nullptr, nullptr};  // block_rows x n_per_row x 7 raw file bytes (63-bit field only)
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr},
+                ev_out[2] = {nullptr, nullptr};
+    size_t blocks = 0;              // blocks processed so far (selects the staging buffer)
+    struct Pending { bool live = false; size_t row0 = 0, nr = 0; int buf = 0; } pending;  // D2H'd block awaiting its scatter
     uint64_t *d_pend[2] = {nullptr, nullptr};  // encoded rows not yet consumed by the column digests
     int cur = 0;
     size_t pend_rows = 0, pend_base = 0;
     uint8_t *d_cvs = nullptr;       // [chunk][column][32]
     uint64_t chunks_cap = 0, chunks_done = 0;
     uint8_t *d_hashes = nullptr;
-    uint64_t *d_col = nullptr;      // [n_cols][block_rows] canonical reprs (column-major emit)
-    uint8_t *h_col = nullptr;       // pinned mirror of d_col
+    uint64_t *d_col[2] = {nullptr, nullptr};  // [n_cols][block_rows] canonical reprs (column-major emit)
+    uint8_t *h_col[2] = {nullptr, nullptr};   // pinned mirrors of d_col
     uint8_t *sink = nullptr;        // host image of the encoded file (may be an mmap), column c at c*sink_cap*w
     size_t sink_cap = 0;
     size_t rows_total = 0, elems_total = 0;
@@ -51,23 +56,29 @@ void stream_release(lcpc_stream *s) {
         cudaStream_t st = plan->ctx->stream;
         cudaSetDevice(plan->ctx->device);
         cudaStreamSynchronize(st);
-        for (void *p : {(void *)s->d_in, (void *)s->d_bytes, (void *)s->d_pend[0], (void *)s->d_pend[1], (void *)s->d_cvs,
-                        (void *)s->d_hashes, (void *)s->d_col})
+        if (plan->ctx->s_in) cudaStreamSynchronize(plan->ctx->s_in);
+        if (plan->ctx->s_out) cudaStreamSynchronize(plan->ctx->s_out);
+        for (void *p : {(void *)s->d_in[0], (void *)s->d_in[1], (void *)s->d_bytes[0], (void *)s->d_bytes[1], (void *)s->d_pend[0],
+                        (void *)s->d_pend[1], (void *)s->d_cvs, (void *)s->d_hashes, (void *)s->d_col[0], (void *)s->d_col[1]})
             if (p) cudaFree(p);
-        if (s->h_col) cudaFreeHost(s->h_col);
+        for (int i = 0; i < 2; i++) {
+            if (s->h_col[i]) cudaFreeHost(s->h_col[i]);
+            for (cudaEvent_t e : {s->ev_in[i], s->ev_comp[i], s->ev_emit[i], s->ev_out[i]})
+                if (e) cudaEventDestroy(e);
+        }
     }
     delete s;
     if (plan) lcpc_plan_destroy(plan);  // drops the stream's reference (handles are reference counted)
 }
 
-// rows [row0, row0 + nr) of the column-major block in h_col -> the sink image
-void scatter_to_sink(lcpc_stream *s, size_t row0, size_t nr) {
+// rows [row0, row0 + nr) of the column-major block in h_col[buf] -> the sink image
+void scatter_to_sink(lcpc_stream *s, size_t row0, size_t nr, int buf) {
     const size_t w = s->wbytes, n_cols = s->n_cols;
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     const unsigned nt = n_cols * nr * w < (1u << 20) ? 1u : hw;
     auto work = [&](unsigned t) {
         for (size_t c = t; c < n_cols; c += nt)
-            memcpy(s->sink + (c * s->sink_cap + row0) * w, s->h_col + c * nr * w, nr * w);
+            memcpy(s->sink + (c * s->sink_cap + row0) * w, s->h_col[buf] + c * nr * w, nr * w);
     };
     if (nt == 1) {
         work(0);
@@ -78,21 +89,34 @@ void scatter_to_sink(lcpc_stream *s, size_t row0, size_t nr) {
     for (auto &x : th) x.join();
 }
 
-// one block of rows is in d_in (padded with zeros): encode, emit, advance the digests
-int32_t process_block(lcpc_stream *s, size_t nr) {
+// the block whose device-to-host copy was enqueued earlier: wait for it and scatter it into the sink
+int32_t flush_pending(lcpc_stream *s) {
+    if (!s->pending.live) return LCPC_OK;
+    CU(cudaEventSynchronize(s->ev_out[s->pending.buf]));
+    scatter_to_sink(s, s->pending.row0, s->pending.nr, s->pending.buf);
+    s->pending.live = false;
+    return LCPC_OK;
+}
+
+// one block of rows is in d_in[b] (padded with zeros; ready on the compute stream): encode, emit, advance the digests
+int32_t process_block(lcpc_stream *s, size_t nr, int b) {
     lcpc_plan *plan = s->plan;
     lcpc_ctx *ctx = plan->ctx;
     const int L = s->L;
     const size_t n_cols = s->n_cols, w = s->wbytes;
-    if (s->rows_total + nr > s->max_rows) return fail(LCPC_ERR_TOO_BIG, "stream: more rows than max_rows");
     uint64_t *pend = s->d_pend[s->cur];
     uint64_t *dst = pend + s->pend_rows * n_cols * L;
-    int32_t rc = encode_dev(plan, s->d_in, nr, dst);
+    int32_t rc = encode_dev(plan, s->d_in[b], nr, dst);
     if (rc != LCPC_OK) return rc;
+    CU(cudaEventRecord(s->ev_comp[b], ctx->stream));  // staging buffer b may be refilled
     if (s->sink) {
         if (s->rows_total + nr > s->sink_cap) return fail(LCPC_ERR_TOO_BIG, "stream: sink row capacity exceeded");
-        CU(emit_colmajor(s->fid, dst, nr, n_cols, n_cols, s->d_col, nr, ctx->lc()));
-        CU(cudaMemcpyAsync(s->h_col, s->d_col, n_cols * nr * w, cudaMemcpyDeviceToHost, ctx->stream));
+        // h_col[b] / d_col[b] were last used two blocks ago; that block's scatter is flushed before this point
+        CU(emit_colmajor(s->fid, dst, nr, n_cols, n_cols, s->d_col[b], nr, ctx->lc()));
+        CU(cudaEventRecord(s->ev_emit[b], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->s_out, s->ev_emit[b], 0));
+        CU(cudaMemcpyAsync(s->h_col[b], s->d_col[b], n_cols * nr * w, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaEventRecord(s->ev_out[b], ctx->s_out));
     }
     s->pend_rows += nr;
     s->rows_total += nr;
@@ -116,8 +140,13 @@ int32_t process_block(lcpc_stream *s, size_t nr) {
         s->pend_rows = keep;
     }
     if (s->sink) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        scatter_to_sink(s, s->rows_total - nr, nr);
+        // the previous block's copy has had this block's GPU work to hide behind; scatter it now, then queue ours
+        int32_t rc2 = flush_pending(s);
+        if (rc2 != LCPC_OK) return rc2;
+        s->pending.live = true;
+        s->pending.row0 = s->rows_total - nr;
+        s->pending.nr = nr;
+        s->pending.buf = b;
     }
     return LCPC_OK;
 }
@@ -139,6 +168,8 @@ int32_t push_common(lcpc_stream *s, const void *data, size_t n_units, bool bytes
     // all or nothing: a push that would overflow the stream is rejected before any of it is consumed
     if (s->rows_total + (n_units + unit_per_row - 1) / unit_per_row > s->max_rows)
         return fail(LCPC_ERR_TOO_BIG, "stream: more rows than max_rows");
+    if (!ctx->s_in) CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     size_t off = 0;
     while (off < n_units) {
         const size_t take = std::min(n_units - off, s->block_rows * unit_per_row);
@@ -146,22 +177,24 @@ int32_t push_common(lcpc_stream *s, const void *data, size_t n_units, bool bytes
         const size_t n_elems = bytes ? (take + 6) / 7 : take;
         if (take % unit_per_row) s->ragged = true;
         const uint8_t *src = static_cast<const uint8_t *>(data) + off * usize;
-        if (bytes) {
-            CU(cudaMemcpyAsync(s->d_bytes, src, take, cudaMemcpyHostToDevice, ctx->stream));
-            CU(pack_bytes7(s->d_bytes, take, s->d_in, ctx->lc()));
-        } else {
-            CU(cudaMemcpyAsync(s->d_in, src, take * usize, cudaMemcpyHostToDevice, ctx->stream));
-        }
+        const int b = (int)(s->blocks & 1);
+        // copy stream: wait until the compute stream has consumed what staging buffer b held (block k-2)
+        if (s->blocks >= 2) CU(cudaStreamWaitEvent(ctx->s_in, s->ev_comp[b], 0));
+        if (bytes) CU(cudaMemcpyAsync(s->d_bytes[b], src, take, cudaMemcpyHostToDevice, ctx->s_in));
+        else CU(cudaMemcpyAsync(s->d_in[b], src, take * usize, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaEventRecord(s->ev_in[b], ctx->s_in));
+        CU(cudaStreamWaitEvent(ctx->stream, s->ev_in[b], 0));
+        if (bytes) CU(pack_bytes7(s->d_bytes[b], take, s->d_in[b], ctx->lc()));
         if (n_elems < nr * s->n_per_row)  // zero fill of the last row (lib.rs:665-674; data_field.rs:38-46)
-            CU(cudaMemsetAsync(s->d_in + n_elems * s->L, 0, (nr * s->n_per_row - n_elems) * s->wbytes, ctx->stream));
-        int32_t rc = process_block(s, nr);
+            CU(cudaMemsetAsync(s->d_in[b] + n_elems * s->L, 0, (nr * s->n_per_row - n_elems) * s->wbytes, ctx->stream));
+        int32_t rc = process_block(s, nr, b);
         if (rc != LCPC_OK) return rc;
-        // the staging buffers are reused by the next block: pageable-source copies above are synchronous with
-        // respect to the host, pinned ones are not
-        CU(cudaStreamSynchronize(ctx->stream));
+        s->blocks++;
         s->elems_total += n_elems;
         off += take;
     }
+    // the caller's buffer may be reused after return: every copy out of it has to be complete
+    CU(cudaStreamSynchronize(ctx->s_in));
     return LCPC_OK;
 }
 
@@ -199,14 +232,22 @@ int32_t lcpc_stream_begin(lcpc_plan *plan, size_t max_rows, size_t block_rows, u
     s->sink = sink;
     s->sink_cap = sink_row_capacity;
     auto body = [&]() -> int32_t {
-        CU(cudaMalloc((void **)&s->d_in, s->block_rows * s->n_per_row * s->wbytes));
-        if (s->fid == FT63) CU(cudaMalloc((void **)&s->d_bytes, s->block_rows * s->n_per_row * 7 + 8));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc((void **)&s->d_in[i], s->block_rows * s->n_per_row * s->wbytes));
+            if (s->fid == FT63) CU(cudaMalloc((void **)&s->d_bytes[i], s->block_rows * s->n_per_row * 7 + 8));
+            CU(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_comp[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_emit[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+        }
         for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&s->d_pend[i], s->pend_cap * s->n_cols * s->wbytes));
         CU(cudaMalloc((void **)&s->d_cvs, (size_t)s->chunks_cap * s->n_cols * 32));
         CU(cudaMalloc((void **)&s->d_hashes, (2 * s->np2 - 1) * 32));
         if (sink) {
-            CU(cudaMalloc((void **)&s->d_col, s->block_rows * s->n_cols * s->wbytes));
-            CU(cudaMallocHost((void **)&s->h_col, s->block_rows * s->n_cols * s->wbytes));
+            for (int i = 0; i < 2; i++) {
+                CU(cudaMalloc((void **)&s->d_col[i], s->block_rows * s->n_cols * s->wbytes));
+                CU(cudaMallocHost((void **)&s->h_col[i], s->block_rows * s->n_cols * s->wbytes));
+            }
         }
         return LCPC_OK;
     };
@@ -236,6 +277,10 @@ int32_t lcpc_stream_finish(lcpc_stream *s, uint8_t *hashes_out, size_t *n_rows_o
     std::lock_guard<std::mutex> g2(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     if (s->rows_total == 0) return fail(LCPC_ERR_DIMS, "cannot commit to zero coefficients");
+    {
+        int32_t rc = flush_pending(s);
+        if (rc != LCPC_OK) return rc;
+    }
     if (!s->finished) {
         const uint64_t total = hash_leaf_bytes(s->fid, s->rows_total), nc = hash_leaf_chunks(s->fid, s->rows_total);
         CU(hash_chunk_range(s->fid, s->d_pend[s->cur], (int64_t)s->pend_base, s->rows_total, s->n_cols, s->n_cols,
