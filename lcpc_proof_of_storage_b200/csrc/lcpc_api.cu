@@ -47,7 +47,7 @@ void free_csr(DevCsr &m) {
 }
 
 // CSC (host, caller's) -> CSR (device)
-int32_t upload_csr(const lcpc_csc &a, int L, DevCsr &out) {
+int32_t upload_csr(const lcpc_csc &a, int fid, int L, DevCsr &out) {
     if (!a.indptr || (a.indptr[a.cols] && (!a.indices || !a.data))) return fail(LCPC_ERR_INVALID_ARG, "null CSC arrays");
     const size_t nnz = (size_t)a.indptr[a.cols];
     if (a.rows > 0xffffffffull || a.cols > 0xffffffffull || nnz > 0xffffffffull)
@@ -76,6 +76,8 @@ int32_t upload_csr(const lcpc_csc &a, int L, DevCsr &out) {
     if (nnz) {
         CU(cudaMemcpy(out.d_colidx, colidx.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(out.d_data, data.data(), nnz * L * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CU(scale_csr_data(fid, out.d_data, nnz, nullptr));
+        CU(cudaDeviceSynchronize());
     }
     return LCPC_OK;
 }
@@ -417,8 +419,8 @@ int32_t lcpc_plan_brakedown(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size
     p->sdig.post.resize(n_levels);
     const int L = limbs_of(field);
     for (size_t l = 0; l < n_levels; l++) {
-        int32_t rc = upload_csr(precodes[l], L, p->sdig.pre[l]);
-        if (rc == LCPC_OK) rc = upload_csr(postcodes[l], L, p->sdig.post[l]);
+        int32_t rc = upload_csr(precodes[l], field, L, p->sdig.pre[l]);
+        if (rc == LCPC_OK) rc = upload_csr(postcodes[l], field, L, p->sdig.post[l]);
         if (rc != LCPC_OK) {
             lcpc_plan_destroy(p);
             return rc;

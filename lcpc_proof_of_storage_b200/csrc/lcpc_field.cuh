@@ -60,6 +60,43 @@ __host__ __device__ constexpr FieldConsts field_consts(int fid) {
     }
 }
 
+// 2^32 * R mod p (the Montgomery form of 2^32), limbs; used to undo the extra 2^-32 of the lazy dot-product reduction
+struct Limbs4 {
+    uint64_t v[4];
+};
+__host__ __device__ constexpr Limbs4 field_two32_mont(int fid) {
+    const FieldConsts fc = field_consts(fid);
+    Limbs4 x{{fc.r[0], fc.r[1], fc.r[2], fc.r[3]}};
+    for (int it = 0; it < 32; it++) {
+        // x = 2x mod p   (2x < 2^(64*limbs) for every lcpc modulus: one spare bit)
+        uint64_t carry = 0;
+        for (int i = 0; i < 4; i++) {
+            const uint64_t nv = (x.v[i] << 1) | carry;
+            carry = x.v[i] >> 63;
+            x.v[i] = nv;
+        }
+        bool ge = true;  // x >= p ?
+        for (int i = 3; i >= 0; i--) {
+            if (x.v[i] != fc.p[i]) {
+                ge = x.v[i] > fc.p[i];
+                break;
+            }
+        }
+        if (ge) {
+            uint64_t borrow = 0;
+            for (int i = 0; i < 4; i++) {
+                const uint64_t d = x.v[i] - fc.p[i];
+                const uint64_t b1 = x.v[i] < fc.p[i];
+                const uint64_t d2 = d - borrow;
+                const uint64_t b2 = d < borrow;
+                x.v[i] = d2;
+                borrow = b1 | b2;
+            }
+        }
+    }
+    return x;
+}
+
 // ---- 63-bit field fast path ----------------------------------------------------------
 // p = 0x46d07600_00000001: low word 1, high word P_HI.  The Montgomery product is computed
 // column-wise with 32x32+64 -> 64 multiply-adds (IMAD.WIDE) only, so that carries propagate
@@ -278,6 +315,60 @@ struct Field {
             m32::mont_redc<2 * LIMBS>(z, x, PWord{});
             return join(z);
         }
+    }
+
+    // ---- lazy dot products: acc = sum_k a_k * b_k with ONE reduction (see lcpc_mont32.cuh) -----------------
+    // Multi-limb fields accumulate unreduced double-width products; the one-limb field keeps its eager
+    // multiply-add (its reduction is two IMAD.WIDE, there is nothing to amortise).
+    struct Dot {
+        uint32_t s[LIMBS == 1 ? 2 : 4 * LIMBS + 2];
+    };
+    __device__ __forceinline__ static void dot_init(Dot &d) {
+#pragma unroll
+        for (int i = 0; i < (LIMBS == 1 ? 2 : 4 * LIMBS + 2); i++) d.s[i] = 0;
+    }
+    __device__ __forceinline__ static void dot_mac(Dot &d, const E &a, const E &b) {
+        if constexpr (LIMBS == 1) {
+            const uint64_t acc = ft63::pack(d.s[0], d.s[1]);
+            const uint64_t r = ft63::add(acc, ft63::mul(a.v[0], b.v[0]));
+            d.s[0] = ft63::lo32(r);
+            d.s[1] = ft63::hi32(r);
+        } else {
+            uint32_t x[2 * LIMBS], y[2 * LIMBS];
+            split(x, a);
+            split(y, b);
+            m32::wide_mac<2 * LIMBS, PWord>(d.s, x, y);
+        }
+    }
+    // sum * 2^-32 for multi-limb fields (callers that pre-scaled one operand class by 2^32, DOT_PRESCALE), the sum itself
+    // for the one-limb field
+    __device__ __forceinline__ static E dot_finish_prescaled(const Dot &d) {
+        E r;
+        if constexpr (LIMBS == 1) {
+            r.v[0] = ft63::pack(d.s[0], d.s[1]);
+        } else {
+            uint32_t z[2 * LIMBS];
+            m32::wide_redc<2 * LIMBS>(z, d.s, PWord{});
+            r = join(z);
+        }
+        return r;
+    }
+    static constexpr bool DOT_PRESCALE = LIMBS > 1;
+    // 2^32 in Montgomery form (one() for the one-limb field, whose dot products need no correction)
+    __device__ __forceinline__ static E dot_scale() {
+        E r;
+        if constexpr (LIMBS == 1) {
+            r = one();
+        } else {
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) r.v[i] = field_two32_mont(FID).v[i];
+        }
+        return r;
+    }
+    // the sum, fully reduced, no pre-scaling needed: one extra product per dot product
+    __device__ __forceinline__ static E dot_finish(const Dot &d) {
+        if constexpr (LIMBS == 1) return dot_finish_prescaled(d);
+        else return mul(dot_finish_prescaled(d), dot_scale());
     }
 
     __device__ static E pow(E base, uint64_t e) {

@@ -129,6 +129,8 @@ struct DevCsr {
     uint32_t *d_colidx = nullptr;  // nnz
     uint64_t *d_data = nullptr;    // nnz * LIMBS
 };
+// one-time preparation of a matrix's non-zeros for the spmv kernel (multiplies by 2^32 for the multi-limb fields)
+cudaError_t scale_csr_data(int fid, uint64_t *d_data, size_t nnz, cudaStream_t s);
 struct SdigPlan {
     int fid = 0;
     size_t n_per_row = 0, n_cols = 0;

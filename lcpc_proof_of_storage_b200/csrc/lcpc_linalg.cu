@@ -35,19 +35,19 @@ k_fold(const uint64_t *__restrict__ mat, size_t n_rows, size_t width, size_t row
     if (j >= width) return;
     const size_t r0 = (size_t)blockIdx.y * rows_per_split;
     const size_t r1 = r0 + rows_per_split < n_rows ? r0 + rows_per_split : n_rows;
-    E acc[NT];
+    typename F::Dot acc[NT];  // unreduced sums for the multi-limb fields: one reduction per output, not per row
 #pragma unroll
-    for (int t = 0; t < NT; t++) acc[t] = F::zero();
+    for (int t = 0; t < NT; t++) F::dot_init(acc[t]);
     for (size_t r = r0; r < r1; r++) {
         const E c = ld_fe<L>(mat + (r * row_stride + j) * L);
 #pragma unroll
         for (int t = 0; t < NT; t++) {
             const E tv = ld_fe<L>(tensors + ((size_t)t * n_rows + r) * L);  // warp-uniform: broadcast
-            acc[t] = F::add(acc[t], F::mul(c, tv));
+            F::dot_mac(acc[t], c, tv);
         }
     }
 #pragma unroll
-    for (int t = 0; t < NT; t++) st_fe<L>(out + (((size_t)blockIdx.y * NT + t) * width + j) * L, acc[t]);
+    for (int t = 0; t < NT; t++) st_fe<L>(out + (((size_t)blockIdx.y * NT + t) * width + j) * L, F::dot_finish(acc[t]));
 }
 
 // out[i] = sum_k parts[k*n + i]
@@ -201,10 +201,11 @@ __global__ void k_column_dots(const uint64_t *__restrict__ cols, size_t n_rows, 
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_open * n_tensors) return;
     const size_t i = idx / n_tensors, t = idx % n_tensors;
-    E acc = F::zero();
+    typename F::Dot acc;
+    F::dot_init(acc);
     for (size_t r = 0; r < n_rows; r++)
-        acc = F::add(acc, F::mul(ld_fe<L>(tensors + (t * n_rows + r) * L), ld_fe<L>(cols + (i * n_rows + r) * L)));
-    st_fe<L>(out + idx * L, acc);
+        F::dot_mac(acc, ld_fe<L>(tensors + (t * n_rows + r) * L), ld_fe<L>(cols + (i * n_rows + r) * L));
+    st_fe<L>(out + idx * L, F::dot_finish(acc));
 }
 
 template <int FID>
@@ -292,14 +293,38 @@ k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colid
     if (i >= m_rows) return;
     const uint32_t k0 = rowptr[i], k1 = rowptr[i + 1];
     for (size_t b = (size_t)blockIdx.y * gs + bl; b < bp; b += (size_t)gridDim.y * gs) {
-        E acc = F::zero();
+        typename F::Dot acc;  // `data` is pre-scaled by 2^32 for the multi-limb fields (scale_csr_data)
+        F::dot_init(acc);
         for (uint32_t k = k0; k < k1; k++) {
             const E a = ld_fe<L>(data + (size_t)k * L);
             const E x = ld_fe<L>(xT + ((size_t)colidx[k] * bp + b) * L);
-            acc = F::add(acc, F::mul(a, x));
+            F::dot_mac(acc, a, x);
         }
-        st_fe<L>(yT + (i * bp + b) * L, acc);
+        st_fe<L>(yT + (i * bp + b) * L, F::dot_finish_prescaled(acc));
     }
+}
+
+// data[k] *= 2^32 for the multi-limb fields: the lazy dot product of k_spmv_t reduces by one extra word
+template <int FID>
+__global__ void k_scale_data(uint64_t *data, size_t n) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    st_fe<L>(data + k * L, F::mul(ld_fe<L>(data + k * L), F::dot_scale()));
+}
+
+template <int FID>
+static cudaError_t scale_csr_data_t(uint64_t *d_data, size_t nnz, cudaStream_t s) {
+    if (!Field<FID>::DOT_PRESCALE || nnz == 0) return cudaSuccess;
+    k_scale_data<FID><<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(d_data, nnz);
+    return cudaGetLastError();
+}
+
+cudaError_t scale_csr_data(int fid, uint64_t *d_data, size_t nnz, cudaStream_t s) {
+#define CALL(F) scale_csr_data_t<F>(d_data, nnz, s)
+    LCPC_FIELD_SWITCH(fid, CALL)
+#undef CALL
 }
 
 // xoT[r][b] = sum_j xiT[j][b] * (r+1)^j by Horner (encode.rs:97-109), transposed layout

@@ -41,12 +41,16 @@ def timed(fn, steps=10, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    ctx.kernel_timing(True)
+    # total first, without the per-kernel events (they serialise launches and show up in short kernels)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         fn()
     e1.record(stream)
+    torch.cuda.synchronize()
+    ctx.kernel_timing(True)
+    for _ in range(steps):
+        fn()
     torch.cuda.synchronize()
     kt = ctx.kernel_timing_report()
     ctx.kernel_timing(False)
