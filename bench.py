@@ -133,9 +133,9 @@ def measured_peak_gbs():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload
-# (profiles/r01b_summary.md); None for kernels that were not captured
-NCU_DRAM_TRAFFIC = {"k_ntt_strided": 134_775_808 + 214_266_624, "k_ntt_block": 268_606_976 + 209_246_464,
-                    "k_hash_chunks": 268_456_448 + 9_687_040}
+# (profiles/r01c_summary.md); None for kernels that were not captured
+NCU_DRAM_TRAFFIC = {"k_ntt_strided": 134_734_848 + 214_809_600, "k_ntt_block": 268_627_968 + 213_919_744,
+                    "k_hash_chunks": 268_462_080 + 10_329_344}
 
 
 # per-kernel compulsory HBM bytes for one launch at this workload (DESIGN.md "Kernels")
@@ -376,7 +376,7 @@ def main() -> None:
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach else None,
                     "traffic": NCU_DRAM_TRAFFIC.get(name.replace("_scatter", "")) if world == 1 else None,
-                    "traffic_source": "ncu --set full, profiles/r01b_summary.md", "peak_source": peak_src,
+                    "traffic_source": "ncu --set full, profiles/r01c_summary.md", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                     "share_of_step": total_ms / ms_total,
                     "kernels_ms_per_step": {k: v[1] / steps for k, v in kt.items()},

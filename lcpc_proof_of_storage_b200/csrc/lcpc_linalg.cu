@@ -24,30 +24,72 @@ namespace lcpc {
 
 // ------------------------------------------------------------------ fold
 
-template <int FID, int NT>
+// VEC adjacent columns per thread (2 for the one-limb field: 16-byte loads) and UNR rows per trip with all
+// loads issued before the arithmetic: the fold is a stream over the matrix (8 B/coefficient) and what
+// bounds it is the number of bytes in flight per SM, not the integer pipes.
+template <int FID, int NT, int VEC>
 __global__ void __launch_bounds__(128)
 k_fold(const uint64_t *__restrict__ mat, size_t n_rows, size_t width, size_t row_stride,
        const uint64_t *__restrict__ tensors, uint64_t *__restrict__ out, size_t rows_per_split) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int UNR = L == 1 ? 8 : (L == 2 ? 4 : 2);
+    const size_t j = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (j >= width) return;
     const size_t r0 = (size_t)blockIdx.y * rows_per_split;
     const size_t r1 = r0 + rows_per_split < n_rows ? r0 + rows_per_split : n_rows;
-    typename F::Dot acc[NT];  // unreduced sums for the multi-limb fields: one reduction per output, not per row
+    const bool full = j + VEC <= width;  // the last thread of an odd-width matrix owns one column only
+    typename F::Dot acc[NT][VEC];  // unreduced sums for the multi-limb fields: one reduction per output, not per row
 #pragma unroll
-    for (int t = 0; t < NT; t++) F::dot_init(acc[t]);
-    for (size_t r = r0; r < r1; r++) {
-        const E c = ld_fe<L>(mat + (r * row_stride + j) * L);
+    for (int t = 0; t < NT; t++)
 #pragma unroll
-        for (int t = 0; t < NT; t++) {
-            const E tv = ld_fe<L>(tensors + ((size_t)t * n_rows + r) * L);  // warp-uniform: broadcast
-            F::dot_mac(acc[t], c, tv);
+        for (int v = 0; v < VEC; v++) F::dot_init(acc[t][v]);
+    size_t r = r0;
+    for (; r + UNR <= r1; r += UNR) {
+        E c[UNR][VEC];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const uint64_t *p = mat + ((r + u) * row_stride + j) * L;
+            if constexpr (L == 1 && VEC == 2) {
+                if (full && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                    const ulonglong2 q = *reinterpret_cast<const ulonglong2 *>(p);
+                    c[u][0].v[0] = q.x;
+                    c[u][1].v[0] = q.y;
+                } else {
+                    c[u][0].v[0] = p[0];
+                    c[u][1].v[0] = full ? p[1] : 0;
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; v++) c[u][v] = (v == 0 || full) ? ld_fe<L>(p + v * L) : F::zero();
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++)
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                const E tv = ld_fe<L>(tensors + ((size_t)t * n_rows + r + u) * L);  // warp-uniform: broadcast
+#pragma unroll
+                for (int v = 0; v < VEC; v++) F::dot_mac(acc[t][v], c[u][v], tv);
+            }
+    }
+    for (; r < r1; r++) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            if (v == 0 || full) {
+                const E c = ld_fe<L>(mat + (r * row_stride + j + v) * L);
+#pragma unroll
+                for (int t = 0; t < NT; t++) F::dot_mac(acc[t][v], c, ld_fe<L>(tensors + ((size_t)t * n_rows + r) * L));
+            }
         }
     }
 #pragma unroll
-    for (int t = 0; t < NT; t++) st_fe<L>(out + (((size_t)blockIdx.y * NT + t) * width + j) * L, F::dot_finish(acc[t]));
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+            if (v == 0 || full)
+                st_fe<L>(out + (((size_t)blockIdx.y * NT + t) * width + j + v) * L, F::dot_finish(acc[t][v]));
 }
 
 // out[i] = sum_k parts[k*n + i]
@@ -64,7 +106,7 @@ __global__ void k_add_partials(const uint64_t *__restrict__ parts, size_t n_part
 }
 
 static size_t fold_splits(size_t n_rows, size_t width) {
-    size_t tiles = (width + 127) / 128;
+    size_t tiles = (width + 127) / 128;  // an upper bound for the two-columns-per-thread case: more, smaller splits
     size_t want = (148 * 8 + tiles - 1) / tiles;  // aim for ~8 CTAs per SM
     size_t max_splits = (n_rows + 15) / 16;        // at least 16 rows per split
     size_t s = want < max_splits ? want : max_splits;
@@ -84,7 +126,8 @@ static cudaError_t fold_t(const uint64_t *d_mat, size_t n_rows, size_t width, si
     if (width == 0 || n_tensors == 0) return cudaSuccess;
     const size_t splits = fold_splits(n_rows, width);
     const size_t rps = (n_rows + splits - 1) / splits;
-    const unsigned gx = (unsigned)((width + 127) / 128);
+    constexpr int VEC = L == 1 ? 2 : 1;
+    const unsigned gx = (unsigned)((width + 128 * VEC - 1) / (128 * VEC));
     size_t done = 0;
     while (done < n_tensors) {
         const size_t nt = n_tensors - done < 4 ? n_tensors - done : 4;
@@ -94,10 +137,10 @@ static cudaError_t fold_t(const uint64_t *d_mat, size_t n_rows, size_t width, si
         dim3 grid(gx, (unsigned)splits);
         lc.begin("k_fold");
         switch (nt) {
-        case 1: k_fold<FID, 1><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
-        case 2: k_fold<FID, 2><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
-        case 3: k_fold<FID, 3><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
-        default: k_fold<FID, 4><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
+        case 1: k_fold<FID, 1, VEC><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
+        case 2: k_fold<FID, 2, VEC><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
+        case 3: k_fold<FID, 3, VEC><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
+        default: k_fold<FID, 4, VEC><<<grid, 128, 0, lc.s>>>(d_mat, n_rows, width, row_stride, tens, dst, rps); break;
         }
         lc.end();
         if (splits > 1) {

@@ -319,3 +319,8 @@ class ShardedLigeroCommitter:
                 node >>= 1
             out.append(LcColumn(col, np.concatenate(path) if path else np.empty((0, 32), np.uint8)))
         return out
+
+
+# The committer is encoding-agnostic: a Brakedown plan (non power-of-two n_cols) takes the all-to-all path over the padded
+# leaf range; only the fused peer-store variant is specific to the NTT kernel.
+ShardedCommitter = ShardedLigeroCommitter

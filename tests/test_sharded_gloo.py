@@ -18,9 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class OracleOps:
     """Same interface as sharded.GpuOps, computed by the CPU oracle (test double)."""
 
-    def __init__(self, O, fid, n_per_row, n_cols):
+    def __init__(self, O, fid, n_per_row, n_cols, oenc=None):
         self.O, self.fid, self.n_per_row, self.n_cols = O, fid, n_per_row, n_cols
         self.L = O.LIMBS[fid]
+        self.oenc = oenc  # an oracle encoding with encode_rows (Brakedown); None = Ligero fft_io
 
     def _np(self, t):
         return t.numpy().view(np.uint64)
@@ -28,7 +29,10 @@ class OracleOps:
     def encode(self, coeffs, n_rows):
         rows = np.zeros((n_rows, self.n_cols, self.L), dtype=np.uint64)
         rows[:, :self.n_per_row] = self._np(coeffs).reshape(n_rows, self.n_per_row, self.L)
-        out = self.O.fft_io(self.fid, rows) if n_rows else rows
+        if n_rows:
+            out = self.oenc.encode_rows(rows) if self.oenc is not None else self.O.fft_io(self.fid, rows)
+        else:
+            out = rows
         return torch.from_numpy(out.view(np.int64).reshape(-1).copy())
 
     def hash_columns(self, mat, n_rows, row_stride, n_cols, out):
@@ -58,7 +62,7 @@ class _Enc:
         self.fid, self.n_per_row, self.n_cols = fid, n_per_row, n_cols
 
 
-def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q):
+def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q, brakedown_seed=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -72,8 +76,12 @@ def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q):
         n = n_rows * n_per_row - 5  # ragged last row
         coeffs = np.zeros((n_rows * n_per_row, L), dtype=np.uint64)
         coeffs[:n] = O.random_field_elements(fid, 99, n)
+        oenc = None
+        if brakedown_seed is not None:  # Brakedown: n_cols is whatever the code generator gives (not a power of two)
+            oenc = O.SdigEncoding(fid, n_per_row, brakedown_seed)
+            n_cols = oenc.n_cols
         enc = _Enc(fid, n_per_row, n_cols)
-        sc = ShardedLigeroCommitter(enc, n_rows, None, ops=OracleOps(O, fid, n_per_row, n_cols))
+        sc = ShardedLigeroCommitter(enc, n_rows, None, ops=OracleOps(O, fid, n_per_row, n_cols, oenc))
         r0, cnt = row_partition(n_rows, world)[rank]
         local = coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt]
         sc.commit(torch.from_numpy(np.ascontiguousarray(local).view(np.int64).reshape(-1)))
@@ -83,7 +91,7 @@ def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q):
         cols = [0, n_cols - 1, n_cols // 2, 3]
         opened = sc.open_columns(cols)
         if rank == 0:
-            exp = O.commit(coeffs[:n], O.LigeroEncoding(fid, n_per_row, n_cols))
+            exp = O.commit(coeffs[:n], oenc if oenc is not None else O.LigeroEncoding(fid, n_per_row, n_cols))
             ok = sc.root() == exp.get_root()
             ok &= np.array_equal(hashes.numpy().reshape(-1, 32), exp.hashes)
             f = folded.numpy().view(np.uint64).reshape(2, n_per_row, L)
@@ -113,6 +121,22 @@ def test_sharded_commit_matches_single_process(oracle, world, fid, n_rows, n_per
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, fid, n_rows, n_per_row, n_cols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+@pytest.mark.parametrize("world,fid,n_rows,n_per_row,seed", [(2, 0, 9, 150, 0), (4, 1, 6, 120, 1)])
+def test_sharded_brakedown_commit_matches_single_process(oracle, world, fid, n_rows, n_per_row, seed):
+    """Brakedown rows shard the same way; the PADDED leaf range (np2 > n_cols) is what gets split into column blocks,
+    so the all-zero padding leaves fall into the last ranks' subtrees."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fid, n_rows, n_per_row, 0, q, seed)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
