@@ -192,10 +192,33 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "root": c.get_root().hex(),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout() -> None:
+    """stdout carries exactly ONE line, the result JSON: libraries that write to fd 1 while the run is set up (NCCL prints its
+    version there) are pointed at stderr, and the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main() -> None:
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -419,7 +442,7 @@ def main() -> None:
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
         "root": gpu_root,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -4,7 +4,7 @@ folds ((n_degree_tests + 1) sequential single-tensor folds, as `prove` issues th
 strong scaling: ONE polynomial of 2^n coefficients whose rows are sharded over the ranks.
 
     python tools/bench_sweep.py                         # 1 GPU
-    torchrun --nproc-per-node N tools/bench_sweep.py [--logs 20 22 24 26 28] [--schemes ligero63 brakedown63 brakedown255]
+    torchrun --nproc-per-node N tools/bench_sweep.py [--log-n 20 22 24 26 28] [--schemes ligero63 brakedown63 brakedown255]
 
 One JSON line per (scheme, n).  Times are CUDA events on the launching stream, max over ranks.
 """
@@ -38,7 +38,7 @@ def rand_elems(fid, n, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--logs", type=int, nargs="*", default=[20, 22, 24, 26, 28])
+    ap.add_argument("--log-n", dest="logs", type=int, nargs="*", default=[20, 22, 24, 26, 28])
     ap.add_argument("--schemes", nargs="*", default=["ligero63", "brakedown63", "brakedown255"])
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
