@@ -334,6 +334,12 @@ void lcpc_stream_free(lcpc_stream *s);
  * the whole tree.  LCPC_ERR_DIMS when the range leaves the committed rows. */
 int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
                                      uint64_t *comm_rows_out, uint8_t *hashes_out);
+/* Append -- FileHandler::append_bytes (file_handler.rs:336-402): rows [row0, row0 + n_rows) are written with
+ * row0 <= committed rows <= row0 + n_rows, i.e. the last (partially filled) row may be replaced and new rows follow.
+ * The resident matrices grow, the new rows are encoded, and only the column-leaf chunks from the first written row
+ * (or the former last chunk, whichever is earlier) onwards are re-hashed. */
+int32_t lcpc_commit_append_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
+                                     uint64_t *comm_rows_out, uint8_t *hashes_out);
 
 /* number of kernels this library has launched on this context since creation */
 uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx);

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "lcpc_stream_finish": (C.c_int32, [C.c_void_p, C.c_void_p, szp]),
     "lcpc_stream_free": (None, [C.c_void_p]),
     "lcpc_commit_update_rows_host": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lcpc_commit_append_rows_host": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcpc_plan_ligero": (C.c_int32, [C.c_void_p, C.c_int32, C.c_size_t, C.c_size_t, u64p, vpp]),
     "lcpc_plan_brakedown": (C.c_int32, [C.c_void_p, C.c_int32, C.c_size_t, C.c_size_t, C.c_size_t,
                                         C.POINTER(LcpcCsc), C.POINTER(LcpcCsc), vpp]),

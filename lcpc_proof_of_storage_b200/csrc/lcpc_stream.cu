@@ -299,10 +299,13 @@ int32_t lcpc_stream_finish(lcpc_stream *s, uint8_t *hashes_out, size_t *n_rows_o
 
 void lcpc_stream_free(lcpc_stream *s) { stream_release(s); }
 
-int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
-                                     uint64_t *comm_rows_out, uint8_t *hashes_out) {
+// rows [row0, row0 + n_rows) <- coeff_rows; the commitment may grow (append) but never shrink
+static int32_t commit_write_rows(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows, bool allow_grow,
+                                 uint64_t *comm_rows_out, uint8_t *hashes_out) {
     if (!c || !coeff_rows) return fail(LCPC_ERR_INVALID_ARG, "null argument");
-    if (n_rows == 0 || row0 + n_rows > c->n_rows || row0 + n_rows < row0) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
+    if (n_rows == 0 || row0 + n_rows < row0 || row0 > c->n_rows) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
+    if (!allow_grow && row0 + n_rows > c->n_rows) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
+    if (allow_grow && row0 + n_rows < c->n_rows) return fail(LCPC_ERR_DIMS, "an append must reach the end of the commitment");
     lcpc_plan *plan = c->plan;
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g0(c->mu);
@@ -311,18 +314,43 @@ int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows,
     CU(cudaSetDevice(ctx->device));
     const int L = limbs_of(plan->fid);
     const size_t w = (size_t)L * 8, npr = c->n_per_row, n_cols = c->n_cols;
+    const size_t old_rows = c->n_rows, new_rows = std::max(old_rows, row0 + n_rows);
+    const uint64_t old_nc = hash_leaf_chunks(plan->fid, old_rows);
+    const uint64_t total = hash_leaf_bytes(plan->fid, new_rows), nc = hash_leaf_chunks(plan->fid, new_rows);
+    if (new_rows > old_rows) {
+        // grow the resident matrices (the reference doubles the file's row capacity, encoded_file_writer.rs:429-462)
+        uint64_t *d_coeffs = nullptr, *d_comm = nullptr;
+        CU(cudaMallocAsync((void **)&d_coeffs, new_rows * npr * w, ctx->stream));
+        CU(cudaMallocAsync((void **)&d_comm, new_rows * n_cols * w, ctx->stream));
+        CU(cudaMemcpyAsync(d_coeffs, c->d_coeffs, old_rows * npr * w, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_comm, c->d_comm, old_rows * n_cols * w, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaFreeAsync(c->d_coeffs, ctx->stream));
+        CU(cudaFreeAsync(c->d_comm, ctx->stream));
+        c->d_coeffs = d_coeffs;
+        c->d_comm = d_comm;
+        if (nc > 1) {
+            uint8_t *d_cvs = nullptr;
+            CU(cudaMallocAsync((void **)&d_cvs, (size_t)nc * n_cols * 32, ctx->stream));
+            if (c->d_cvs && old_nc > 1) CU(cudaMemcpyAsync(d_cvs, c->d_cvs, (size_t)old_nc * n_cols * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (c->d_cvs) CU(cudaFreeAsync(c->d_cvs, ctx->stream));
+            c->d_cvs = d_cvs;
+        }
+        c->n_rows = new_rows;
+    }
     uint64_t *d_rows = c->d_coeffs + row0 * npr * L;
     uint64_t *d_enc = c->d_comm + row0 * n_cols * L;
     CU(cudaMemcpyAsync(d_rows, coeff_rows, n_rows * npr * w, cudaMemcpyHostToDevice, ctx->stream));
     int32_t rc = encode_dev(plan, d_rows, n_rows, d_enc);
     if (rc != LCPC_OK) return rc;
-    const uint64_t total = hash_leaf_bytes(plan->fid, c->n_rows), nc = hash_leaf_chunks(plan->fid, c->n_rows);
     if (nc <= 1 || !c->d_cvs) {
         DevBuf scratch;
         CU(scratch.alloc(hash_scratch_bytes(plan->fid, c->n_rows, n_cols), ctx->stream));
         CU(hash_columns(plan->fid, c->d_comm, c->n_rows, n_cols, n_cols, nullptr, c->d_hashes, scratch.as<uint8_t>(), ctx->lc()));
     } else {
-        const uint64_t c_lo = (32 + (uint64_t)row0 * w) / 1024;
+        // chunks that contain the written rows; when the leaf grew, also its former last chunk (it was hashed as a final,
+        // possibly partial, possibly ROOT-flagged chunk)
+        uint64_t c_lo = (32 + (uint64_t)row0 * w) / 1024;
+        if (new_rows > old_rows) c_lo = std::min<uint64_t>(c_lo, old_nc - 1);
         const uint64_t c_hi = (32 + (uint64_t)(row0 + n_rows) * w - 1) / 1024 + 1;
         CU(hash_chunk_range(plan->fid, c->d_comm, 0, c->n_rows, n_cols, n_cols, c_lo, std::min(c_hi, nc), total, nc, c->d_cvs,
                             ctx->lc()));
@@ -333,6 +361,16 @@ int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows,
     if (hashes_out) CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LCPC_OK;
+}
+
+int32_t lcpc_commit_update_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
+                                     uint64_t *comm_rows_out, uint8_t *hashes_out) {
+    return commit_write_rows(c, row0, n_rows, coeff_rows, false, comm_rows_out, hashes_out);
+}
+
+int32_t lcpc_commit_append_rows_host(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows,
+                                     uint64_t *comm_rows_out, uint8_t *hashes_out) {
+    return commit_write_rows(c, row0, n_rows, coeff_rows, true, comm_rows_out, hashes_out);
 }
 
 }  // extern "C"

@@ -252,3 +252,23 @@ def edit_bytes(commit: LcCommit, total_data_bytes: int, byte_start: int, new_byt
         elems |= b[:, k] << np.uint64(8 * k)
     tree = commit.update_rows(start_row, elems.reshape(end_row - start_row, commit.n_per_row, 1))
     return original, MerkleTree(tree)
+
+
+def append_bytes(commit: LcCommit, total_data_bytes: int, bytes_to_add: bytes) -> MerkleTree:
+    """FileHandler::append_bytes (file_handler.rs:336-402) on a device-resident commitment of a file of
+    `total_data_bytes` bytes: the partially filled last row is completed and re-encoded, further rows are appended."""
+    row_bytes = commit.n_per_row * DATA_BYTE_CAPACITY
+    start_row = total_data_bytes // row_bytes
+    head = b""
+    if start_row < commit.n_rows:  # bytes already in the last, partially filled row
+        row = commit.coeffs[start_row, :, 0]
+        head = np.ascontiguousarray(row).view(np.uint8).reshape(-1, 8)[:, :7].tobytes()[:total_data_bytes - start_row * row_bytes]
+    raw = head + bytes_to_add
+    n_rows = -(-len(raw) // row_bytes)
+    buf = np.zeros(n_rows * row_bytes, dtype=np.uint8)
+    buf[:len(raw)] = np.frombuffer(raw, dtype=np.uint8)
+    b = buf.reshape(-1, 7).astype(np.uint64)
+    elems = np.zeros(b.shape[0], dtype=np.uint64)
+    for k in range(7):
+        elems |= b[:, k] << np.uint64(8 * k)
+    return MerkleTree(commit.append_rows(start_row, elems.reshape(n_rows, commit.n_per_row, 1)))

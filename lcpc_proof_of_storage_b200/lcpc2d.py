@@ -551,6 +551,19 @@ class LcCommit:
         self._hashes = hashes
         return hashes
 
+    def append_rows(self, row0: int, coeff_rows: np.ndarray) -> np.ndarray:
+        """Write rows [row0, row0 + k) with row0 <= n_rows <= row0 + k: the last row may be replaced and new rows follow
+        (proof-of-storage FileHandler::append_bytes, lcpc_online/file_handler.rs:336-402).  Returns the new flat tree."""
+        L = self.enc.limbs
+        rows = np.ascontiguousarray(coeff_rows, dtype=np.uint64).reshape(-1, self.n_per_row, L)
+        k = rows.shape[0]
+        hashes = np.empty((2 * next_pow2(self.n_cols) - 1, 32), dtype=np.uint8)
+        _prover_call(_lib.load().lcpc_commit_append_rows_host(self._h, row0, k, _ptr(rows), None, _ptr(hashes)))
+        self.n_rows = max(self.n_rows, row0 + k)
+        self._coeffs = self._comm = None  # re-read lazily from the (grown) device matrices
+        self._hashes = hashes
+        return hashes
+
     # -- folds / openings ----------------------------------------------------------------
     def fold(self, tensors: np.ndarray, encoded: bool = False) -> np.ndarray:
         """collapse_columns for a batch of tensors: (n_tensors, n_rows, L) -> (n_tensors, width, L)."""

@@ -67,6 +67,76 @@ def _worker(rank, world, port, fused, q):
         dist.destroy_process_group()
 
 
+def _worker_brakedown(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import lcpc_proof_of_storage_b200 as P
+        from lcpc_proof_of_storage_b200.sharded import ShardedCommitter, row_partition
+        from oracle import lcpc_oracle as O
+
+        ok = True
+        for fid, n_per_row, n_rows, seed in [(0, 300, 23, 0), (3, 150, 9, 1)]:
+            L = O.LIMBS[fid]
+            oenc = O.SdigEncoding(fid, n_per_row, seed)
+            n = n_rows * n_per_row - 7
+            coeffs = np.zeros((n_rows * n_per_row, L), dtype=np.uint64)
+            coeffs[:n] = O.random_field_elements(fid, 5, n)
+            ctx = P.Context(rank, stream=torch.cuda.current_stream().cuda_stream)
+            enc = P.SdigEncoding.new_from_dims(fid, n_per_row, oenc.n_cols, seed=seed, ctx=ctx)
+            sc = ShardedCommitter(enc, n_rows, None)
+            assert not sc.fused  # n_cols is not a power of two: NCCL all-to-all over the padded leaf range
+            r0, cnt = row_partition(n_rows, world)[rank]
+            local = torch.from_numpy(coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
+            sc.commit(local)
+            hashes = sc.gather_hashes()
+            tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, L)
+            folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda())
+            cols = [0, oenc.n_cols - 1, oenc.n_cols // 2]
+            opened = sc.open_columns(cols)
+            if rank == 0:
+                exp = O.commit(coeffs[:n], oenc)
+                ok &= sc.root() == exp.get_root()
+                ok &= np.array_equal(hashes.cpu().numpy().reshape(-1, 32), exp.hashes)
+                f = folded.cpu().numpy().view(np.uint64).reshape(2, n_per_row, L)
+                for t in range(2):
+                    ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+                for c, col in zip(cols, opened):
+                    e = O.open_column(exp, c)
+                    ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)
+        if rank == 0:
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_brakedown_commit_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_brakedown, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 @pytest.mark.parametrize("fused", [False, True])
 def test_sharded_commit_two_gpus(fused):
     import torch

@@ -166,3 +166,38 @@ def test_edit_bytes_matches_commit_of_edited_file(P, oracle):
     assert tree.root() == exp.get_root() == c.get_root()
     with pytest.raises(ValueError):
         EF.edit_bytes(c, len(data), len(data) - 3, b"12345")
+
+
+@pytest.mark.parametrize("fid,n_per_row,n_cols,n_rows,row0,k", [
+    (0, 64, 128, 50, 50, 3),       # single chunk stays a single chunk
+    (0, 64, 128, 120, 119, 10),    # grows from one chunk to two: the ROOT-flagged chunk is re-hashed
+    (0, 64, 128, 700, 700, 1), (0, 64, 128, 700, 699, 300),
+    (2, 16, 32, 200, 199, 40), (3, 64, 128, 70, 70, 33),
+])
+def test_append_rows_equals_recommit(P, oracle, fid, n_per_row, n_cols, n_rows, row0, k):
+    O = oracle
+    elems = O.random_field_elements(fid, 11 + fid, n_rows * n_per_row)
+    c = P.LcCommit.commit(elems, P.LigeroEncoding(fid, n_per_row, n_cols))
+    new_rows = O.random_field_elements(fid, 78, k * n_per_row)
+    hashes = c.append_rows(row0, new_rows)
+    grown = np.concatenate([elems[:row0 * n_per_row], new_rows])
+    exp = O.commit(grown, O.LigeroEncoding(fid, n_per_row, n_cols))
+    assert c.n_rows == exp.n_rows
+    assert np.array_equal(hashes, exp.hashes) and c.get_root() == exp.get_root()
+    assert np.array_equal(c.comm, exp.comm) and np.array_equal(c.coeffs, exp.coeffs)
+    with pytest.raises(Exception):
+        c.append_rows(0, new_rows[:n_per_row])  # an append must reach the end
+
+
+def test_append_bytes_matches_commit_of_longer_file(P, oracle):
+    from lcpc_proof_of_storage_b200 import encoded_file as EF
+
+    O = oracle
+    rng = np.random.default_rng(6)
+    data = rng.integers(0, 256, 100_003, dtype=np.uint8).tobytes()
+    more = rng.integers(0, 256, 54_321, dtype=np.uint8).tobytes()
+    c = P.LcCommit.commit_bytes(data, P.LigeroEncoding(0, 64, 128))
+    tree = EF.append_bytes(c, len(data), more)
+    exp = O.commit(O.pack_bytes7(data + more), O.LigeroEncoding(0, 64, 128))
+    assert tree.root() == exp.get_root() == c.get_root()
+    assert np.array_equal(c.coeffs, exp.coeffs)

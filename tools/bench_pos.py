@@ -64,8 +64,13 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     cols = pos.get_column_indicies_from_random_seed(1337, soundness, enc_cols)
+    sc.open_columns(cols)  # first call: NCCL sets up the point-to-point channels to rank 0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     opened = sc.open_columns(cols)
+    torch.cuda.synchronize()
     t_open = time.perf_counter() - t0
     if rank == 0:
         root = sc.root()
