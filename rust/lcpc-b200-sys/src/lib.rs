@@ -5,6 +5,7 @@ use std::os::raw::{c_char, c_void};
 
 #[repr(C)] pub struct lcpc_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct lcpc_plan { _p: [u8; 0] }
+#[repr(C)] pub struct lcpc_stream { _p: [u8; 0] }
 #[repr(C)] pub struct lcpc_commit { _p: [u8; 0] }
 #[repr(C)] pub struct lcpc_transcript { _p: [u8; 0] }
 
@@ -51,6 +52,17 @@ extern "C" {
     pub fn lcpc_open_columns_host(c: *mut lcpc_commit, cols: *const u64, n: usize, cols_out: *mut u64,
                                   paths_out: *mut u8) -> i32;
     pub fn lcpc_leaves_host(c: *mut lcpc_commit, cols: *const u64, n: usize, leaves_out: *mut u8) -> i32;
+    // streaming commit (EncodedFileWriter + ColumnDigestAccumulator) and edits on a resident commitment
+    pub fn lcpc_stream_begin(plan: *mut lcpc_plan, max_rows: usize, block_rows: usize, sink: *mut u8,
+                             sink_row_capacity: usize, out: *mut *mut lcpc_stream) -> i32;
+    pub fn lcpc_stream_push_elems_host(s: *mut lcpc_stream, elems: *const u64, n_elems: usize) -> i32;
+    pub fn lcpc_stream_push_bytes_host(s: *mut lcpc_stream, bytes: *const u8, n_bytes: usize) -> i32;
+    pub fn lcpc_stream_finish(s: *mut lcpc_stream, hashes_out: *mut u8, n_rows_out: *mut usize) -> i32;
+    pub fn lcpc_stream_free(s: *mut lcpc_stream);
+    pub fn lcpc_commit_update_rows_host(c: *mut lcpc_commit, row0: usize, n_rows: usize, coeff_rows: *const u64,
+                                        comm_rows_out: *mut u64, hashes_out: *mut u8) -> i32;
+    pub fn lcpc_commit_append_rows_host(c: *mut lcpc_commit, row0: usize, n_rows: usize, coeff_rows: *const u64,
+                                        comm_rows_out: *mut u64, hashes_out: *mut u8) -> i32;
 }
 
 #[allow(dead_code)]
