@@ -85,6 +85,9 @@ COMMIT_CASES = [
     (0, 300 * 2048 - 777, 2048, 4096),
     (0, 9 * 65536 - 1, 65536, 131072),
     (3, 75 * 2048 - 5, 2048, 4096),
+    # a million multi-limb coefficients each: ~2e7 Montgomery products per case through every NTT pass shape
+    (1, (1 << 20) - 3, 16384, 32768),
+    (3, (1 << 20) - 3, 16384, 32768),
 ]
 
 
