@@ -184,6 +184,8 @@ int32_t commit_host_pipelined(lcpc_plan *plan, lcpc_commit *c, const uint64_t *h
     CU(cudaEventRecord(ready, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->s_in, ready, 0));
     CU(cudaStreamWaitEvent(ctx->s_out, ready, 0));
+    // 8 chunks: measured best at 2^24 (5.55 ms; 32 chunks of 8 MiB: 6.78 ms -- many small copies in both directions
+    // leave bubbles between the copy engines' event waits)
     size_t n_chunks = n_rows < 8 ? n_rows : 8;
     const size_t rows_per = (n_rows + n_chunks - 1) / n_chunks;
     n_chunks = (n_rows + rows_per - 1) / rows_per;
