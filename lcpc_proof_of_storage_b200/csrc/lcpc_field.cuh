@@ -98,17 +98,15 @@ __host__ __device__ constexpr Limbs4 field_two32_mont(int fid) {
 }
 
 // ---- 63-bit field fast path ----------------------------------------------------------
-// p = 0x46d07600_00000001: low word 1, high word P_HI.  The Montgomery product is computed
-// column-wise with 32x32+64 -> 64 multiply-adds (IMAD.WIDE) only, so that carries propagate
-// inside the FMA pipe instead of through IADD3/ISETP/SEL chains on the ALU pipe (which is
-// what bound the first version of the NTT kernels, profiles/r01a_summary.md).
-// Multipliers that ptxas cannot see through (read from the constant bank): `mad.wide.u32 d, x, 1,
-// acc` would be strength-reduced to an IADD3/IADD3.X carry chain on the ALU pipe, and a literal
-// modulus word would be split into IMAD + IMAD.HI + 3-input IADD3; opaque, they stay single
-// IMAD.WIDE instructions whose 64-bit accumulate carries inside the FMA pipe.
-static __constant__ uint32_t LCPC_ONE = 1u;
+// p = 0x46d07600_00000001: low word 1, high word P_HI.  A product is four 32x32 -> 64 partial products
+// (IMAD.WIDE) plus two Montgomery digits of one IMAD.WIDE each: six IMAD.WIDE in all, and IMAD.WIDE is the
+// expensive instruction on this part (4 issue cycles on the FMA pipe and 2 on the ALU side, against 2 for IMAD /
+// IADD3 / LOP3 / SHF: profiles/r01c_summary.md).  Everything around them is written to need no compare and no
+// select: column sums are three-input carry chains, a digit is `acc + w*Q` with the high word adjusted (see
+// redc_digit), and the final correction is fix().
+// The digit multiplier is read from the constant bank so that ptxas keeps it one IMAD.WIDE (a literal modulus
+// word is split into IMAD + IMAD.HI + a 3-input add).
 static __constant__ uint32_t LCPC_FT63_Q = 0xb92f8a00u;   // 2^32 - P_HI
-static __constant__ uint32_t LCPC_NEG1 = 0xffffffffu;
 
 namespace ft63 {
 constexpr uint64_t P = 0x46d0760000000001ull;
@@ -118,11 +116,6 @@ constexpr uint64_t NEG_P = 0 - P;                         // 2^64 - p
 __device__ __forceinline__ uint64_t wmul(uint32_t a, uint32_t b) {
     uint64_t d;
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint64_t wmad(uint32_t a, uint32_t b, uint64_t c) {
-    uint64_t d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
     return d;
 }
 __device__ __forceinline__ uint32_t lo32(uint64_t x) { return (uint32_t)x; }
