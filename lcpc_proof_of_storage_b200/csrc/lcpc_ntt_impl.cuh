@@ -1,0 +1,416 @@
+// Ligero Reed-Solomon encoder: batched multi-row NTT over the lcpc prime fields (kernels and per-field host templates;
+// instantiated once per field in lcpc_ntt_f*.cu so that the four fields compile in parallel).
+//
+// Computes what the reference's LigeroEncodingRho::encode does per row
+// (lcpc-ligero-pc/src/lib.rs:162-164 -> fffft fft_io_pc): the length-n decimation-in-
+// frequency transform, in-order input, bit-reversed output,
+//     out[bitrev(i)] = sum_j in[j] * w^(i*j),   w = ROOT_OF_UNITY^(2^(S-k)), n = 2^k,
+// on zero-padded rows (lcpc-2d/src/lib.rs:665-682: the copy of the n_per_row message
+// into the n_cols-wide row is fused into the first pass's loads).
+//
+// Structure (B200): the in-place DIF is cut into passes.  A pass that covers r bits
+// is a radix-2^r transform held in registers (constant small twiddles from the kernel
+// parameter bank), followed by one multiplication per element by a per-pass twiddle
+// table T[m][lo] = w_sub^(lo*bitrev(m)) laid out so that a warp reads it coalesced.
+// Leading passes run over global memory with stride n/2^r ("strided" passes: adjacent
+// threads own adjacent columns, so every load/store is a full line); the trailing
+// 2^LB-point transform of each contiguous block runs out of shared memory
+// (limb planes, padded 1-in-16 against bank conflicts) in register-radix sub-steps.
+// Because an in-place DIF leaves element i holding X[bitrev(i)], no permutation pass
+// is needed for fffft's "io" order.
+#pragma once
+#include "lcpc_field.cuh"
+#include "lcpc_kernels.h"
+
+#ifndef LCPC_NTT_CTAS1
+#define LCPC_NTT_CTAS1 3  // resident 256-thread CTAs per SM for the one-limb field (register budget 80)
+#endif
+
+namespace lcpc {
+
+template <int FID>
+struct SmallTw {
+    typename Field<FID>::E w[8];
+};
+
+__device__ __forceinline__ unsigned bitrev_bits(unsigned x, int bits) {
+    return bits == 0 ? 0u : (__brev(x) >> (32 - bits));
+}
+
+// ------------------------------------------------------------------ plan-time kernels
+
+template <int FID>
+__global__ void k_init_root(const uint64_t *root_in, int log_n, uint64_t *w_out, uint64_t *stw_out) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    E w;
+    if (root_in != nullptr) {
+        w = ld_fe<L>(root_in);
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; i++) w.v[i] = field_consts(FID).root[i];
+        for (int i = 0; i < F::TWO_ADICITY - log_n; i++) w = F::mul(w, w);
+    }
+    st_fe<L>(w_out, w);
+    const uint64_t n = 1ull << log_n;
+    for (uint64_t e = 0; e < 8; e++) {
+        E v = F::one();
+        if ((e * n) % 16 == 0) v = F::pow(w, e * n / 16);
+        st_fe<L>(stw_out + e * L, v);
+    }
+}
+
+// T[m][lo] = w^(mult * lo * bitrev_R(m)), m < 2^R, lo < 2^log_n2
+template <int FID>
+__global__ void k_build_twiddles(uint64_t *out, const uint64_t *w_n, uint64_t mult, int R, int log_n2) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)1 << (R + log_n2);
+    if (idx >= total) return;
+    uint64_t m = idx >> log_n2, lo = idx & (((size_t)1 << log_n2) - 1);
+    uint64_t e = mult * lo * bitrev_bits((unsigned)m, R);
+    st_fe<L>(out + idx * L, F::pow(ld_fe<L>(w_n), e));
+}
+
+// ------------------------------------------------------------------ register radix
+
+// 2^R-point DIF on registers; x[j] ends up holding the output of index bitrev_R(j).
+template <int FID, int R>
+__device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], const SmallTw<FID> &tw) {
+    using F = Field<FID>;
+    using E = typename F::E;
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+        const int gap = 1 << (R - 1 - t);
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++) {
+            if ((j & gap) == 0) {
+                E a = x[j], b = x[j + gap];
+                x[j] = F::add(a, b);
+                const int e16 = ((j & (gap - 1)) << t) << (4 - R);  // exponent of w16
+                x[j + gap] = (e16 == 0) ? F::sub(a, b) : F::mul(F::sub_for_mul(a, b), tw.w[e16]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ strided pass
+
+template <int FID, int R>
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? LCPC_NTT_CTAS1 : 2)
+k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows,
+              int log_sub, const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    const int log_n2 = log_sub - R;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (n >> R)) return;
+    const size_t hi = g >> log_n2, lo = g & (((size_t)1 << log_n2) - 1);
+    const size_t base = (hi << log_sub) + lo;
+    for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        E x[1 << R];
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            const size_t idx = base + ((size_t)m << log_n2);
+            x[m] = idx < src_valid ? ld_fe<L>(src + (row * src_stride + idx) * L) : F::zero();
+        }
+        radix_dif<FID, R>(x, stw);
+        if constexpr (L == 1) {
+            E t[1 << R];
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+        } else {
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            const size_t idx = base + ((size_t)m << log_n2);
+            st_fe<L>(dst + (row * n + idx) * L, x[m]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ shared-memory block pass
+
+// shared-memory indices are 32-bit on purpose: 64-bit index arithmetic doubles the SHF/IADD3 count on the
+// ALU pipe, which is the pipe that bounds these kernels
+__device__ __forceinline__ unsigned sm_phys(unsigned i) { return i + (i >> 4); }
+
+// GSRC: the sub-step takes its inputs straight from global memory (the first sub-step of a block: adjacent
+// threads own adjacent elements, so the loads are full lines and the staging copy into shared memory, one
+// STS + LDS per element and a barrier, is skipped); elements at or beyond `valid` read as zero.
+template <int FID, int R, bool TW, bool GSRC>
+__device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                              const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
+                                              const uint64_t *__restrict__ gsrc, unsigned valid) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    const int log_n2 = log_sub - R;
+    const unsigned groups = (1u << LB) >> R;
+    for (unsigned g = threadIdx.x; g < groups; g += blockDim.x) {
+        const unsigned hi = g >> log_n2, lo = g & ((1u << log_n2) - 1);
+        const unsigned base = (hi << log_sub) + lo;
+        E x[1 << R];
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            const unsigned i = base + ((unsigned)m << log_n2);
+            if constexpr (GSRC) {
+                x[m] = i < valid ? ld_fe<L>(gsrc + (size_t)i * L) : F::zero();
+            } else {
+                const unsigned p = sm_phys(i);
+#pragma unroll
+                for (int l = 0; l < L; l++) x[m].v[l] = sm[l * plane + p];
+            }
+        }
+        radix_dif<FID, R>(x, stw);
+        if constexpr (TW) {
+            if constexpr (L == 1) {
+                // all pass twiddles of this group in flight together (one exposed L1/L2 latency, not 2^R - 1)
+                E t[1 << R];
+#pragma unroll
+                for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((unsigned)m << log_n2) + lo) * L);
+#pragma unroll
+                for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
+            } else {
+                // wide elements: keep one twiddle live at a time (register pressure decides occupancy here)
+#pragma unroll
+                for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (size_t)(((unsigned)m << log_n2) + lo) * L));
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            const unsigned p = sm_phys(base + ((unsigned)m << log_n2));
+#pragma unroll
+            for (int l = 0; l < L; l++) sm[l * plane + p] = x[m].v[l];
+        }
+    }
+}
+
+template <int FID, int R, bool GSRC>
+__device__ __forceinline__ void block_substep_any(uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                                  const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
+                                                  const uint64_t *__restrict__ gsrc, unsigned valid) {
+    if (log_sub - R > 0) block_substep<FID, R, true, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    else block_substep<FID, R, false, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+}
+
+template <int FID, int RMAX, bool GSRC>
+__device__ __forceinline__ void block_substep_r(int R, uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                                const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
+                                                const uint64_t *__restrict__ gsrc, unsigned valid) {
+    if (R == 4) {
+        if constexpr (RMAX >= 4) block_substep_any<FID, 4, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    } else if (R == 3) {
+        block_substep_any<FID, 3, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    } else if (R == 2) {
+        block_substep_any<FID, 2, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    } else {
+        block_substep_any<FID, 1, GSRC>(sm, plane, LB, log_sub, tw, stw, gsrc, valid);
+    }
+}
+
+template <int FID, int RMAX, bool SCATTER>
+__global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? LCPC_NTT_CTAS1 : 2)
+k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows, int LB,
+            const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw,
+            const __grid_constant__ ScatterDst sc) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    extern __shared__ uint64_t sm[];
+    const unsigned NB = 1u << LB;
+    const unsigned plane = NB + (NB >> 4) + 1;
+    const size_t col0 = (size_t)blockIdx.x << LB;
+    const unsigned valid = src_valid > col0 ? (unsigned)(src_valid - col0 < NB ? src_valid - col0 : NB) : 0u;
+    for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        int log_sub = LB;
+        size_t tw_off = 0;
+        bool first = true;
+        while (log_sub > 0) {
+            const int R = log_sub < RMAX ? log_sub : RMAX;
+            const uint64_t *t = tw + tw_off * L;
+            if (first) block_substep_r<FID, RMAX, true>(R, sm, plane, LB, log_sub, t, stw, src + (row * src_stride + col0) * L, valid);
+            else block_substep_r<FID, RMAX, false>(R, sm, plane, LB, log_sub, t, stw, nullptr, 0u);
+            first = false;
+            if (log_sub - R > 0) tw_off += (size_t)1 << log_sub;
+            log_sub -= R;
+            __syncthreads();
+        }
+        for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) {
+            E v;
+            const unsigned p = sm_phys(i);
+#pragma unroll
+            for (int l = 0; l < L; l++) v.v[l] = sm[l * plane + p];
+            if constexpr (SCATTER) {
+                // whole block lands in one rank's column-block matrix (1 << log_cb >= 1 << LB)
+                uint64_t *base = sc.base[col0 >> sc.log_cb];
+                const size_t off = ((sc.row0 + row) << sc.log_cb) + (col0 & (((size_t)1 << sc.log_cb) - 1)) + i;
+                st_fe<L>(base + off * L, v);
+            } else {
+                st_fe<L>(dst + (row * n + col0 + i) * L, v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ host side
+
+static int block_bits_max(int limbs) { return limbs == 1 ? 12 : (limbs == 2 ? 11 : 10); }
+static int radix_max(int limbs) { return limbs <= 2 ? 4 : 3; }
+
+template <int FID>
+cudaError_t plan_build_t(NttPlan &plan, int log_n, const uint64_t *root_mont, const Launch &lc) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    plan.fid = FID;
+    plan.log_n = log_n;
+    plan.n = (size_t)1 << log_n;
+    plan.passes.clear();
+    const int rmax = radix_max(L);
+    const int lb = log_n < block_bits_max(L) ? log_n : block_bits_max(L);
+    // leading strided passes
+    int rem = log_n - lb;
+    int n_strided = (rem + rmax - 1) / rmax;
+    size_t tw_elems = 0;
+    int log_sub = log_n;
+    for (int i = 0; i < n_strided; i++) {
+        int bits = rem / (n_strided - i) + ((rem % (n_strided - i)) ? 1 : 0);
+        plan.passes.push_back({0, bits, log_sub, tw_elems});
+        tw_elems += (size_t)1 << log_sub;
+        log_sub -= bits;
+        rem -= bits;
+    }
+    // trailing block pass and its sub-step tables
+    if (lb > 0) {
+        plan.passes.push_back({1, lb, lb, tw_elems});
+        int ls = lb;
+        while (ls > 0) {
+            int r = ls < rmax ? ls : rmax;
+            if (ls - r > 0) tw_elems += (size_t)1 << ls;
+            ls -= r;
+        }
+    }
+    plan.tw_elems = tw_elems;
+    cudaError_t e;
+    uint64_t *d_consts = nullptr;  // [w_n | stw(8)] | optional root_in
+    if ((e = cudaMalloc(&d_consts, (size_t)(1 + 8 + 1) * L * sizeof(uint64_t))) != cudaSuccess) return e;
+    uint64_t *d_root_in = nullptr;
+    if (root_mont != nullptr) {
+        d_root_in = d_consts + 9 * L;
+        if ((e = cudaMemcpyAsync(d_root_in, root_mont, L * sizeof(uint64_t), cudaMemcpyHostToDevice, lc.s)) != cudaSuccess) {
+            cudaFree(d_consts);
+            return e;
+        }
+    }
+    lc.begin("k_init_root");
+    k_init_root<FID><<<1, 1, 0, lc.s>>>(d_root_in, log_n, d_consts, d_consts + L);
+    lc.end();
+    if (tw_elems > 0) {
+        if ((e = cudaMalloc(&plan.d_tw, tw_elems * L * sizeof(uint64_t))) != cudaSuccess) {
+            cudaFree(d_consts);
+            return e;
+        }
+    }
+    auto build = [&](size_t off, int ls, int r) {
+        size_t total = (size_t)1 << ls;
+        unsigned blocks = (unsigned)((total + 255) / 256);
+        lc.begin("k_build_twiddles");
+        k_build_twiddles<FID><<<blocks, 256, 0, lc.s>>>(plan.d_tw + off * L, d_consts, (uint64_t)1 << (log_n - ls), r, ls - r);
+        lc.end();
+    };
+    for (const NttPass &p : plan.passes) {
+        if (p.kind == 0) {
+            build(p.tw_off, p.log_sub, p.bits);
+        } else {
+            int ls = p.bits;
+            size_t off = p.tw_off;
+            while (ls > 0) {
+                int r = ls < rmax ? ls : rmax;
+                if (ls - r > 0) {
+                    build(off, ls, r);
+                    off += (size_t)1 << ls;
+                }
+                ls -= r;
+            }
+        }
+    }
+    uint64_t h_stw[8 * L];
+    e = cudaMemcpyAsync(h_stw, d_consts + L, sizeof h_stw, cudaMemcpyDeviceToHost, lc.s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(lc.s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_consts);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 8; i++)
+        for (int l = 0; l < MAX_LIMBS; l++) plan.stw.w[i][l] = l < L ? h_stw[i * L + l] : 0;
+    return cudaSuccess;
+}
+
+template <int FID>
+cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
+                            uint64_t *dst, size_t n_rows, const Launch &lc, const ScatterDst *scatter) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    constexpr int RMAX = L <= 2 ? 4 : 3;
+    if (n_rows == 0) return cudaSuccess;
+    SmallTw<FID> stw;
+    for (int i = 0; i < 8; i++)
+        for (int l = 0; l < L; l++) stw.w[i].v[l] = plan.stw.w[i][l];
+    const size_t n = plan.n;
+    const unsigned gy = (unsigned)(n_rows < 65535 ? n_rows : 65535);
+    if (plan.log_n == 0) {  // length-1 transform: a copy
+        if (src != dst || src_stride != n)
+            return cudaMemcpy2DAsync(dst, n * L * 8, src, src_stride * L * 8, L * 8, n_rows, cudaMemcpyDeviceToDevice, lc.s);
+        return cudaSuccess;
+    }
+    bool first = true;
+    for (const NttPass &p : plan.passes) {
+        const uint64_t *in = first ? src : dst;
+        const size_t in_stride = first ? src_stride : n;
+        const size_t in_valid = first ? src_valid : n;
+        const uint64_t *tw = plan.d_tw + p.tw_off * L;
+        if (p.kind == 0) {
+            const size_t groups = n >> p.bits;
+            dim3 grid((unsigned)((groups + 255) / 256), gy);
+            lc.begin("k_ntt_strided");
+            switch (p.bits) {
+            case 1: k_ntt_strided<FID, 1><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break;
+            case 2: k_ntt_strided<FID, 2><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break;
+            case 3: k_ntt_strided<FID, 3><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break;
+            default:
+                if constexpr (RMAX >= 4)
+                    k_ntt_strided<FID, 4><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw);
+                break;
+            }
+        } else {
+            const int LB = p.bits;
+            const size_t NB = (size_t)1 << LB;
+            const size_t plane = NB + (NB >> 4) + 1;
+            const size_t smem = plane * L * sizeof(uint64_t);
+            size_t thr = NB >> RMAX;
+            thr = thr < 32 ? 32 : (thr > 256 ? 256 : thr);
+            dim3 grid((unsigned)(n >> LB), gy);
+            if (scatter) {
+                if (LB > scatter->log_cb) return cudaErrorInvalidValue;
+                lc.begin("k_ntt_block_scatter");
+                k_ntt_block<FID, RMAX, true><<<grid, (unsigned)thr, smem, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, LB, tw, stw, *scatter);
+            } else {
+                lc.begin("k_ntt_block");
+                k_ntt_block<FID, RMAX, false><<<grid, (unsigned)thr, smem, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, LB, tw, stw, ScatterDst{});
+            }
+        }
+        lc.end();
+        first = false;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace lcpc
