@@ -146,18 +146,29 @@ __device__ __forceinline__ unsigned sm_phys(unsigned i) { return i + (i >> 4); }
 // GSRC: the sub-step takes its inputs straight from global memory (the first sub-step of a block: adjacent
 // threads own adjacent elements, so the loads are full lines and the staging copy into shared memory, one
 // STS + LDS per element and a barrier, is skipped); elements at or beyond `valid` read as zero.
-template <int FID, int R, bool TW, bool GSRC>
+// LN2 >= 0 fixes log_sub - R at compile time (the 4096-point block of the one-limb field): every shared-memory and
+// twiddle address is then one base plus a literal offset, instead of five integer instructions per access (shift,
+// add, two LEAs for the 1-in-16 padding and the byte address) -- 14 % of the executed instructions, mostly on the
+// ALU pipe that bounds the kernel.
+template <int FID, int R, bool TW, bool GSRC, int LN2 = -1>
 __device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int LB, int log_sub,
                                               const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
                                               const uint64_t *__restrict__ gsrc, unsigned valid) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
-    const int log_n2 = log_sub - R;
+    const int log_n2 = LN2 >= 0 ? LN2 : log_sub - R;
+    // padded index of element base + (m << log_n2), given p0 = sm_phys(base)
+    auto phys = [&](unsigned base, unsigned p0, int m) -> unsigned {
+        if constexpr (LN2 >= 4) return p0 + (unsigned)m * ((1u << LN2) + (1u << (LN2 - 4)));  // m << LN2 is a multiple of 16
+        else if constexpr (LN2 == 0) return p0 + (unsigned)m;                                  // base is a multiple of 2^R = 16
+        else return sm_phys(base + ((unsigned)m << log_n2));
+    };
     const unsigned groups = (1u << LB) >> R;
     for (unsigned g = threadIdx.x; g < groups; g += blockDim.x) {
         const unsigned hi = g >> log_n2, lo = g & ((1u << log_n2) - 1);
         const unsigned base = (hi << log_sub) + lo;
+        const unsigned p0 = sm_phys(base);
         E x[1 << R];
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
@@ -165,7 +176,7 @@ __device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int 
             if constexpr (GSRC) {
                 x[m] = i < valid ? ld_fe<L>(gsrc + (size_t)i * L) : F::zero();
             } else {
-                const unsigned p = sm_phys(i);
+                const unsigned p = phys(base, p0, m);
 #pragma unroll
                 for (int l = 0; l < L; l++) x[m].v[l] = sm[l * plane + p];
             }
@@ -187,7 +198,7 @@ __device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int 
         }
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
-            const unsigned p = sm_phys(base + ((unsigned)m << log_n2));
+            const unsigned p = phys(base, p0, m);
 #pragma unroll
             for (int l = 0; l < L; l++) sm[l * plane + p] = x[m].v[l];
         }
@@ -231,7 +242,17 @@ k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *
     const size_t col0 = (size_t)blockIdx.x << LB;
     const unsigned valid = src_valid > col0 ? (unsigned)(src_valid - col0 < NB ? src_valid - col0 : NB) : 0u;
     for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
-        int log_sub = LB;
+        if constexpr (L == 1 && RMAX == 4) {
+            if (LB == 12) {  // the full-size block: three radix-16 sub-steps with literal strides 256, 16, 1
+                block_substep<FID, 4, true, true, 8>(sm, plane, 12, 12, tw, stw, src + (row * src_stride + col0) * L, valid);
+                __syncthreads();
+                block_substep<FID, 4, true, false, 4>(sm, plane, 12, 8, tw + ((size_t)1 << 12) * L, stw, nullptr, 0u);
+                __syncthreads();
+                block_substep<FID, 4, false, false, 0>(sm, plane, 12, 4, nullptr, stw, nullptr, 0u);
+                __syncthreads();
+            }
+        }
+        int log_sub = (L == 1 && RMAX == 4 && LB == 12) ? 0 : LB;
         size_t tw_off = 0;
         bool first = true;
         while (log_sub > 0) {
