@@ -78,7 +78,10 @@ __global__ void k_build_twiddles(uint64_t *out, const uint64_t *w_n, uint64_t mu
 // ------------------------------------------------------------------ register radix
 
 // 2^R-point DIF on registers; x[j] ends up holding the output of index bitrev_R(j).
-template <int FID, int R>
+// ZB > 0: the inputs x[m], m >= 2^(R - ZB), are known to be zero (the zero padding of a rate-2^-ZB Reed-Solomon
+// row in the first pass).  In the first ZB stages every butterfly then has a zero lower input: the sum is the
+// upper input itself and the difference is the upper input, so both the addition and the subtraction disappear.
+template <int FID, int R, int ZB = 0>
 __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], const SmallTw<FID> &tw) {
     using F = Field<FID>;
     using E = typename F::E;
@@ -88,10 +91,14 @@ __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], c
 #pragma unroll
         for (int j = 0; j < (1 << R); j++) {
             if ((j & gap) == 0) {
-                E a = x[j], b = x[j + gap];
-                x[j] = F::add(a, b);
                 const int e16 = ((j & (gap - 1)) << t) << (4 - R);  // exponent of w16
-                x[j + gap] = (e16 == 0) ? F::sub(a, b) : F::mul(F::sub_for_mul(a, b), tw.w[e16]);
+                if (t < ZB) {
+                    x[j + gap] = (e16 == 0) ? x[j] : F::mul(x[j], tw.w[e16]);
+                } else {
+                    E a = x[j], b = x[j + gap];
+                    x[j] = F::add(a, b);
+                    x[j + gap] = (e16 == 0) ? F::sub(a, b) : F::mul(F::sub_for_mul(a, b), tw.w[e16]);
+                }
             }
         }
     }
@@ -99,41 +106,47 @@ __device__ __forceinline__ void radix_dif(typename Field<FID>::E (&x)[1 << R], c
 
 // ------------------------------------------------------------------ strided pass
 
-template <int FID, int R>
+// LN2 >= 0: log_sub - R is that literal (the last strided pass always leaves blocks of 2^LBMAX elements), so every
+// element and twiddle address is one base pointer plus a literal offset.  ZB > 0: first pass of a rate-2^-ZB code,
+// src_valid == n >> ZB: the zero half (three quarters) is neither loaded nor bounds-checked, see radix_dif.
+template <int FID, int R, int LN2 = -1, int ZB = 0>
 __global__ void __launch_bounds__(256, Field<FID>::LIMBS == 1 ? LCPC_NTT_CTAS1 : 2)
 k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows,
               int log_sub, const uint64_t *__restrict__ tw, const __grid_constant__ SmallTw<FID> stw) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
-    const int log_n2 = log_sub - R;
+    const int log_n2 = LN2 >= 0 ? LN2 : log_sub - R;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (n >> R)) return;
     const size_t hi = g >> log_n2, lo = g & (((size_t)1 << log_n2) - 1);
     const size_t base = (hi << log_sub) + lo;
     for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
         E x[1 << R];
+        const uint64_t *in = src + (row * src_stride + base) * L;
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
-            const size_t idx = base + ((size_t)m << log_n2);
-            x[m] = idx < src_valid ? ld_fe<L>(src + (row * src_stride + idx) * L) : F::zero();
+            if constexpr (ZB > 0) {
+                x[m] = m < (1 << (R - ZB)) ? ld_fe<L>(in + ((size_t)m << log_n2) * L) : F::zero();
+            } else {
+                x[m] = base + ((size_t)m << log_n2) < src_valid ? ld_fe<L>(in + ((size_t)m << log_n2) * L) : F::zero();
+            }
         }
-        radix_dif<FID, R>(x, stw);
+        radix_dif<FID, R, ZB>(x, stw);
+        const uint64_t *twp = tw + lo * L;
         if constexpr (L == 1) {
             E t[1 << R];
 #pragma unroll
-            for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L);
+            for (int m = 1; m < (1 << R); m++) t[m] = ld_fe<L>(twp + ((size_t)m << log_n2) * L);
 #pragma unroll
             for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], t[m]);
         } else {
 #pragma unroll
-            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(tw + (((size_t)m << log_n2) + lo) * L));
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(twp + ((size_t)m << log_n2) * L));
         }
+        uint64_t *out = dst + (row * n + base) * L;
 #pragma unroll
-        for (int m = 0; m < (1 << R); m++) {
-            const size_t idx = base + ((size_t)m << log_n2);
-            st_fe<L>(dst + (row * n + idx) * L, x[m]);
-        }
+        for (int m = 0; m < (1 << R); m++) st_fe<L>(out + ((size_t)m << log_n2) * L, x[m]);
     }
 }
 
@@ -402,15 +415,34 @@ cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride
             const size_t groups = n >> p.bits;
             dim3 grid((unsigned)((groups + 255) / 256), gy);
             lc.begin("k_ntt_strided");
+            // specialised instances for the one-limb field: literal stride when this pass leaves full blocks behind, and
+            // zero-aware first stage(s) when it is the first pass over a rate-1/2 or rate-1/4 row
+            const int lbmax = block_bits_max(L);
+            int zb = 0;
+            if (first && in_valid < n) {
+                if ((in_valid << 1) == n) zb = 1;
+                else if ((in_valid << 2) == n) zb = 2;
+            }
+            if (zb > p.bits) zb = 0;
+            const bool lit = L == 1 && p.log_sub - p.bits == lbmax;
+#define LCPC_STRIDED(RR)                                                                                                       \
+    do {                                                                                                                       \
+        if constexpr (L == 1) {                                                                                                \
+            if (lit && zb == 1 && RR >= 1) { k_ntt_strided<FID, RR, 12, (RR >= 1 ? 1 : 0)><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
+            if (lit && zb == 0) { k_ntt_strided<FID, RR, 12, 0><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
+            if (!lit && zb == 1 && RR >= 1) { k_ntt_strided<FID, RR, -1, (RR >= 1 ? 1 : 0)><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
+        }                                                                                                                      \
+        k_ntt_strided<FID, RR><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw);            \
+    } while (0)
             switch (p.bits) {
-            case 1: k_ntt_strided<FID, 1><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break;
-            case 2: k_ntt_strided<FID, 2><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break;
-            case 3: k_ntt_strided<FID, 3><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break;
+            case 1: LCPC_STRIDED(1); break;
+            case 2: LCPC_STRIDED(2); break;
+            case 3: LCPC_STRIDED(3); break;
             default:
-                if constexpr (RMAX >= 4)
-                    k_ntt_strided<FID, 4><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw);
+                if constexpr (RMAX >= 4) LCPC_STRIDED(4);
                 break;
             }
+#undef LCPC_STRIDED
         } else {
             const int LB = p.bits;
             const size_t NB = (size_t)1 << LB;
