@@ -150,6 +150,67 @@ k_ntt_strided(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t
     }
 }
 
+// ------------------------------------------------------------------ two strided passes in one trip
+
+// For rows longer than 16 * 4096 the leading RA + RB bits take two strided passes, i.e. two full trips through HBM;
+// at 2^28 coefficients those two kernels are bandwidth-bound (4.5 TB/s) while everything else is bound by the integer
+// pipes.  This kernel does both passes on a tile that stays in shared memory: the CTA owns all 2^(RA+RB) elements at
+// stride 4096 for 32 adjacent columns, runs pass A (radix 2^RA over the top bits, table twA) into shared memory and
+// pass B (radix 2^RB over the next bits, table twB) out of it.  Same arithmetic, same tables, half the HBM traffic.
+// One-limb field, first passes of the transform (log_sub = log_n), log_n - RA - RB = 12.
+template <int FID, int RA, int RB, int ZB>
+__global__ void __launch_bounds__(256, 3)
+k_ntt_strided_fused(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst, size_t n, size_t n_rows,
+                    const uint64_t *__restrict__ twA, const uint64_t *__restrict__ twB,
+                    const __grid_constant__ SmallTw<FID> stw) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    static_assert(F::LIMBS == 1, "one-limb field only");
+    constexpr int R = RA + RB, LN2 = 12, C = 32;
+    __shared__ uint64_t tile[1 << R][C];
+    const unsigned c = threadIdx.x & (C - 1), u = threadIdx.x >> 5;  // column inside the tile, phase-specific index
+    const size_t col = (size_t)blockIdx.x * C + c;                   // lo2: position inside the final 4096-block
+    for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        // pass A: thread (sB = u, c) owns the 2^RA elements s = a * 2^RB + sB; lo1 = sB * 4096 + col
+        for (unsigned sB = u; sB < (1u << RB); sB += blockDim.x / C) {
+            const size_t lo1 = ((size_t)sB << LN2) + col;
+            const uint64_t *in = src + (row * src_stride + lo1);
+            E x[1 << RA];
+#pragma unroll
+            for (int a = 0; a < (1 << RA); a++) {
+                const size_t off = (size_t)a << (LN2 + RB);
+                if constexpr (ZB > 0) x[a].v[0] = a < (1 << (RA - ZB)) ? in[off] : 0;
+                else x[a].v[0] = lo1 + off < src_valid ? in[off] : 0;
+            }
+            radix_dif<FID, RA, ZB>(x, stw);
+            E t[1 << RA];
+#pragma unroll
+            for (int a = 1; a < (1 << RA); a++) t[a].v[0] = twA[((size_t)a << (LN2 + RB)) + lo1];
+#pragma unroll
+            for (int a = 1; a < (1 << RA); a++) x[a] = F::mul(x[a], t[a]);
+#pragma unroll
+            for (int a = 0; a < (1 << RA); a++) tile[(a << RB) + sB][c] = x[a].v[0];
+        }
+        __syncthreads();
+        // pass B: thread (a = u, c) owns the 2^RB elements of sub-block a; lo2 = col
+        for (unsigned a = u; a < (1u << RA); a += blockDim.x / C) {
+            E x[1 << RB];
+#pragma unroll
+            for (int b = 0; b < (1 << RB); b++) x[b].v[0] = tile[(a << RB) + b][c];
+            radix_dif<FID, RB, 0>(x, stw);
+            E t[1 << RB];
+#pragma unroll
+            for (int b = 1; b < (1 << RB); b++) t[b].v[0] = twB[((size_t)b << LN2) + col];
+#pragma unroll
+            for (int b = 1; b < (1 << RB); b++) x[b] = F::mul(x[b], t[b]);
+            uint64_t *out = dst + (row * n + ((size_t)a << (LN2 + RB)) + col);
+#pragma unroll
+            for (int b = 0; b < (1 << RB); b++) out[(size_t)b << LN2] = x[b].v[0];
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ shared-memory block pass
 
 // shared-memory indices are 32-bit on purpose: 64-bit index arithmetic doubles the SHF/IADD3 count on the
@@ -406,7 +467,34 @@ cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride
         return cudaSuccess;
     }
     bool first = true;
+    size_t skip = 0;
+    if constexpr (L == 1) {
+        // two leading strided passes that end on 4096-blocks: one trip through HBM instead of two
+        if (plan.passes.size() >= 3 && plan.passes[0].kind == 0 && plan.passes[1].kind == 0 && plan.passes[2].kind == 1 &&
+            plan.passes[1].log_sub - plan.passes[1].bits == 12 && plan.passes[0].bits == 3 &&
+            (plan.passes[1].bits == 2 || plan.passes[1].bits == 3)) {
+            const NttPass &pa = plan.passes[0], &pb = plan.passes[1];
+            const uint64_t *twA = plan.d_tw + pa.tw_off, *twB = plan.d_tw + pb.tw_off;
+            const bool zb = (src_valid << 1) == n;
+            dim3 grid((unsigned)(4096 / 32), gy);
+            lc.begin("k_ntt_strided_fused");
+            if (pb.bits == 3) {
+                if (zb) k_ntt_strided_fused<FID, 3, 3, 1><<<grid, 256, 0, lc.s>>>(src, src_stride, src_valid, dst, n, n_rows, twA, twB, stw);
+                else k_ntt_strided_fused<FID, 3, 3, 0><<<grid, 256, 0, lc.s>>>(src, src_stride, src_valid, dst, n, n_rows, twA, twB, stw);
+            } else {
+                if (zb) k_ntt_strided_fused<FID, 3, 2, 1><<<grid, 256, 0, lc.s>>>(src, src_stride, src_valid, dst, n, n_rows, twA, twB, stw);
+                else k_ntt_strided_fused<FID, 3, 2, 0><<<grid, 256, 0, lc.s>>>(src, src_stride, src_valid, dst, n, n_rows, twA, twB, stw);
+            }
+            lc.end();
+            first = false;
+            skip = 2;
+        }
+    }
     for (const NttPass &p : plan.passes) {
+        if (skip) {
+            skip--;
+            continue;
+        }
         const uint64_t *in = first ? src : dst;
         const size_t in_stride = first ? src_stride : n;
         const size_t in_valid = first ? src_valid : n;
