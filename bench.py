@@ -133,9 +133,9 @@ def measured_peak_gbs():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload
-# (profiles/r01c_summary.md); None for kernels that were not captured
-NCU_DRAM_TRAFFIC = {"k_ntt_strided": 134_734_848 + 214_809_600, "k_ntt_block": 268_627_968 + 213_919_744,
-                    "k_hash_chunks": 268_462_080 + 10_329_344}
+# (profiles/r01e_summary.md); None for kernels that were not captured
+NCU_DRAM_TRAFFIC = {"k_ntt_strided": 134_726_656 + 212_986_368, "k_ntt_block": 268_538_368 + 212_768_512,
+                    "k_hash_chunks": 268_462_848 + 11_402_240}
 
 
 # per-kernel compulsory HBM bytes for one launch at this workload (DESIGN.md "Kernels")
@@ -410,7 +410,7 @@ def main() -> None:
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach else None,
                     "traffic": NCU_DRAM_TRAFFIC.get(name.replace("_scatter", "")) if world == 1 else None,
-                    "traffic_source": "ncu --set full, profiles/r01c_summary.md", "peak_source": peak_src,
+                    "traffic_source": "ncu --set full, profiles/r01e_summary.md", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                     "share_of_step": total_ms / ms_total_timed,
                     "ms_per_step_with_launch_events": ms_total_timed / steps,
