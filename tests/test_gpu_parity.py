@@ -85,6 +85,12 @@ COMMIT_CASES = [
     (0, 300 * 2048 - 777, 2048, 4096),
     (0, 9 * 65536 - 1, 65536, 131072),
     (3, 75 * 2048 - 5, 2048, 4096),
+    # strided first passes whose valid prefix is not half the row: non power-of-two n_per_row (bounds-checked loads),
+    # rate 1/4, and the fused two-pass kernel with a ragged prefix
+    (0, 5 * 20000 - 7, 20000, 65536),
+    (0, 3 * 16384, 16384, 65536),
+    (0, 2 * 50000 - 1, 50000, 131072),
+    (0, 2 * 65536, 65536, 262144),
     # a million multi-limb coefficients each: ~2e7 Montgomery products per case through every NTT pass shape
     (1, (1 << 20) - 3, 16384, 32768),
     (3, (1 << 20) - 3, 16384, 32768),
