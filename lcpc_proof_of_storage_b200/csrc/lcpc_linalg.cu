@@ -322,28 +322,43 @@ cudaError_t pack_bytes7(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elem
 // x[col_k][b .. b+GS) is then one contiguous run, the non-zero a[i,k] is loaded once per lane group
 // instead of once per matrix row, and the output run is contiguous too.  A lane group of GS = 8, 16 or
 // 32 lanes owns one output index i; a warp covers 32/GS of them.
-template <int FID>
+// KSPLIT (the deep levels, a few hundred rows): the whole warp owns ONE output index and its 32/GS lane groups take
+// every (32/GS)-th non-zero, then add up through shuffles -- those levels are a chain of dependent L2 round trips per
+// thread and nothing else, so a chain four times shorter is a launch three times shorter.
+template <int FID, bool KSPLIT>
 __global__ void __launch_bounds__(128)
 k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint64_t *__restrict__ data,
          size_t m_rows, const uint64_t *xT, uint64_t *yT, size_t bp, int log_gs) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
-    const int gs = 1 << log_gs;
+    const int gs = 1 << log_gs, slices = 32 >> log_gs;
     const int lane = threadIdx.x & 31, sub = lane >> log_gs, bl = lane & (gs - 1);
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t i = warp * (32 >> log_gs) + sub;
+    const size_t i = KSPLIT ? warp : warp * slices + sub;
     if (i >= m_rows) return;
     const uint32_t k0 = rowptr[i], k1 = rowptr[i + 1];
+    const uint32_t kfirst = KSPLIT ? k0 + (uint32_t)sub : k0, kstep = KSPLIT ? (uint32_t)slices : 1u;
     for (size_t b = (size_t)blockIdx.y * gs + bl; b < bp; b += (size_t)gridDim.y * gs) {
         typename F::Dot acc;  // `data` is pre-scaled by 2^32 for the multi-limb fields (scale_csr_data)
         F::dot_init(acc);
-        for (uint32_t k = k0; k < k1; k++) {
+        for (uint32_t k = kfirst; k < k1; k += kstep) {
             const E a = ld_fe<L>(data + (size_t)k * L);
             const E x = ld_fe<L>(xT + ((size_t)colidx[k] * bp + b) * L);
             F::dot_mac(acc, a, x);
         }
-        st_fe<L>(yT + (i * bp + b) * L, F::dot_finish_prescaled(acc));
+        E r = F::dot_finish_prescaled(acc);
+        if constexpr (KSPLIT) {
+            for (int off = gs; off < 32; off <<= 1) {
+                E o;
+#pragma unroll
+                for (int l = 0; l < L; l++) o.v[l] = __shfl_xor_sync(0xffffffffu, r.v[l], off);
+                r = F::add(r, o);
+            }
+            if (sub == 0) st_fe<L>(yT + (i * bp + b) * L, r);
+        } else {
+            st_fe<L>(yT + (i * bp + b) * L, r);
+        }
     }
 }
 
@@ -492,11 +507,14 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t 
     transpose_launch<L>(d_comm, n_rows, npr, n_cols, xT, bp, 1, lc);
     auto spmv = [&](const DevCsr &m, size_t x_off, uint64_t *y) {
         if (m.rows == 0) return;
-        const size_t rows_per_cta = 4 * (32 >> log_gs);
-        const size_t groups = bp / gs;
+        const size_t slices = (size_t)32 >> log_gs, groups = bp / gs;
+        // too few warps to fill the machine: one row per warp, its non-zeros split over the lane groups
+        const bool ksplit = slices > 1 && (m.rows / slices + 1) * groups < (size_t)148 * 16;
+        const size_t rows_per_cta = ksplit ? 4 : 4 * slices;
         dim3 grid((unsigned)((m.rows + rows_per_cta - 1) / rows_per_cta), (unsigned)(groups < 65535 ? groups : 65535));
         lc.begin("k_spmv_t");
-        k_spmv_t<FID><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, xT + x_off * bp * L, y, bp, log_gs);
+        if (ksplit) k_spmv_t<FID, true><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, xT + x_off * bp * L, y, bp, log_gs);
+        else k_spmv_t<FID, false><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, xT + x_off * bp * L, y, bp, log_gs);
         lc.end();
     };
     // encode.rs:46-58 precodes all the way down
