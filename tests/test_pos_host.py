@@ -44,3 +44,44 @@ def test_dimension_errors_follow_the_reference_messages():
                       (pos.Specified(8, 8), "greater than the number of columns")]:
         with pytest.raises(ValueError, match=msg):
             pos.convert_file_data_to_commit(b"x" * 100, pos.Commit(), dims)
+
+
+# ----------------------------------------------------------------------------- encoded_file.py host pieces (no GPU)
+
+def test_merkle_tree_mirror_matches_oracle_paths(oracle):
+    """MerkleTree::{new layout, root, get_path, to_bytes, from_bytes} (lcpc_online/merkle_tree.rs:7-100) on a tree built by
+    the oracle: get_path must equal open_column's path (lcpc-2d lib.rs:841-851)."""
+    import numpy as np
+
+    from lcpc_proof_of_storage_b200 import encoded_file as EF
+
+    O = oracle
+    c = O.commit(O.random_field_elements(0, 3, 700), O.LigeroEncoding(0, 16, 32))
+    t = EF.MerkleTree(c.hashes)
+    assert t.width == 32 and len(t) == 63 and t.root() == c.get_root()
+    for col in (0, 1, 17, 31):
+        assert t.get_path(col) == [bytes(p) for p in O.open_column(c, col).path]
+    assert t.get_path(32) is None
+    t2 = EF.MerkleTree.from_bytes(t.to_bytes())
+    assert t2.root() == t.root() and t2[5] == t[5]
+    import pytest
+
+    with pytest.raises(ValueError):
+        EF.MerkleTree(np.zeros((6, 32), dtype=np.uint8))  # not 2^k - 1 digests
+
+
+def test_encoded_file_metadata_json_round_trip(tmp_path):
+    """encoded_file_metadata.rs:5-27: the serde_json field names."""
+    import json
+
+    from lcpc_proof_of_storage_b200 import encoded_file as EF
+
+    m = EF.EncodedFileMetadata(EF._new_ulid(), 4, 8, 22, 44, 598)
+    path = tmp_path / "f.meta"
+    with open(path, "wb") as f:
+        m.write_to_file(f)
+    raw = json.loads(path.read_text())
+    assert list(raw) == ["ulid", "pre_encoded_size", "encoded_size", "rows_written", "row_capacity", "bytes_of_data"]
+    assert len(raw["ulid"]) == 26 and set(raw["ulid"]) <= set("0123456789ABCDEFGHJKMNPQRSTVWXYZ")
+    with open(path, "rb") as f:
+        assert EF.EncodedFileMetadata.read_from_file(f) == m
