@@ -64,6 +64,27 @@ def make_coeffs(seed: int, n: int) -> np.ndarray:
     return z.reshape(n, 1)
 
 
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host buffer is allocated, so that
+    first touch puts the buffers on the GPU's NUMA node (with N ranks copying 128 MiB each, remote-socket buffers are what
+    limits the end-to-end step).  Best effort: returns what was done."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {index}"
+        return "no local cpus reported"
+    except Exception as e:  # NVML missing, cgroup restrictions, ...
+        return f"unbound ({type(e).__name__})"
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -243,6 +264,7 @@ def main() -> None:
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: not bound"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -451,6 +473,7 @@ def main() -> None:
                        f"row shards x{world}; " + ("encode kernel stores into peer column blocks over NVLink (symmetric memory)"
                                                    if sc.fused else "NCCL all-to-all") + "; per-rank Merkle subtrees, roots all-gathered")},
         "algorithmic_GBps": step_gbs,
+        "host_binding": numa,
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
         "root": gpu_root,
     }
