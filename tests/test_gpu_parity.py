@@ -91,6 +91,12 @@ COMMIT_CASES = [
     (0, 3 * 16384, 16384, 65536),
     (0, 2 * 50000 - 1, 50000, 131072),
     (0, 2 * 65536, 65536, 262144),
+    # many BLAKE3 chunks per column: the level-parallel chunk merge (8+ chunks), even / odd / non power-of-two counts
+    (0, 2000 * 64, 64, 128),        # 16 chunks
+    (0, 1100 * 32 - 5, 32, 64),     # 9 chunks: the last one is carried up four levels
+    (0, 5000 * 16, 16, 32),         # 40 chunks
+    (1, 700 * 16, 16, 32),          # 16-byte elements, 11 chunks
+    (3, 300 * 16, 16, 32),          # 32-byte elements, 10 chunks
     # a million multi-limb coefficients each: ~2e7 Montgomery products per case through every NTT pass shape
     (1, (1 << 20) - 3, 16384, 32768),
     (3, (1 << 20) - 3, 16384, 32768),
