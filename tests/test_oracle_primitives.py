@@ -121,6 +121,36 @@ def test_fft_io_is_bit_reversed_dft(oracle, fid, log_n):
     assert O.from_mont(fid, O.ifft_oi(fid, X)[0]) == x
 
 
+@pytest.mark.parametrize("fid", FIELDS)
+@pytest.mark.parametrize("log_n", [1, 4, 7])
+def test_fft_io_matches_the_published_fffft_loop(oracle, fid, log_n):
+    """The one convention no file in the reference pins: the `fffft` crate is a path dependency outside
+    the tree.  This restates its published forward transform as recalled -- an in-place Gentleman-Sande sweep, gaps
+    n/2, n/4, ..., 1, butterfly (x, y) -> (x + y, (x - y) * roots[nchunks * idx]) over the table roots[i] = w^i with
+    w = ROOT_OF_UNITY^(2^(S - log n)), no reordering pass ("io" = in-order in, out-of-order out) -- in plain Python
+    integers, and checks the oracle against it.  If the crate differs, this loop is the place that says how."""
+    O = oracle
+    p, n = O.MODULUS[fid], 1 << log_n
+    S = O.TWO_ADICITY[fid]
+    w = pow(pow(O.GENERATOR[fid], (p - 1) >> S, p), 1 << (S - log_n), p)
+    roots = [pow(w, i, p) for i in range(max(1, n // 2))]
+    rnd = random.Random(7 * fid + log_n)
+    x = [rnd.randrange(p) for _ in range(n)]
+    xi = list(x)
+    gap = n // 2
+    while gap > 0:
+        nchunks = n // (2 * gap)
+        for cidx in range(nchunks):
+            offset = 2 * cidx * gap
+            for idx in range(gap):
+                neg = (xi[offset + idx] - xi[offset + idx + gap]) % p
+                xi[offset + idx] = (xi[offset + idx] + xi[offset + idx + gap]) % p
+                xi[offset + idx + gap] = neg * roots[nchunks * idx] % p
+        gap //= 2
+    got = O.from_mont(fid, O.fft_io(fid, O.to_mont(fid, x).reshape(1, n, -1))[0])
+    assert got == xi
+
+
 def test_keccak_f1600_via_sha3(oracle):
     lib = oracle.lib()
 
