@@ -453,12 +453,15 @@ def main() -> None:
             cpu_in = make_coeffs(2, n_total)
         else:
             cpu_in = h_coeffs_np
-        t0 = time.perf_counter()
-        oc = O.commit(cpu_in, oenc)
-        dt = time.perf_counter() - t0
+        oc = O.commit(cpu_in, oenc)  # warm-up (page faults of the 256 MiB encoded matrix, thread pool start)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 20 and (reps < 3 or time.perf_counter() - t0 < 10.0):  # a bounded ~10 s sample, at least 3 commits
+            oc = O.commit(cpu_in, oenc)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
         cpu = {"value": cpu_in.shape[0] / dt, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
-               "sample": f"one commit of {sample_rows} rows x {N_PER_ROW} -> {N_COLS} ({dt:.2f} s), C restatement of the "
-                         f"reference algorithm with its rayon decomposition as OpenMP",
+               "sample": f"{reps} commits of {sample_rows} rows x {N_PER_ROW} -> {N_COLS} after one warm-up ({dt:.3f} s each), "
+                         f"C restatement of the reference algorithm with its rayon decomposition as OpenMP",
                "root_matches_gpu": (oc.get_root().hex() == gpu_root) if world <= 2 else None}
         if world <= 2:
             assert oc.get_root().hex() == gpu_root, "GPU Merkle root differs from the CPU oracle"
