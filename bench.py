@@ -441,8 +441,9 @@ def main() -> None:
     step_gbs = algorithmic_bytes(n_total, n_rows_total) / (ms_per_step * 1e-3) / 1e9
 
     # ---- CPU baseline: oracle on the same input, all host threads; also the parity gate ------------
+    # (rank 0 at N = 1 only: at N > 1 the other ranks have left and the line carries no CPU leg)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle import lcpc_oracle as O
 
         O.build()
