@@ -112,7 +112,8 @@ class ShardedLigeroCommitter:
         self.col0 = self.rank * self.cb
         self.cols_local = max(0, min(self.n_cols, self.col0 + self.cb) - self.col0)  # real columns in my block
         self.coeffs_local: Optional[torch.Tensor] = None
-        self.comm_cols: Optional[torch.Tensor] = None   # [n_rows_total, cb, L]: my column block, all rows
+        self.comm_cols: Optional[torch.Tensor] = None   # [n_rows_total, col_stride, L]: my column block, all rows
+        self.col_stride = self.cb                        # row stride of comm_cols (n_cols on the single-rank path)
         self.subtree: Optional[torch.Tensor] = None     # [(2*cb-1)*32] uint8
         self.top: Optional[torch.Tensor] = None         # rank 0: [(2*world-1)*32] uint8
         # Fused path (GPU back end, world > 1, power-of-two n_cols): the column-block matrix lives in
@@ -162,6 +163,12 @@ class ShardedLigeroCommitter:
             self._finish_tree(dev)
             return
         comm = self.ops.encode(coeffs_local, self.rows_local)  # [rows_local, n_cols, L]
+        if W == 1:
+            # a single rank owns every column: hash the encoded matrix where it is (row stride n_cols, no padding copy)
+            self.comm_cols = comm
+            self.col_stride = self.n_cols
+            self._finish_tree(dev)
+            return
         # pack: one contiguous slab per destination rank = that rank's column block of my rows
         if self.np2 != self.n_cols:
             padded = torch.zeros(self.rows_local, self.np2, L, dtype=torch.int64, device=dev)
@@ -189,7 +196,7 @@ class ShardedLigeroCommitter:
             self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
             self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
         if self.cols_local:
-            self.ops.hash_columns(recv, self.n_rows, cb, self.cols_local, self.subtree)
+            self.ops.hash_columns(recv, self.n_rows, self.col_stride, self.cols_local, self.subtree)
         self.ops.merkle_tree(self.subtree, cb)
         # only the subtree roots travel (32 bytes per rank); rank 0 joins them
         my_root = self.subtree[-32:]
@@ -277,7 +284,7 @@ class ShardedLigeroCommitter:
 
         def my_payload():
             idx = torch.tensor([c - self.col0 for c in mine], dtype=torch.long, device=dev)
-            m3 = self.comm_cols.view(self.n_rows, cb, L)
+            m3 = self.comm_cols.view(self.n_rows, self.col_stride, L)
             vals = m3.index_select(1, idx).transpose(0, 1).contiguous().view(len(mine), -1)  # [k, n_rows*L]
             sub = self.subtree.view(-1, 32)
             parts, off, n, node = [], 0, cb, idx.clone()

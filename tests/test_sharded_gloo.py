@@ -115,7 +115,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,fid,n_rows,n_per_row,n_cols", [(2, 0, 7, 16, 32), (2, 3, 4, 8, 16), (4, 0, 10, 16, 64)])
+@pytest.mark.parametrize("world,fid,n_rows,n_per_row,n_cols", [(1, 0, 5, 16, 32), (2, 0, 7, 16, 32), (2, 3, 4, 8, 16), (4, 0, 10, 16, 64)])
 def test_sharded_commit_matches_single_process(oracle, world, fid, n_rows, n_per_row, n_cols):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -129,7 +129,7 @@ def test_sharded_commit_matches_single_process(oracle, world, fid, n_rows, n_per
     assert q.get(timeout=5) is True
 
 
-@pytest.mark.parametrize("world,fid,n_rows,n_per_row,seed", [(2, 0, 9, 150, 0), (4, 1, 6, 120, 1)])
+@pytest.mark.parametrize("world,fid,n_rows,n_per_row,seed", [(1, 0, 5, 150, 0), (2, 0, 9, 150, 0), (4, 1, 6, 120, 1)])
 def test_sharded_brakedown_commit_matches_single_process(oracle, world, fid, n_rows, n_per_row, seed):
     """Brakedown rows shard the same way; the PADDED leaf range (np2 > n_cols) is what gets split into column blocks,
     so the all-zero padding leaves fall into the last ranks' subtrees."""
