@@ -516,9 +516,9 @@ cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride
 #define LCPC_STRIDED(RR)                                                                                                       \
     do {                                                                                                                       \
         if constexpr (L == 1) {                                                                                                \
-            if (lit && zb == 1 && RR >= 1) { k_ntt_strided<FID, RR, 12, (RR >= 1 ? 1 : 0)><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
+            if (lit && zb == 1) { k_ntt_strided<FID, RR, 12, 1><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
             if (lit && zb == 0) { k_ntt_strided<FID, RR, 12, 0><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
-            if (!lit && zb == 1 && RR >= 1) { k_ntt_strided<FID, RR, -1, (RR >= 1 ? 1 : 0)><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
+            if (!lit && zb == 1) { k_ntt_strided<FID, RR, -1, 1><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw); break; } \
         }                                                                                                                      \
         k_ntt_strided<FID, RR><<<grid, 256, 0, lc.s>>>(in, in_stride, in_valid, dst, n, n_rows, p.log_sub, tw, stw);            \
     } while (0)
