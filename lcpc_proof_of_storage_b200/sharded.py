@@ -121,6 +121,7 @@ class ShardedLigeroCommitter:
         # NVLink, and no separate pack / all-to-all pass exists.  fused=None tries it and falls back
         # to NCCL all_to_all_single when peer mapping is not available.
         self._symm = self._hdl = self._peer_ptrs = self._scratch = None
+        self._pending: Optional[int] = None  # buffer index of a commit whose exchange is issued but not yet hashed
         want = fused if fused is not None else (isinstance(self.ops, GpuOps) and self.world > 1)
         if want and isinstance(self.ops, GpuOps) and self.world > 1 and self.np2 == self.n_cols and self.world <= 16:
             try:
@@ -129,15 +130,18 @@ class ShardedLigeroCommitter:
                 import torch.distributed._symmetric_memory as symm_mem
 
                 dev = torch.device("cuda", enc.ctx.device)
-                # two matrices used alternately: a rank may start writing commit k+1 into its peers while
-                # they still hash commit k, so one barrier per commit (after the encode) is enough
+                # Three matrices used in turn.  Commit k is finished (barrier, hash, tree) either right after its own
+                # encode or, with defer=True, after the encode of commit k+1 has been issued -- the exchange of commit k
+                # then drains over NVLink, and slower ranks catch up, behind useful work.  Encode j writes buffer j % 3,
+                # last read by the hashing of commit j-3; encode j is issued after this rank's barrier of commit j-2,
+                # which every rank reaches only after hashing commit j-3: no extra synchronisation is needed.
                 per = self.n_rows * self.cb * self.L
-                self._symm = symm_mem.empty(2 * per, dtype=torch.int64, device=dev)
+                self._symm = symm_mem.empty(3 * per, dtype=torch.int64, device=dev)
                 self._hdl = symm_mem.rendezvous(self._symm, group if group is not None else dist.group.WORLD)
-                self._peer_ptrs = [(C.c_void_p * self.world)(*[int(p) + half * per * 8 for p in self._hdl.buffer_ptrs])
-                                   for half in range(2)]
-                self._halves = [self._symm[:per], self._symm[per:]]
-                self._flip = 0
+                self._peer_ptrs = [(C.c_void_p * self.world)(*[int(p) + b * per * 8 for p in self._hdl.buffer_ptrs])
+                                   for b in range(3)]
+                self._bufs = [self._symm[b * per:(b + 1) * per] for b in range(3)]
+                self._k = 0
                 self._scratch = torch.empty(max(1, self.rows_local) * self.n_cols * self.L, dtype=torch.int64, device=dev)
             except Exception:
                 if fused:
@@ -149,18 +153,21 @@ class ShardedLigeroCommitter:
         return self._hdl is not None
 
     # ------------------------------------------------------------------ commit
-    def commit(self, coeffs_local: torch.Tensor) -> None:
+    def commit(self, coeffs_local: torch.Tensor, defer: bool = False) -> None:
+        """defer=True (fused path only): the encode + exchange of this commit is issued, its hashing and tree follow when
+        the next commit has issued its encode, or at flush().  Every rank must make the same sequence of calls."""
         L, cb, W = self.L, self.cb, self.world
         assert coeffs_local.numel() == self.rows_local * self.n_per_row * L
         dev = coeffs_local.device
         self.coeffs_local = coeffs_local
         if self.fused:
-            half = self._flip
-            self._flip ^= 1
-            self.ops.encode_scatter(coeffs_local, self.rows_local, self.row0, self._scratch, self._peer_ptrs[half])
-            self._hdl.barrier(channel=half)  # every rank's rows have landed (and commit k-1 is fully hashed everywhere)
-            self.comm_cols = self._halves[half]
-            self._finish_tree(dev)
+            b = self._k % 3
+            self._k += 1
+            self.ops.encode_scatter(coeffs_local, self.rows_local, self.row0, self._scratch, self._peer_ptrs[b])
+            self.flush()          # the previous commit, if it was deferred
+            self._pending = b
+            if not defer:
+                self.flush()
             return
         comm = self.ops.encode(coeffs_local, self.rows_local)  # [rows_local, n_cols, L]
         if W == 1:
@@ -186,6 +193,15 @@ class ShardedLigeroCommitter:
             recv = send.view(-1)
         self.comm_cols = recv  # row-major [n_rows_total, cb, L] because row blocks arrive in rank order
         self._finish_tree(dev)
+
+    def flush(self) -> None:
+        """Finish the deferred commit, if any (collective: every rank calls it at the same point)."""
+        if self._pending is None:
+            return
+        b, self._pending = self._pending, None
+        self._hdl.barrier(channel=b)  # every rank's rows of that commit have landed in my column block
+        self.comm_cols = self._bufs[b]
+        self._finish_tree(self.comm_cols.device)
 
     def _finish_tree(self, dev) -> None:
         cb, W = self.cb, self.world
@@ -224,11 +240,13 @@ class ShardedLigeroCommitter:
     def root(self) -> bytes:
         """LcCommit::get_root on rank 0."""
         assert self.rank == 0 and self.top is not None
+        assert self._pending is None, "a deferred commit is pending: call flush() on every rank first"
         return bytes(self.top[-32:].cpu().numpy())
 
     def gather_hashes(self) -> Optional[torch.Tensor]:
         """The full flat tree `LcCommit.hashes` ([np2 | np2/2 | ... | 1] digests) on rank 0."""
         W, cb = self.world, self.cb
+        assert self._pending is None, "a deferred commit is pending: call flush() on every rank first"
         dev = self.subtree.device
         if W == 1:
             return self.subtree.clone()
@@ -271,6 +289,7 @@ class ShardedLigeroCommitter:
         import numpy as np
 
         L, cb, W = self.L, self.cb, self.world
+        assert self._pending is None, "a deferred commit is pending: call flush() on every rank first"
         for c in cols:
             if not 0 <= c < self.n_cols:
                 from .lcpc2d import ProverError

@@ -46,6 +46,32 @@ def _worker(rank, world, port, fused, q):
         if rank == 0:
             exp2 = O.commit(O.pack_bytes7(file_bytes.tobytes()), O.LigeroEncoding(fid, n_per_row, n_cols))
             assert sc2.root() == exp2.get_root()
+        if fused:
+            # deferred commits: the tree of commit k appears once commit k+1 has issued its encode, or at flush();
+            # three symmetric buffers rotate, so run more than three and alternate two inputs
+            coeffs_b = np.zeros_like(coeffs)
+            coeffs_b[:n] = O.random_field_elements(fid, 6, n)
+            local_b = torch.from_numpy(coeffs_b.reshape(n_rows, n_per_row)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
+            root_b = O.commit(coeffs_b[:n], O.LigeroEncoding(fid, n_per_row, n_cols)).get_root() if rank == 0 else None
+            seen = []
+            for i in range(7):
+                sc.commit(local_b if i % 2 else local, defer=True)
+                if i and rank == 0:  # commit i-1 is finished now
+                    seen.append(bytes(sc.top[-32:].cpu().numpy()))
+            sc.flush()
+            if rank == 0:
+                seen.append(sc.root())
+                assert seen == [root_b if i % 2 else root_elems for i in range(7)]
+            with_pending_ok = True
+            sc.commit(local, defer=True)
+            try:
+                if rank == 0:
+                    sc.root()
+                    with_pending_ok = False
+            except AssertionError:
+                pass
+            sc.flush()
+            assert with_pending_ok
         sc.commit(local)
         hashes = sc.gather_hashes()
         tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, 1)
