@@ -88,10 +88,13 @@ def bind_to_gpu_numa_node(index: int) -> str:
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
+        self.nv = None
+        if not enabled:  # ranks other than 0: their samples are never reported, and concurrent NVML queries slow each other
+            return
         try:
             import pynvml
 
@@ -99,6 +102,8 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()  # pays NVML's first-call costs outside any timed region; discarded (the GPU may be idle)
+            self.samples, self.reasons = [], set()
         except Exception:
             self.nv = None
 
@@ -142,6 +147,15 @@ class ClockSampler:
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def expected_root(n_gpus: int):
+    """Merkle root of the N-GPU workload from the committed fixture (None when N is not in it)."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_roots.json")) as f:
+            return json.load(f)["roots_by_n_gpus"].get(str(n_gpus))
+    except OSError:
+        return None
 
 
 def measured_peak_gbs():
@@ -320,14 +334,18 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # NVML is set up and the sampling thread started BEFORE the barrier: its first calls take milliseconds, more when
+    # eight processes make them at once, and a different time on every rank.  Between the barrier and the first event
+    # that skew lands inside the timed region of the fast ranks (they wait for the slowest rank in the first commit's
+    # exchange barrier): at 8 GPUs it cost 2 - 20 ms of a 15 ms region (profiles/r01c_scaling_and_configs.md).
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
     for _ in range(warmup):
         step()
     finish()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    launches0 = ctx.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = ctx.launch_count()
     # the timed region: exactly `steps` steps between two events on the launching stream, nothing else enqueued
     ev0.record(stream)
     for _ in range(steps):
@@ -478,6 +496,12 @@ def main() -> None:
         if world <= 2:
             assert oc.get_root().hex() == gpu_root, "GPU Merkle root differs from the CPU oracle"
 
+    # known-answer root of this workload at N GPUs (tests/golden/bench_roots.json, computed once by the CPU oracle):
+    # the parity gate of the multi-GPU lines, where no CPU leg runs
+    kat = expected_root(world)
+    if kat is not None:
+        assert gpu_root == kat, f"GPU Merkle root at {world} GPUs differs from tests/golden/bench_roots.json"
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -491,7 +515,7 @@ def main() -> None:
         "algorithmic_GBps": step_gbs,
         "host_binding": numa,
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-        "root": gpu_root,
+        "root": gpu_root, "root_matches_golden": (gpu_root == kat) if kat is not None else None,
     }
     _emit(line)
     if dist is not None:
