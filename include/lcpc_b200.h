@@ -45,7 +45,11 @@ typedef enum {
     LCPC_FT63 = 0,  /* p = 5102708120182849537, 1 limb  */
     LCPC_FT127 = 1, /* 2 limbs */
     LCPC_FT191 = 2, /* 3 limbs */
-    LCPC_FT255 = 3  /* 4 limbs */
+    LCPC_FT255 = 3, /* 4 limbs */
+    /* proof-of-storage/src/fields/ft253_192.rs:6-10: p = (2^61 - 1) * 2^192 + 1, generator 3, 4 limbs, and the one
+     * field whose to_repr() is BIG-endian: leaves, transcript messages and the encoded-file image use those bytes.
+     * Elements still cross this interface as Montgomery limbs, least-significant limb first, fully reduced. */
+    LCPC_FT253_192 = 4
 } lcpc_field;
 
 /* status codes; the first block maps onto lcpc_2d::ProverError (lib.rs:113-132) */
@@ -153,7 +157,10 @@ int32_t lcpc_commit_host(lcpc_plan *plan, const uint64_t *coeffs, size_t n_coeff
  * one element whose limb IS the little-endian integer, proof-of-storage/src/fields/
  * writable_ft63.rs:35-40, data_field.rs:38-46) fused in front of the commit
  * (lcpc_online.rs:81-143 convert_file_data_to_commit, CommitRequestType::Commit).
- * Plan field must be LCPC_FT63. */
+ * Plan field LCPC_FT63, or LCPC_FT253_192 with Ft253_192::from_data_bytes (ft253_192.rs:18-30): 31 file bytes per
+ * element, limb i = the big-endian integer of bytes [8i, 8i+8) of the zero-padded group.  A group whose limbs are not
+ * below the modulus (byte 24 of the group > 0x1f) is refused with LCPC_ERR_INVALID_ARG: the reference computes on
+ * such unreduced limbs with a carry-dropping add, and the outcome is not a field computation that could be matched. */
 int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_t n_bytes,
                                uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out,
                                lcpc_commit **keep);

@@ -9,14 +9,14 @@ fallback.
 from . import _lib
 from ._lib import LcpcError
 from .lcpc2d import (
-    FT63, FT127, FT191, FT255, FIELD_LIMBS, FIELD_NAMES,
+    FT63, FT127, FT191, FT255, FT253_192, FIELD_LIMBS, FIELD_NAMES,
     Context, LigeroEncoding, SdigEncoding, CscMatrix, LcCommit, LcColumn, LcEvalProof,
     ProverError, VerifierError, Transcript, commit, prove, verify, open_column, collapse_columns, log2, next_pow2,
     n_degree_tests, sdig_codeword_length,
 )
 
 __all__ = [
-    "FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "FIELD_NAMES", "Context", "LigeroEncoding",
+    "FT63", "FT127", "FT191", "FT255", "FT253_192", "FIELD_LIMBS", "FIELD_NAMES", "Context", "LigeroEncoding",
     "SdigEncoding", "CscMatrix", "LcCommit", "LcColumn", "LcEvalProof", "ProverError", "VerifierError",
     "LcpcError", "Transcript", "commit", "prove", "verify", "sdig_codeword_length", "open_column", "collapse_columns", "log2", "next_pow2", "n_degree_tests",
 ]

@@ -505,12 +505,15 @@ int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_
                                uint64_t *comm_out, uint8_t *hashes_out, lcpc_commit **keep) {
     if (keep) *keep = nullptr;
     if (!plan || !file_bytes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
-    if (plan->fid != FT63) return fail(LCPC_ERR_INVALID_ARG, "byte packing is defined for the 63-bit field only");
+    if (plan->fid != FT63 && plan->fid != FT253_192)
+        return fail(LCPC_ERR_INVALID_ARG, "byte packing is defined for the DataField types only (Ft63, Ft253_192)");
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    const size_t n_coeffs = (n_bytes + 6) / 7;
+    const bool wide = plan->fid == FT253_192;  // 31 data bytes per element instead of 7
+    const size_t L = (size_t)limbs_of(plan->fid);
+    const size_t n_coeffs = wide ? (n_bytes + 30) / 31 : (n_bytes + 6) / 7;
     lcpc_commit *c = new (std::nothrow) lcpc_commit;
     if (!c) return fail(LCPC_ERR_NOMEM, "host allocation failed");
     int32_t rc = commit_shape(plan, n_coeffs, c);
@@ -519,10 +522,23 @@ int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_
         DevBuf raw;
         CU(raw.alloc(n_bytes, ctx->stream));
         CU(cudaMemcpyAsync(raw.p, file_bytes, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMallocAsync((void **)&c->d_coeffs, padded * sizeof(uint64_t), ctx->stream));
-        CU(pack_bytes7(raw.as<uint8_t>(), n_bytes, c->d_coeffs, ctx->lc()));
+        CU(cudaMallocAsync((void **)&c->d_coeffs, padded * L * sizeof(uint64_t), ctx->stream));
+        if (wide) {
+            DevBuf bad;
+            CU(bad.alloc(sizeof(uint32_t), ctx->stream));
+            CU(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), ctx->stream));
+            CU(pack_bytes31(raw.as<uint8_t>(), n_bytes, c->d_coeffs, bad.as<uint32_t>(), ctx->lc()));
+            uint32_t h_bad = 0;
+            CU(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (h_bad)
+                return fail(LCPC_ERR_INVALID_ARG,
+                            "Ft253_192::from_data_bytes: a 31-byte group is not below the modulus (byte 24 of the group > 0x1f)");
+        } else {
+            CU(pack_bytes7(raw.as<uint8_t>(), n_bytes, c->d_coeffs, ctx->lc()));
+        }
         if (padded > n_coeffs)
-            CU(cudaMemsetAsync(c->d_coeffs + n_coeffs, 0, (padded - n_coeffs) * sizeof(uint64_t), ctx->stream));
+            CU(cudaMemsetAsync(c->d_coeffs + n_coeffs * L, 0, (padded - n_coeffs) * L * sizeof(uint64_t), ctx->stream));
         return commit_finish(plan, c, coeffs_out, comm_out, hashes_out);
     };
     if (rc == LCPC_OK) rc = body();

@@ -4,8 +4,10 @@
 // R = 2^(64*LIMBS), always fully reduced on loads/stores to global memory -- the
 // in-memory form ff_derive 0.13 gives the reference's fields
 // (lcpc-test-fields/src/lib.rs:18-70; WriteableFt63: proof-of-storage/src/fields/
-// writable_ft63.rs:8-12).  All four moduli are p = c*2^40 + 1 in their low limb, so
-// -p^-1 mod 2^32 = 0xffffffff: the Montgomery quotient digit is a negation.
+// writable_ft63.rs:8-12; Ft253_192: proof-of-storage/src/fields/ft253_192.rs:6-10).  Every modulus is
+// 1 mod 2^40 (Ft253_192: 1 mod 2^192), so -p^-1 mod 2^32 = 0xffffffff: the Montgomery quotient digit
+// is a negation.  Ft253_192 is the one field whose to_repr() is BIG-endian (PrimeFieldReprEndianness =
+// "big"): Field::to_repr() below returns the element whose memory image is those bytes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -14,7 +16,7 @@
 
 namespace lcpc {
 
-enum FieldId : int { FT63 = 0, FT127 = 1, FT191 = 2, FT255 = 3, N_FIELDS = 4 };
+enum FieldId : int { FT63 = 0, FT127 = 1, FT191 = 2, FT255 = 3, FT253_192 = 4, N_FIELDS = 5 };
 
 template <int L>
 struct Fe {
@@ -25,6 +27,7 @@ struct Fe {
 struct FieldConsts {
     int limbs, num_bits, two_adicity;
     uint64_t p[4], inv, r[4], r2[4], root[4];
+    bool repr_big_endian;
 };
 
 __host__ __device__ constexpr FieldConsts field_consts(int fid) {
@@ -35,28 +38,35 @@ __host__ __device__ constexpr FieldConsts field_consts(int fid) {
                 0x46d075ffffffffffull,
                 {0x2b8e9dfffffffffdull, 0, 0, 0},
                 {0x13085abb0716119eull, 0, 0, 0},
-                {0x23bcb75f84213a43ull, 0, 0, 0}};
+                {0x23bcb75f84213a43ull, 0, 0, 0}, false};
     case FT127:
         return {2, 127, 40,
                 {0x7f2bd90000000001ull, 0x6e754097ba20e0bfull, 0, 0},
                 0x7f2bd8ffffffffffull,
                 {0x01a84dfffffffffeull, 0x23157ed08bbe3e81ull, 0, 0},
                 {0x816bd5407cf6dce5ull, 0x2c1637057de6fce8ull, 0, 0},
-                {0xf491a1dff39975f8ull, 0x178fd41c0f6a04faull, 0, 0}};
+                {0xf491a1dff39975f8ull, 0x178fd41c0f6a04faull, 0, 0}, false};
     case FT191:
         return {3, 191, 41,
                 {0xd246820000000001ull, 0x936888270ceecbcdull, 0x453708aa3fbc8ddaull, 0},
                 0xd24681ffffffffffull,
                 {0x892c79fffffffffdull, 0x45c6678ad9339c96ull, 0x305ae60140ca5670ull, 0},
                 {0x6c25128031d873e2ull, 0xf71a3697a97ffdceull, 0x07ef71ae547daef9ull, 0},
-                {0xecd905456df2b092ull, 0x53ce189f0df0a05aull, 0x3f6e6da556ed31d9ull, 0}};
+                {0xecd905456df2b092ull, 0x53ce189f0df0a05aull, 0x3f6e6da556ed31d9ull, 0}, false};
+    case FT253_192:  // p = (2^61 - 1) * 2^192 + 1, generator 3, 2-adicity 192
+        return {4, 253, 192,
+                {0x0000000000000001ull, 0, 0, 0x1fffffffffffffffull},
+                0xffffffffffffffffull,
+                {0xfffffffffffffff8ull, 0xffffffffffffffffull, 0xffffffffffffffffull, 0x0000000000000007ull},
+                {0xffffffffffff8040ull, 0xffffffffffffefffull, 0xfffffffffffffdffull, 0x0000000000007f7full},
+                {0xe94731e93d73da14ull, 0x0e0f79fb69eec7bfull, 0x246cdb0e8f061ce3ull, 0x029543679ced2616ull}, true};
     default:
         return {4, 255, 41,
                 {0x02a4f20000000001ull, 0xef73c79086595f30ull, 0xfda9df04b9575969ull, 0x663c799b6e4d2900ull},
                 0x02a4f1ffffffffffull,
                 {0xfab61bfffffffffeull, 0x211870def34d419full, 0x04ac41f68d514d2cull, 0x33870cc92365adfeull},
                 {0xcf06aad260ab9990ull, 0x12f0d8856156a683ull, 0x5da77ded73588e21ull, 0x38725a1646845639ull},
-                {0x9c745ae52a496067ull, 0x95ee9a4091329682ull, 0x854a3ee53365b80eull, 0x16edffae79969e76ull}};
+                {0x9c745ae52a496067ull, 0x95ee9a4091329682ull, 0x854a3ee53365b80eull, 0x16edffae79969e76ull}, false};
     }
 }
 
@@ -307,6 +317,24 @@ struct Field {
             split(x, a);
             m32::mont_redc<2 * LIMBS>(z, x, PWord{});
             return join(z);
+        }
+    }
+
+    // PrimeField::to_repr() as an element whose in-memory bytes ARE the repr: the canonical value itself for the
+    // little-endian fields; for Ft253_192 the byte-reversed canonical value (limb order and the bytes of every limb)
+    static constexpr bool REPR_BE = field_consts(FID).repr_big_endian;
+    __device__ __forceinline__ static E to_repr(const E &a) {
+        const E c = to_canon(a);
+        if constexpr (!REPR_BE) {
+            return c;
+        } else {
+            E r;
+#pragma unroll
+            for (int i = 0; i < LIMBS; i++) {
+                const uint64_t v = c.v[LIMBS - 1 - i];
+                r.v[i] = ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123);
+            }
+            return r;
         }
     }
 

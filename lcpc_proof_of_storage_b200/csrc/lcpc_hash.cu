@@ -43,7 +43,7 @@ __device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t 
         for (int e = 0; e < EPB; e++) {
             const int64_t row = (int64_t)(ve0 + e) - K;
             E c = F::zero();
-            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L));
+            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_repr(ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L));
 #pragma unroll
             for (int l = 0; l < L; l++) {
                 m[e * WPE + 2 * l] = (uint32_t)c.v[l];
@@ -58,7 +58,7 @@ __device__ __forceinline__ void load_block_words(uint32_t m[16], const uint64_t 
         for (int e = 0; e < NE; e++) {
             const int64_t row = (int64_t)(ve0 + e) - K;
             E c = F::zero();
-            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_canon(ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L));
+            if (row >= 0 && (uint64_t)row < n_rows) c = F::to_repr(ld_fe<L>(mat + ((size_t)(row - row_base) * row_stride + col) * L));
 #pragma unroll
             for (int l = 0; l < L; l++) {
                 w[e * WPE + 2 * l] = (uint32_t)c.v[l];
@@ -102,11 +102,11 @@ struct BlockElems {
                                                         : Field<FID>::zero();
         }
     }
-    // canonical little-endian words of the block (the de-Montgomery reduction of zero is zero)
+    // to_repr() bytes of the block as little-endian message words (the de-Montgomery reduction of zero is zero)
     __device__ __forceinline__ void words(uint32_t m[16]) const {
 #pragma unroll
         for (int i = 0; i < EPB; i++) {
-            const typename Field<FID>::E c = Field<FID>::to_canon(e[i]);
+            const typename Field<FID>::E c = Field<FID>::to_repr(e[i]);
 #pragma unroll
             for (int l = 0; l < L; l++) {
                 m[i * WPE + 2 * l] = (uint32_t)c.v[l];
@@ -251,6 +251,7 @@ cudaError_t hash_chunk_range(int fid, const uint64_t *d_mat, int64_t row_base, s
     case FT127: return LCPC_HCR(FT127);
     case FT191: return LCPC_HCR(FT191);
     case FT255: return LCPC_HCR(FT255);
+    case FT253_192: return LCPC_HCR(FT253_192);
     default: return cudaErrorInvalidValue;
     }
 #undef LCPC_HCR
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(256) k_emit_colmajor(const uint64_t *__restric
     for (int k = 0; k < 4; k++) {
         const size_t r = r0 + ty + 8 * k, c = c0 + tx;
         typename F::E v = F::zero();
-        if (r < n_rows && c < n_cols) v = F::to_canon(ld_fe<L>(mat + (r * row_stride + c) * L));
+        if (r < n_rows && c < n_cols) v = F::to_repr(ld_fe<L>(mat + (r * row_stride + c) * L));
 #pragma unroll
         for (int l = 0; l < L; l++) tile[l][ty + 8 * k][tx] = v.v[l];
     }
@@ -315,6 +316,7 @@ cudaError_t emit_colmajor(int fid, const uint64_t *d_mat, size_t n_rows, size_t 
     case FT127: k_emit_colmajor<FT127><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
     case FT191: k_emit_colmajor<FT191><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
     case FT255: k_emit_colmajor<FT255><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
+    case FT253_192: k_emit_colmajor<FT253_192><<<grid, 256, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, d_out, out_col_stride); break;
     default: return cudaErrorInvalidValue;
     }
     lc.end();
@@ -328,6 +330,7 @@ cudaError_t hash_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t r
     case FT127: return hash_columns_t<FT127>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
     case FT191: return hash_columns_t<FT191>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
     case FT255: return hash_columns_t<FT255>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
+    case FT253_192: return hash_columns_t<FT253_192>(d_mat, n_rows, row_stride, n_cols, d_col_idx, d_leaves, d_cv_scratch, lc);
     default: return cudaErrorInvalidValue;
     }
 }

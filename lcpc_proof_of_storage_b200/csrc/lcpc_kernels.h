@@ -121,6 +121,8 @@ cudaError_t verify_paths(const uint8_t *d_leaves, const uint8_t *d_paths, int de
                          const uint8_t *d_root, uint32_t *d_ok, const Launch &lc);
 
 cudaError_t pack_bytes7(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems, const Launch &lc);
+// Ft253_192::from_data_bytes; *d_bad (zeroed by the caller) becomes non-zero when a 31-byte group is not below the modulus
+cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems, uint32_t *d_bad, const Launch &lc);
 
 // Brakedown: matrices in CSR on the device (converted from the caller's CSC once).
 struct DevCsr {

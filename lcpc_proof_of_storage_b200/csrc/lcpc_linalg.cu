@@ -19,6 +19,7 @@ namespace lcpc {
     case FT127: return CALL(FT127);                   \
     case FT191: return CALL(FT191);                   \
     case FT255: return CALL(FT255);                   \
+    case FT253_192: return CALL(FT253_192);           \
     default: return cudaErrorInvalidValue;            \
     }
 
@@ -207,15 +208,15 @@ cudaError_t gather_columns(int fid, const uint64_t *d_mat, size_t n_rows, size_t
 
 // ------------------------------------------------------------------ verifier helpers
 
-// canonical (de-Montgomery) limbs of each element: what FieldHash::to_hash_repr feeds the
-// transcript (lcpc-2d/src/lib.rs:48-58)
+// PrimeField::to_repr() of each element (canonical value; big-endian bytes for Ft253_192): what
+// FieldHash::to_hash_repr feeds the transcript (lcpc-2d/src/lib.rs:48-58)
 template <int FID>
 __global__ void k_to_canon(const uint64_t *__restrict__ in, size_t n, uint64_t *__restrict__ out) {
     using F = Field<FID>;
     constexpr int L = F::LIMBS;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    st_fe<L>(out + i * L, F::to_canon(ld_fe<L>(in + i * L)));
+    st_fe<L>(out + i * L, F::to_repr(ld_fe<L>(in + i * L)));
 }
 
 template <int FID>
@@ -311,6 +312,42 @@ cudaError_t pack_bytes7(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elem
     const size_t groups = (n_elems + 7) / 8;
     lc.begin("k_pack_bytes7");
     k_pack_bytes7<<<(unsigned)((groups + 127) / 128), 128, 0, lc.s>>>(d_bytes, n_bytes, d_elems, n_elems);
+    lc.end();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ 31-byte packing (Ft253_192)
+
+// Ft253_192::from_data_bytes (proof-of-storage/src/fields/ft253_192.rs:18-30): the 31 bytes are zero-padded to 32 and
+// limb i = u64::from_be_bytes(padded[8i .. 8i+8]) -- limb 0 (least significant) comes from the FIRST eight bytes --
+// stored directly as the Montgomery limbs.  The top limb is bytes 24..30 shifted left by 8, so any chunk whose byte 24
+// exceeds 0x1f gives limbs >= p; the reference then computes on unreduced values (ff_derive's add drops the carry
+// out of 2^256: the results are not field elements).  Such input is reported through *bad instead of being encoded.
+__global__ void k_pack_bytes31(const uint8_t *__restrict__ bytes, size_t n_bytes, uint64_t *__restrict__ elems,
+                               size_t n_elems, uint32_t *__restrict__ bad) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    uint64_t limb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const size_t b = e * 31 + 8 * i + k;
+            const uint64_t byte = (8 * i + k < 31 && b < n_bytes) ? bytes[b] : 0;
+            v = (v << 8) | byte;
+        }
+        limb[i] = v;
+        elems[e * 4 + i] = v;
+    }
+    if (Field<FT253_192>::geq_p(limb)) atomicOr(bad, 1u);
+}
+
+cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems, uint32_t *d_bad, const Launch &lc) {
+    const size_t n_elems = (n_bytes + 30) / 31;
+    if (n_elems == 0) return cudaSuccess;
+    lc.begin("k_pack_bytes31");
+    k_pack_bytes31<<<(unsigned)((n_elems + 255) / 256), 256, 0, lc.s>>>(d_bytes, n_bytes, d_elems, n_elems, d_bad);
     lc.end();
     return cudaGetLastError();
 }

@@ -1,5 +1,5 @@
 // Field dispatch of the Ligero encoder; the kernels live in lcpc_ntt_impl.cuh and are instantiated per field in
-// lcpc_ntt_f0.cu .. lcpc_ntt_f3.cu.
+// lcpc_ntt_f0.cu .. lcpc_ntt_f4.cu.
 #include "lcpc_field.cuh"
 #include "lcpc_kernels.h"
 
@@ -17,6 +17,7 @@ cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride
     case FT127: return CALL(FT127);                   \
     case FT191: return CALL(FT191);                   \
     case FT255: return CALL(FT255);                   \
+    case FT253_192: return CALL(FT253_192);           \
     default: return cudaErrorInvalidValue;            \
     }
 

@@ -1,0 +1,8 @@
+// NTT kernels of the FT253_192 field (explicit instantiation of lcpc_ntt_impl.cuh).
+#include "lcpc_ntt_impl.cuh"
+
+namespace lcpc {
+template cudaError_t plan_build_t<FT253_192>(NttPlan &, int, const uint64_t *, const Launch &);
+template cudaError_t encode_t<FT253_192>(const NttPlan &, const uint64_t *, size_t, size_t, uint64_t *, size_t, const Launch &,
+                                     const ScatterDst *);
+}  // namespace lcpc

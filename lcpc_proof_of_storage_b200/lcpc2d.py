@@ -21,11 +21,13 @@ import numpy as np
 from . import _lib
 from ._lib import LcpcCsc, LcpcError, check, u64p
 
-FT63, FT127, FT191, FT255 = 0, 1, 2, 3
-FIELD_NAMES = {FT63: "Ft63", FT127: "Ft127", FT191: "Ft191", FT255: "Ft255"}
-FIELD_LIMBS = {FT63: 1, FT127: 2, FT191: 3, FT255: 4}
-FIELD_NUM_BITS = {FT63: 63, FT127: 127, FT191: 191, FT255: 255}
-FIELD_TWO_ADICITY = {FT63: 41, FT127: 40, FT191: 41, FT255: 41}
+FT63, FT127, FT191, FT255, FT253_192 = 0, 1, 2, 3, 4
+FIELD_NAMES = {FT63: "Ft63", FT127: "Ft127", FT191: "Ft191", FT255: "Ft255", FT253_192: "Ft253_192"}
+FIELD_LIMBS = {FT63: 1, FT127: 2, FT191: 3, FT255: 4, FT253_192: 4}
+FIELD_NUM_BITS = {FT63: 63, FT127: 127, FT191: 191, FT255: 255, FT253_192: 253}
+FIELD_TWO_ADICITY = {FT63: 41, FT127: 40, FT191: 41, FT255: 41, FT253_192: 192}
+# PrimeFieldReprEndianness: "big" for Ft253_192 only (proof-of-storage/src/fields/ft253_192.rs:9)
+FIELD_REPR_BIG_ENDIAN = {FT63: False, FT127: False, FT191: False, FT255: False, FT253_192: True}
 
 
 class ProverError(Exception):
@@ -482,17 +484,21 @@ class LcCommit:
 
     @classmethod
     def commit_bytes(cls, data: bytes, enc: _Encoding, download: bool = True) -> "LcCommit":
-        """proof-of-storage: WriteableFt63::from_byte_vec + commit (lcpc_online.rs:81-143)."""
+        """proof-of-storage: DataField::from_byte_vec + commit (lcpc_online.rs:81-143).  WriteableFt63 packs 7 bytes per
+        element (writable_ft63.rs:35-40), Ft253_192 packs 31 (ft253_192.rs:18-30; groups that are not below the modulus
+        are refused, see include/lcpc_b200.h)."""
         buf = np.frombuffer(data, dtype=np.uint8)
-        n = (len(data) + 6) // 7
+        per = 31 if enc.fid == FT253_192 else 7
+        L = FIELD_LIMBS[enc.fid]
+        n = (len(data) + per - 1) // per
         if n == 0:
             raise ValueError("Cannot convert empty file to commit")  # lcpc_online.rs:91
         n_rows, n_per_row, n_cols = enc.get_dims(n)
         np2 = next_pow2(n_cols)
         comm = coeffs = hashes = None
         if download:
-            coeffs = np.empty((n_rows, n_per_row, 1), dtype=np.uint64)
-            comm = np.empty((n_rows, n_cols, 1), dtype=np.uint64)
+            coeffs = np.empty((n_rows, n_per_row, L), dtype=np.uint64)
+            comm = np.empty((n_rows, n_cols, L), dtype=np.uint64)
             hashes = np.empty((2 * np2 - 1, 32), dtype=np.uint8)
         h = C.c_void_p()
         _prover_call(_lib.load().lcpc_commit_bytes_host(enc.plan, _ptr(buf), len(data), _ptr(coeffs), _ptr(comm),

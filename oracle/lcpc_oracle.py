@@ -28,19 +28,22 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liborc.so")
 
-FT63, FT127, FT191, FT255 = 0, 1, 2, 3
-FIELD_NAMES = {FT63: "Ft63", FT127: "Ft127", FT191: "Ft191", FT255: "Ft255"}
-LIMBS = {FT63: 1, FT127: 2, FT191: 3, FT255: 4}
-# lcpc-test-fields/src/lib.rs:19,42,54,66 (PrimeFieldModulus)
+FT63, FT127, FT191, FT255, FT253_192 = 0, 1, 2, 3, 4
+FIELD_NAMES = {FT63: "Ft63", FT127: "Ft127", FT191: "Ft191", FT255: "Ft255", FT253_192: "Ft253_192"}
+LIMBS = {FT63: 1, FT127: 2, FT191: 3, FT255: 4, FT253_192: 4}
+# lcpc-test-fields/src/lib.rs:19,42,54,66 and proof-of-storage/src/fields/ft253_192.rs:7 (PrimeFieldModulus)
 MODULUS = {
     FT63: 5102708120182849537,
     FT127: 146823888364060453008360742206866194433,
     FT191: 1697146272512170708389931801544665676545308500647389167617,
     FT255: 46242760681095663677370860714659204618859642560429202607213929836750194081793,
+    FT253_192: 14474011154664524421669271390699307717822958659997404088829842556525106692097,
 }
-GENERATOR = {FT63: 10, FT127: 3, FT191: 5, FT255: 5}
+GENERATOR = {FT63: 10, FT127: 3, FT191: 5, FT255: 5, FT253_192: 3}
 NUM_BITS = {f: MODULUS[f].bit_length() for f in MODULUS}
-TWO_ADICITY = {FT63: 41, FT127: 40, FT191: 41, FT255: 41}
+TWO_ADICITY = {FT63: 41, FT127: 40, FT191: 41, FT255: 41, FT253_192: 192}
+# PrimeFieldReprEndianness (ft253_192.rs:9): to_repr() of Ft253_192 is the canonical value BIG-endian
+REPR_BIG_ENDIAN = {FT63: False, FT127: False, FT191: False, FT255: False, FT253_192: True}
 
 
 def build(force: bool = False) -> str:
@@ -149,6 +152,14 @@ def fe_to_canon(fid, a):
     out = np.empty_like(a)
     lib().orc_fe_to_canon(C.c_int(fid), _p64(out), _p64(a), C.c_size_t(a.size // LIMBS[fid]))
     return out
+
+
+def fe_to_repr(fid, a) -> bytes:
+    """PrimeField::to_repr() of every element, concatenated (8 * LIMBS bytes each; big-endian for Ft253_192)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty(a.size * 8, dtype=np.uint8)
+    lib().orc_fe_to_repr(C.c_int(fid), out.ctypes.data_as(u8p), _p64(a), C.c_size_t(a.size // LIMBS[fid]))
+    return out.tobytes()
 
 
 def fe_from_canon(fid, a):
@@ -588,10 +599,9 @@ def random_columns(key: bytes, n_cols: int, n: int) -> np.ndarray:
 
 def _transcript_update(tr: Transcript, label: bytes, fid: int, elems: np.ndarray) -> None:
     """FieldHash::transcript_update per element (lib.rs:48-50): to_repr bytes, one message each."""
-    canon = fe_to_canon(fid, elems)
     w = 8 * LIMBS[fid]
-    raw = canon.tobytes()
-    for i in range(canon.shape[0]):
+    raw = fe_to_repr(fid, elems)
+    for i in range(len(raw) // w):
         tr.append_message(label, raw[i * w:(i + 1) * w])
 
 
@@ -728,3 +738,21 @@ def pack_bytes7(data: bytes) -> np.ndarray:
     for k in range(7):
         out |= b[:, k] << np.uint64(8 * k)
     return out.reshape(n, 1)
+
+
+def pack_bytes31(data: bytes) -> np.ndarray:
+    """DataField::from_byte_vec for Ft253_192 (fields/data_field.rs:38-46, ft253_192.rs:18-30): each 31-byte group is
+    zero-padded to 32 and limb i = u64::from_be_bytes(group[8i : 8i+8]); the limbs are stored as they are (Montgomery
+    limbs).  Raises ValueError when a group is not below the modulus: the reference goes on computing with unreduced
+    limbs there, which is not a field computation (ff_derive's add drops the carry out of 2^256)."""
+    n = (len(data) + 30) // 31
+    buf = np.zeros((n, 32), dtype=np.uint8)
+    flat = np.zeros(n * 31, dtype=np.uint8)
+    flat[:len(data)] = np.frombuffer(data, dtype=np.uint8)
+    buf[:, :31] = flat.reshape(n, 31)
+    out = buf.reshape(n, 4, 8)[:, :, ::-1].copy().view(np.uint64).reshape(n, 4)  # big-endian bytes -> u64 per limb
+    p = MODULUS[FT253_192]
+    for v in from_limbs(out):
+        if v >= p:
+            raise ValueError("Ft253_192::from_data_bytes: group not below the modulus")
+    return out

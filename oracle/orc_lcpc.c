@@ -45,7 +45,7 @@ static const orc_field FIELDS[ORC_N_FIELDS] = {
      {0x2b8e9dfffffffffdull},
      {0x13085abb0716119eull},
      {0x23bcb75f84213a43ull},
-     0x7fffffffffffffffull},
+     0x7fffffffffffffffull, 0},
     {/* Ft127, generator 3 */
      2, 127, 40,
      {0x7f2bd90000000001ull, 0x6e754097ba20e0bfull},
@@ -53,7 +53,7 @@ static const orc_field FIELDS[ORC_N_FIELDS] = {
      {0x01a84dfffffffffeull, 0x23157ed08bbe3e81ull},
      {0x816bd5407cf6dce5ull, 0x2c1637057de6fce8ull},
      {0xf491a1dff39975f8ull, 0x178fd41c0f6a04faull},
-     0x7fffffffffffffffull},
+     0x7fffffffffffffffull, 0},
     {/* Ft191, generator 5 */
      3, 191, 41,
      {0xd246820000000001ull, 0x936888270ceecbcdull, 0x453708aa3fbc8ddaull},
@@ -61,7 +61,7 @@ static const orc_field FIELDS[ORC_N_FIELDS] = {
      {0x892c79fffffffffdull, 0x45c6678ad9339c96ull, 0x305ae60140ca5670ull},
      {0x6c25128031d873e2ull, 0xf71a3697a97ffdceull, 0x07ef71ae547daef9ull},
      {0xecd905456df2b092ull, 0x53ce189f0df0a05aull, 0x3f6e6da556ed31d9ull},
-     0x7fffffffffffffffull},
+     0x7fffffffffffffffull, 0},
     {/* Ft255, generator 5 */
      4, 255, 41,
      {0x02a4f20000000001ull, 0xef73c79086595f30ull, 0xfda9df04b9575969ull, 0x663c799b6e4d2900ull},
@@ -69,7 +69,16 @@ static const orc_field FIELDS[ORC_N_FIELDS] = {
      {0xfab61bfffffffffeull, 0x211870def34d419full, 0x04ac41f68d514d2cull, 0x33870cc92365adfeull},
      {0xcf06aad260ab9990ull, 0x12f0d8856156a683ull, 0x5da77ded73588e21ull, 0x38725a1646845639ull},
      {0x9c745ae52a496067ull, 0x95ee9a4091329682ull, 0x854a3ee53365b80eull, 0x16edffae79969e76ull},
-     0x7fffffffffffffffull},
+     0x7fffffffffffffffull, 0},
+    {/* Ft253_192 (proof-of-storage/src/fields/ft253_192.rs:6-10): p = (2^61 - 1) * 2^192 + 1, generator 3,
+        big-endian repr; REPR_SHAVE_BITS = 3 */
+     4, 253, 192,
+     {0x0000000000000001ull, 0, 0, 0x1fffffffffffffffull},
+     0xffffffffffffffffull,
+     {0xfffffffffffffff8ull, 0xffffffffffffffffull, 0xffffffffffffffffull, 0x0000000000000007ull},
+     {0xffffffffffff8040ull, 0xffffffffffffefffull, 0xfffffffffffffdffull, 0x0000000000007f7full},
+     {0xe94731e93d73da14ull, 0x0e0f79fb69eec7bfull, 0x246cdb0e8f061ce3ull, 0x029543679ced2616ull},
+     0x1fffffffffffffffull, 1},
 };
 
 const orc_field *orc_get_field(int fid) {
@@ -149,6 +158,17 @@ void orc_fe_to_canon(int fid, uint64_t *out, const uint64_t *a, size_t n) {
     int L = F->limbs;
     for (size_t i = 0; i < n; i++) {
 #define CALL(S) fe_to_canon##S(F, out + i * L, a + i * L)
+        DISPATCH(F, CALL);
+#undef CALL
+    }
+}
+
+/* PrimeField::to_repr() bytes of each element (8*LIMBS bytes per element) */
+void orc_fe_to_repr(int fid, uint8_t *out, const uint64_t *a, size_t n) {
+    const orc_field *F = &FIELDS[fid];
+    int L = F->limbs;
+    for (size_t i = 0; i < n; i++) {
+#define CALL(S) fe_to_repr##S(F, out + i * L * 8, a + i * L)
         DISPATCH(F, CALL);
 #undef CALL
     }

@@ -107,6 +107,19 @@ static inline void SUF(fe_to_canon)(const orc_field *F, uint64_t *r, const uint6
     SUF(fe_mul)(F, r, a, one);
 }
 
+/* PrimeField::to_repr(): the canonical value as 8*LIMBS bytes, little-endian for the lcpc-test-fields fields and
+ * WriteableFt63, big-endian for Ft253_192 (ff_derive's PrimeFieldReprEndianness attribute).  Host is little-endian. */
+static inline void SUF(fe_to_repr)(const orc_field *F, uint8_t *out, const uint64_t *a) {
+    uint64_t canon[LIMBS];
+    SUF(fe_to_canon)(F, canon, a);
+    if (!F->repr_big_endian) {
+        memcpy(out, canon, sizeof canon);
+    } else {
+        const uint8_t *src = (const uint8_t *)canon;
+        for (int i = 0; i < 8 * LIMBS; i++) out[i] = src[8 * LIMBS - 1 - i];
+    }
+}
+
 static inline void SUF(fe_from_canon)(const orc_field *F, uint64_t *r, const uint64_t *a) {
     SUF(fe_mul)(F, r, a, F->r2);
 }
@@ -127,7 +140,11 @@ static void SUF(fe_pow)(const orc_field *F, uint64_t *r, const uint64_t *a, uint
 static void SUF(fe_inv)(const orc_field *F, uint64_t *r, const uint64_t *a) {
     uint64_t e[LIMBS], acc[LIMBS], base[LIMBS];
     for (int i = 0; i < LIMBS; i++) { e[i] = F->p[i]; acc[i] = F->r[i]; base[i] = a[i]; }
-    e[0] -= 2; /* p is odd and > 2, low limb ends in ...01: no borrow */
+    for (int i = 0, borrow = 2; i < LIMBS && borrow; i++) { /* e = p - 2 (Ft253_192's low limb is 1: the borrow ripples) */
+        uint64_t v = e[i];
+        e[i] = v - (uint64_t)borrow;
+        borrow = v < (uint64_t)borrow;
+    }
     for (int i = 0; i < LIMBS; i++)
         for (int b = 0; b < 64; b++) {
             if ((e[i] >> b) & 1) SUF(fe_mul)(F, acc, acc, base);
@@ -246,9 +263,9 @@ static void SUF(hash_columns)(const orc_field *F, const uint64_t *comm, uint8_t 
         }
         for (size_t r = 0; r < n_rows; r++)
             for (size_t c = 0; c < nc; c++) {
-                uint64_t canon[LIMBS]; /* little-endian host: limbs == repr bytes */
-                SUF(fe_to_canon)(F, canon, comm + (r * row_stride + c0 + c) * LIMBS);
-                orc_b3_update(&dig[c], canon, sizeof canon);
+                uint8_t repr[8 * LIMBS];
+                SUF(fe_to_repr)(F, repr, comm + (r * row_stride + c0 + c) * LIMBS);
+                orc_b3_update(&dig[c], repr, sizeof repr);
             }
         for (size_t c = 0; c < nc; c++) orc_b3_finalize(&dig[c], hashes + (c0 + c) * 32);
     }
@@ -291,9 +308,9 @@ static void SUF(hash_column)(const orc_field *F, const uint64_t *col, size_t n_r
     orc_b3_init(&h);
     orc_b3_update(&h, zeros, 32);
     for (size_t r = 0; r < n_rows; r++) {
-        uint64_t canon[LIMBS];
-        SUF(fe_to_canon)(F, canon, col + r * LIMBS);
-        orc_b3_update(&h, canon, sizeof canon);
+        uint8_t repr[8 * LIMBS];
+        SUF(fe_to_repr)(F, repr, col + r * LIMBS);
+        orc_b3_update(&h, repr, sizeof repr);
     }
     orc_b3_finalize(&h, out);
 }

@@ -23,6 +23,8 @@ pub const LCPC_FT63: i32 = 0;
 pub const LCPC_FT127: i32 = 1;
 pub const LCPC_FT191: i32 = 2;
 pub const LCPC_FT255: i32 = 3;
+/// proof-of-storage `Ft253_192` (big-endian `to_repr`)
+pub const LCPC_FT253_192: i32 = 4;
 
 pub const LCPC_OK: i32 = 0;
 pub const LCPC_ERR_TOO_BIG: i32 = -1;

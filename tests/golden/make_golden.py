@@ -35,7 +35,10 @@ FIELDS = {
     1: (0x6e754097ba20e0bf7f2bd90000000001, 2, 40, 3),
     2: (0x453708aa3fbc8dda936888270ceecbcdd246820000000001, 3, 41, 5),
     3: (0x663c799b6e4d2900fda9df04b9575969ef73c79086595f3002a4f20000000001, 4, 41, 5),
+    # Ft253_192, proof-of-storage/src/fields/ft253_192.rs:6-10: (2^61 - 1) * 2^192 + 1, big-endian repr
+    4: (0x1fffffffffffffff000000000000000000000000000000000000000000000001, 4, 192, 3),
 }
+REPR_BYTE_ORDER = {0: "little", 1: "little", 2: "little", 3: "little", 4: "big"}  # PrimeFieldReprEndianness
 
 
 def sha(a) -> str:
@@ -98,14 +101,14 @@ def independent_section():
             for i in range(nc):
                 enc[bitrev(i, k)] = sum(row[j] * pow(w, i * j, p) for j in range(nc)) % p
             comm.append(enc)
-        # leaf = BLAKE3(0^32 || canonical little-endian repr of the column); the stored (Montgomery) limbs are
-        # value*R mod p, so with "value" taken as the canonical integer the repr is the value itself
+        # leaf = BLAKE3(0^32 || to_repr() of the column's elements): the canonical value, little-endian (big-endian for
+        # Ft253_192); the stored (Montgomery) limbs are value*R mod p, so the repr is the integer "value" itself
         leaves = []
         for c in range(nc):
             h = blake3.blake3()
             h.update(bytes(32))
             for r in range(n_rows):
-                h.update(comm[r][c].to_bytes(8 * limbs, "little"))
+                h.update(comm[r][c].to_bytes(8 * limbs, REPR_BYTE_ORDER[fid]))
             leaves.append(h.digest())
         level, tree = leaves, list(leaves)
         while len(level) > 1:
@@ -124,7 +127,7 @@ def derived_section():
     O.build()
     out = {"ligero": [], "brakedown": [], "pos_bytes": [], "prove": []}
     for fid, n, npr, nc in [(0, 1 << 16, 2048, 4096), (0, 125 * 64, 64, 128), (0, 3000, 100, 256), (1, 5000, 100, 256),
-                            (2, 3000, 60, 128), (3, 5000, 100, 256), (0, 700 * 32, 32, 64)]:
+                            (2, 3000, 60, 128), (3, 5000, 100, 256), (0, 700 * 32, 32, 64), (4, 5000, 100, 256)]:
         coeffs = O.random_field_elements(fid, 1000 + fid, n)
         c = O.commit(coeffs, O.LigeroEncoding(fid, npr, nc))
         tensor = O.random_field_elements(fid, 2000 + fid, c.n_rows)
@@ -133,7 +136,7 @@ def derived_section():
                               "root": c.get_root().hex(), "comm_sha256": sha(c.comm), "hashes_sha256": sha(c.hashes),
                               "fold_sha256": sha(O.collapse_columns(fid, c.coeffs, tensor)), "open_column": nc // 3,
                               "open_col_sha256": sha(col.col), "open_path_sha256": sha(col.path)})
-    for fid, npr, n_rows, seed in [(0, 150, 20, 0), (3, 150, 7, 1), (1, 400, 5, 0)]:
+    for fid, npr, n_rows, seed in [(0, 150, 20, 0), (3, 150, 7, 1), (1, 400, 5, 0), (4, 150, 7, 1)]:
         enc = O.SdigEncoding(fid, npr, seed)
         coeffs = O.random_field_elements(fid, 41, n_rows * npr - 3)
         c = O.commit(coeffs, enc)
@@ -146,8 +149,14 @@ def derived_section():
         c = O.commit(O.pack_bytes7(data), O.LigeroEncoding(0, npr, nc))
         out["pos_bytes"].append({"n_bytes": n_bytes, "n_per_row": npr, "n_cols": nc, "input": "bytes(i % 251 for i in range(n_bytes))",
                                  "root": c.get_root().hex(), "hashes_sha256": sha(c.hashes), "coeffs_sha256": sha(c.coeffs)})
-    # one full prove transcript: commitment, challenges and openings all hashed
-    fid, n = 0, 1 << 12
+    # full prove transcripts: commitment, challenges and openings all hashed (Ft63; Ft253_192 for the big-endian
+    # transcript messages)
+    for fid, n in [(0, 1 << 12), (4, 1 << 10)]:
+        _prove_case(O, out, fid, n)
+    return out
+
+
+def _prove_case(O, out, fid, n):
     enc = O.LigeroEncoding.new(fid, n)
     coeffs = O.random_field_elements(fid, 5, n)
     c = O.commit(coeffs, enc)
@@ -164,7 +173,6 @@ def derived_section():
                          "paths_sha256": sha(np.stack([col.path for col in proof.columns])),
                          "challenge_after_prove": tr.challenge_bytes(b"check", 32).hex()})
     del x
-    return out
 
 
 def main():

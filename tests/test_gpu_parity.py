@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-FIELDS = [0, 1, 2, 3]
+FIELDS = [0, 1, 2, 3, 4]
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +39,7 @@ def test_ligero_encode_rows_match_fft_io(P, oracle, fid, log_n):
     assert np.array_equal(got, O.fft_io(fid, rows))
 
 
-@pytest.mark.parametrize("fid,log_n", [(0, 17), (0, 18), (1, 17), (3, 15)])
+@pytest.mark.parametrize("fid,log_n", [(0, 17), (0, 18), (1, 17), (3, 15), (4, 15)])
 def test_ligero_encode_large_rows(P, oracle, fid, log_n):
     """Rows that need two or more strided passes in front of the shared-memory pass."""
     O = oracle
@@ -100,6 +100,13 @@ COMMIT_CASES = [
     # a million multi-limb coefficients each: ~2e7 Montgomery products per case through every NTT pass shape
     (1, (1 << 20) - 3, 16384, 32768),
     (3, (1 << 20) - 3, 16384, 32768),
+    # Ft253_192 (proof-of-storage/src/fields/ft253_192.rs): big-endian repr in the leaves, modulus words 0 / 0xffffffff
+    (4, 1, 1, 2),
+    (4, 5000, 100, 256),
+    (4, 70 * 64, 64, 128),          # 3 chunks
+    (4, 300 * 16, 16, 32),          # 10 chunks
+    (4, 75 * 2048 - 5, 2048, 4096), # chunk-pipelined host path
+    (4, (1 << 18) - 3, 8192, 16384),
 ]
 
 
@@ -206,7 +213,7 @@ def _to_pkg_csc(P, mats):
     return [P.CscMatrix(m.rows, m.cols, m.indptr, m.indices, m.data) for m in mats]
 
 
-@pytest.mark.parametrize("fid,n_per_row,n_rows,seed", [(0, 150, 20, 0), (3, 150, 7, 1), (1, 400, 5, 0), (2, 120, 3, 1)])
+@pytest.mark.parametrize("fid,n_per_row,n_rows,seed", [(0, 150, 20, 0), (3, 150, 7, 1), (1, 400, 5, 0), (2, 120, 3, 1), (4, 150, 7, 1)])
 def test_brakedown_commit_matches_oracle(P, oracle, fid, n_per_row, n_rows, seed):
     """SdigEncodingS::encode on every row + Merkle tree with a non power-of-two n_cols
     (padding leaves stay zero, lib.rs:685-695)."""
@@ -252,6 +259,43 @@ def test_commit_bytes_matches_oracle(P, oracle, n_bytes):
     got = P.LcCommit.commit_bytes(data, P.LigeroEncoding(0, n_per_row, n_cols))
     assert np.array_equal(got.coeffs, exp.coeffs)
     assert np.array_equal(got.hashes, exp.hashes)
+
+
+def _ft253_file(n_bytes: int, seed: int) -> bytes:
+    """Random file bytes whose 31-byte groups are all below the Ft253_192 modulus (byte 24 of a group <= 0x1f)."""
+    rng = np.random.default_rng(seed)
+    data = rng.integers(0, 256, n_bytes, dtype=np.uint8)
+    data[24::31] &= 0x1F
+    return data.tobytes()
+
+
+@pytest.mark.parametrize("n_bytes", [1, 24, 25, 30, 31, 32, 62, 63, 598, 100003])
+def test_commit_bytes_ft253_192_matches_oracle(P, oracle, n_bytes):
+    """Ft253_192::from_data_bytes (ft253_192.rs:18-30) fused in front of the commit: 31 bytes per element, big-endian limbs."""
+    O = oracle
+    data = _ft253_file(n_bytes, n_bytes)
+    elems = O.pack_bytes31(data)
+    n_per_row, n_cols = (4, 8) if n_bytes < 1000 else (64, 128)
+    exp = O.commit(elems, O.LigeroEncoding(4, n_per_row, n_cols))
+    got = P.LcCommit.commit_bytes(data, P.LigeroEncoding(4, n_per_row, n_cols))
+    assert np.array_equal(got.coeffs, exp.coeffs)
+    assert np.array_equal(got.comm, exp.comm)
+    assert np.array_equal(got.hashes, exp.hashes)
+
+
+def test_commit_bytes_ft253_192_refuses_unreduced_groups(P, oracle):
+    """A group with byte 24 > 0x1f has limbs >= p; the reference keeps computing on them (not a field computation), the
+    library refuses (include/lcpc_b200.h, lcpc_commit_bytes_host)."""
+    data = bytearray(_ft253_file(31 * 40, 7))
+    data[31 * 17 + 24] = 0x20
+    with pytest.raises(ValueError):
+        oracle.pack_bytes31(bytes(data))
+    with pytest.raises(P.LcpcError):
+        P.LcCommit.commit_bytes(bytes(data), P.LigeroEncoding(4, 4, 8))
+    data[31 * 17 + 24] = 0x1F  # the largest top byte that is still below the modulus
+    got = P.LcCommit.commit_bytes(bytes(data), P.LigeroEncoding(4, 4, 8))
+    exp = oracle.commit(oracle.pack_bytes31(bytes(data)), oracle.LigeroEncoding(4, 4, 8))
+    assert got.get_root() == exp.get_root()
 
 
 # ----------------------------------------------------------------------------- full size

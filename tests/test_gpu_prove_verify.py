@@ -50,7 +50,7 @@ def _same_proof(a, b):
         assert np.array_equal(u.col, v.col) and np.array_equal(u.path, v.path)
 
 
-@pytest.mark.parametrize("fid,length", [(0, 1 << 12), (0, 5000), (1, 1 << 11), (3, 1 << 10)])
+@pytest.mark.parametrize("fid,length", [(0, 1 << 12), (0, 5000), (1, 1 << 11), (3, 1 << 10), (4, 1 << 10)])
 def test_ligero_prove_verify_matches_oracle(P, oracle, fid, length):
     O = oracle
     coeffs = O.random_field_elements(fid, 70 + fid, length)
@@ -152,7 +152,7 @@ def test_verify_rejects_tampering_with_reference_variants(P, oracle):
     assert ei.value.variant == "OuterTensor"
 
 
-@pytest.mark.parametrize("fid,seed", [(0, 0), (3, 1)])
+@pytest.mark.parametrize("fid,seed", [(0, 0), (3, 1), (4, 1)])
 def test_brakedown_prove_verify_matches_oracle(P, oracle, fid, seed):
     """SdigEncoding::new(len, seed) on both sides (host-side matgen), then commit/prove/verify."""
     O = oracle

@@ -49,6 +49,7 @@ def _stream_elems(P, enc, elems, max_rows, block_rows, pushes):
     (1, 64, 128, 130, 3, 17),       # 16-byte elements: 64 rows per chunk
     (2, 16, 32, 200, 0, 23),        # 24-byte elements straddle chunk boundaries
     (3, 64, 128, 70, 9, 11),        # 32-byte elements
+    (4, 64, 128, 70, 9, 11),        # Ft253_192: big-endian repr
 ])
 def test_stream_commit_equals_in_memory_commit(P, oracle, fid, n_per_row, n_cols, n_rows, ragged, block_rows):
     O = oracle
@@ -126,7 +127,7 @@ def test_convert_unencoded_file_layout_and_tree(P, oracle, tmp_path, n_bytes, pr
 @pytest.mark.parametrize("fid,n_per_row,n_cols,n_rows,row0,k", [
     (0, 64, 128, 700, 0, 1), (0, 64, 128, 700, 123, 3), (0, 64, 128, 700, 699, 1), (0, 64, 128, 700, 100, 400),
     (0, 64, 128, 50, 7, 2),      # single-chunk leaves
-    (2, 16, 32, 200, 41, 5), (3, 64, 128, 70, 30, 9),
+    (2, 16, 32, 200, 41, 5), (3, 64, 128, 70, 30, 9), (4, 64, 128, 70, 30, 9),
 ])
 def test_update_rows_equals_recommit(P, oracle, fid, n_per_row, n_cols, n_rows, row0, k):
     O = oracle

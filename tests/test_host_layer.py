@@ -30,7 +30,7 @@ def test_transcript_kat_and_matches_oracle(oracle):
     assert c.challenge_bytes(b"x", 32) == a.challenge_bytes(b"x", 32) == b.challenge_bytes(b"x", 32)
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4])
 def test_challenge_expansion_matches_oracle(oracle, fid):
     lib = _lib.load()
     key = bytes((11 * i + fid) % 256 for i in range(32))

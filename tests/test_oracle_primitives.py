@@ -17,7 +17,7 @@ import pytest
 
 blake3_pkg = pytest.importorskip("blake3")
 
-FIELDS = [0, 1, 2, 3]
+FIELDS = [0, 1, 2, 3, 4]
 
 
 @pytest.mark.parametrize(

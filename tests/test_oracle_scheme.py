@@ -19,7 +19,7 @@ def _py_leaf(O, fid, comm, j):
     h = blake3_pkg.blake3()
     h.update(bytes(32))
     for v in O.from_mont(fid, comm[:, j]):
-        h.update(v.to_bytes(w, "little"))
+        h.update(v.to_bytes(w, "big" if O.REPR_BIG_ENDIAN[fid] else "little"))  # PrimeFieldReprEndianness
     return h.digest()
 
 
@@ -32,7 +32,7 @@ def _py_tree(leaves):
     return [h for lvl in levels for h in lvl]
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4])
 def test_merkleize_matches_serial(oracle, fid):
     """T1: lcpc-2d/src/tests.rs:136-149 (parallel merkleize == merkleize_ser)."""
     O = oracle
@@ -49,7 +49,7 @@ def test_merkleize_matches_serial(oracle, fid):
     assert [t.tobytes() for t in tree] == exp
 
 
-@pytest.mark.parametrize("fid", [0, 3])
+@pytest.mark.parametrize("fid", [0, 3, 4])
 def test_collapse_columns_matches_ints(oracle, fid):
     """T2: lcpc-2d/src/tests.rs:151-165 (collapse_columns == eval_outer_ser)."""
     O = oracle
