@@ -327,18 +327,34 @@ __global__ void k_pack_bytes31(const uint8_t *__restrict__ bytes, size_t n_bytes
                                size_t n_elems, uint32_t *__restrict__ bad) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_elems) return;
+    // Every load is unconditional on a clamped address and the value is masked afterwards, and the limbs are put
+    // together from 32-bit words: the first version (predicated byte loads summed into zeroed 64-bit register pairs)
+    // returned 0x0c in the low byte of limb 0 whenever byte 6 of the group lay beyond the end of the file
+    // (gpurun_out/dbg1.log of round 1; the stale value is the address offset of byte 12, held in the same register a
+    // few instructions earlier).
+    const size_t last = n_bytes - 1;  // n_elems > 0 implies n_bytes > 0
+    uint32_t word[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = 4 * j + k;  // position inside the zero-padded 32-byte group
+            uint32_t byte = 0;
+            if (idx < 31) {
+                const size_t b = e * 31 + idx;
+                const uint32_t v = bytes[b < n_bytes ? b : last];
+                byte = b < n_bytes ? v : 0u;
+            }
+            w = (w << 8) | byte;
+        }
+        word[j] = w;
+    }
     uint64_t limb[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        uint64_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const size_t b = e * 31 + 8 * i + k;
-            const uint64_t byte = (8 * i + k < 31 && b < n_bytes) ? bytes[b] : 0;
-            v = (v << 8) | byte;
-        }
-        limb[i] = v;
-        elems[e * 4 + i] = v;
+        limb[i] = ((uint64_t)word[2 * i] << 32) | word[2 * i + 1];
+        elems[e * 4 + i] = limb[i];
     }
     if (Field<FT253_192>::geq_p(limb)) atomicOr(bad, 1u);
 }

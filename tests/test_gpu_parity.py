@@ -269,7 +269,7 @@ def _ft253_file(n_bytes: int, seed: int) -> bytes:
     return data.tobytes()
 
 
-@pytest.mark.parametrize("n_bytes", [1, 24, 25, 30, 31, 32, 62, 63, 598, 100003])
+@pytest.mark.parametrize("n_bytes", [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 23, 24, 25, 30, 31, 32, 33, 38, 62, 63, 598, 100003])
 def test_commit_bytes_ft253_192_matches_oracle(P, oracle, n_bytes):
     """Ft253_192::from_data_bytes (ft253_192.rs:18-30) fused in front of the commit: 31 bytes per element, big-endian limbs."""
     O = oracle
