@@ -260,6 +260,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hashing", default="columns", choices=["columns", "rows"],
+                    help="N > 1 only: 'rows' hashes BLAKE3 chunks where the rows are and re-shards 32-byte chaining values "
+                         "instead of the encoded matrix (ShardedLigeroCommitter hashing='rows'; not the default yet)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,7 +296,12 @@ def main() -> None:
     n_total = n_rows_total * N_PER_ROW
     np2 = N_COLS
     # this rank's rows of the coefficient matrix (seed 2 stream, sliced by row block)
-    h_coeffs_np = make_coeffs(2, n_total)[rank * ROWS_PER_GPU * N_PER_ROW:(rank + 1) * ROWS_PER_GPU * N_PER_ROW]
+    row0, rows_local = rank * ROWS_PER_GPU, ROWS_PER_GPU
+    if world > 1 and args.hashing == "rows":  # chunk-aligned row blocks: 508 / 512 / ... / 516 rows at 8 GPUs
+        from lcpc_proof_of_storage_b200.sharded import chunk_row_partition
+
+        row0, rows_local = chunk_row_partition(1, n_rows_total, world)[0][rank]
+    h_coeffs_np = make_coeffs(2, n_total)[row0 * N_PER_ROW:(row0 + rows_local) * N_PER_ROW]
     h_coeffs = torch.from_numpy(h_coeffs_np.view(np.int64).reshape(-1)).pin_memory()
     d_coeffs = h_coeffs.cuda(non_blocking=True)
     torch.cuda.synchronize()
@@ -316,12 +324,13 @@ def main() -> None:
     else:
         from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter
 
-        sc = ShardedLigeroCommitter(enc, n_rows_total, dist.group.WORLD)
+        sc = ShardedLigeroCommitter(enc, n_rows_total, dist.group.WORLD, hashing=args.hashing)
+        assert (sc.row0, sc.rows_local) == (row0, rows_local)
 
         def step():
             # commit k's column hashing is issued after commit k+1's encode (three symmetric buffers): its exchange drains
             # over NVLink behind the next encode.  finish() below completes the last one INSIDE the timed region.
-            sc.commit(d_coeffs, defer=True)
+            sc.commit(d_coeffs, defer=sc.fused)
 
         def root_hex():
             return sc.root().hex() if rank == 0 else ""
@@ -382,7 +391,7 @@ def main() -> None:
     e2e = None
     h_comm = torch.empty(ROWS_PER_GPU * N_COLS, dtype=torch.int64).pin_memory()
     h_hashes = torch.empty((2 * np2 - 1) * 32, dtype=torch.uint8).pin_memory()
-    n_local = ROWS_PER_GPU * N_PER_ROW
+    n_local = rows_local * N_PER_ROW
     e2e_steps = max(1, min(steps, 20))
 
     def e2e_step():
@@ -516,7 +525,9 @@ def main() -> None:
                    "parallelism": "single GPU" if world == 1 else (
                        f"row shards x{world}; " + ("encode kernel stores into peer column blocks over NVLink (symmetric memory); commit k hashed "
                                                     "after commit k+1's encode is issued, all K finished inside the timed region"
-                                                   if sc.fused else "NCCL all-to-all") + "; per-rank Merkle subtrees, roots all-gathered")},
+                                                   if sc.fused else ("BLAKE3 chunk chaining values hashed where the rows are, NCCL all-to-all of "
+                                                                     "32 B per chunk and column" if sc.hashing == "rows" else "NCCL all-to-all"))
+                       + "; per-rank Merkle subtrees, roots all-gathered")},
         "algorithmic_GBps": step_gbs,
         "host_binding": numa,
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,

@@ -290,6 +290,19 @@ int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_
  * matrix with `n_rows` rows whose row stride is `row_stride` elements, starting at d_mat. */
 int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows,
                               size_t row_stride, size_t n_cols, uint8_t *d_leaves);
+/* Row-sharded form of hash_columns (lib.rs:736-775) for the one-process-per-GPU path: a leaf is BLAKE3 over
+ * 32 + n_rows_total * w bytes, and BLAKE3 hashes every 1024-byte chunk of that stream independently before its parent
+ * tree joins them.  A rank that owns the rows of whole chunks computes their chaining values for ALL columns from its
+ * own rows, and only 32 bytes per (chunk, column) travel.  d_mat = encoded rows starting at global row `row_base`
+ * (row stride `row_stride` elements); chunks [chunk0, chunk_end) of the n_rows_total-row leaf are written to
+ * d_cvs[((chunk - chunk0) * n_cols + column) * 32].  The rows of those chunks must lie inside d_mat.  LCPC_ERR_DIMS when the leaf is a single chunk (its chaining value IS the leaf: use
+ * lcpc_dev_hash_columns) or when an element straddles chunk boundaries (24-byte elements). */
+int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
+                                  size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
+                                  uint64_t chunk_end, uint8_t *d_cvs);
+/* leaves[j] = BLAKE3 parent tree over d_cvs[(c * n_cols + j) * 32], c in [0, n_chunks), n_chunks >= 2: the second half
+ * of hash_columns once every chunk's chaining value is in place. */
+int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves);
 /* merkle_tree (lib.rs:777-815) in place over [n_leaves | n_leaves/2 | ... | 1]; n_leaves a power of two. */
 int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves);
 /* collapse_columns on device buffers; d_out has n_tensors*width elements. */

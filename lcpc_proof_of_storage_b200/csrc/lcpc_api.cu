@@ -754,6 +754,37 @@ int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_ma
     return LCPC_OK;
 }
 
+int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
+                                  size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
+                                  uint64_t chunk_end, uint8_t *d_cvs) {
+    if (!ctx || !d_mat || !d_cvs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    const uint64_t w = 8ull * (uint64_t)limbs_of(field);
+    const uint64_t total = 32 + (uint64_t)n_rows_total * w, n_chunks = (total + 1023) / 1024;
+    if (1024 % w != 0) return fail(LCPC_ERR_DIMS, "elements straddle BLAKE3 chunk boundaries for this field");
+    if (n_chunks < 2) return fail(LCPC_ERR_DIMS, "single-chunk leaf: use lcpc_dev_hash_columns");
+    if (chunk0 > chunk_end || chunk_end > n_chunks) return fail(LCPC_ERR_INVALID_ARG, "chunk range outside the leaf");
+    // first row of chunk0 (chunk 0 starts with the 32-byte zero prefix) must not lie in front of the window
+    const uint64_t first_row = chunk0 == 0 ? 0 : (chunk0 * 1024 - 32) / w;
+    if (chunk0 < chunk_end && first_row < row_base) return fail(LCPC_ERR_INVALID_ARG, "chunk range starts before row_base");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    // the kernel indexes chaining values by absolute chunk number; the caller's buffer starts at chunk0
+    uint8_t *cvs_abs = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(d_cvs) - (uintptr_t)(chunk0 * n_cols * 32));
+    CU(hash_chunk_range(field, d_mat, (int64_t)row_base, n_rows_total, row_stride, n_cols, chunk0, chunk_end, total, n_chunks,
+                        cvs_abs, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves) {
+    if (!ctx || !d_cvs || !d_leaves) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (n_chunks < 2) return fail(LCPC_ERR_DIMS, "a single chaining value is the leaf itself");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(hash_merge(d_cvs, n_cols, n_chunks, d_leaves, ctx->lc()));
+    return LCPC_OK;
+}
+
 int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves) {
     if (!ctx || !d_hashes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two");

@@ -8,6 +8,10 @@ lcpc-2d/src/lib.rs:651-700: `par_chunks_mut` over rows (:677-682) becomes the ro
 log2(world) levels of `merkle_tree` (:777-815) are computed once on rank 0.  The result
 (root, tree, fold vectors, opened columns) is bit-identical to the single-GPU commit.
 
+A second hashing mode (hashing="rows", SURVEY.md section 8e's lower-traffic alternative) keeps the encoded matrix
+row-sharded: BLAKE3 hashes the 1024-byte chunks of a leaf independently, so each rank computes the chunk chaining values
+of ALL columns over its own (chunk-aligned) rows and only those 32-byte values are re-sharded to column blocks.
+
 `torch.distributed` carries the plumbing (NCCL over NVLink on GPUs; gloo in the CPU tests,
 where the numerical back end is injected by the test).
 """
@@ -20,6 +24,35 @@ import torch.distributed as dist
 
 from . import _lib
 from .lcpc2d import FIELD_LIMBS, LcColumn, LigeroEncoding, log2, next_pow2
+
+
+def chunk_row_partition(limbs: int, n_rows: int, world: int):
+    """Row blocks whose boundaries are BLAKE3 chunk boundaries of the column leaves (the
+    lower-traffic hashing): the leaf stream of a column is 32 zero bytes followed by 8*limbs bytes per row, BLAKE3
+    cuts it into 1024-byte chunks, so chunk 0 holds the first (1024 - 32) / w rows and every later chunk 1024 / w.
+    Rank q owns chunks [c0, c1) and exactly their rows; the boundaries are the chunk boundaries nearest to the even
+    split q * n_rows / world.  Returns (rows, chunks): [(row0, count)] and [(c0, c1)] per rank, or None when the
+    elements straddle chunk boundaries (24-byte elements) or the leaf is a single chunk."""
+    w = 8 * limbs
+    if 1024 % w:
+        return None
+    n_chunks = (32 + n_rows * w + 1023) // 1024
+    if n_chunks < 2:
+        return None
+    first, per = (1024 - 32) // w, 1024 // w
+
+    def start(c: int) -> int:  # first row of chunk c; start(n_chunks) = n_rows
+        return 0 if c == 0 else min(n_rows, first + (c - 1) * per)
+
+    bounds = [0]
+    for q in range(1, world):
+        target = q * n_rows / world
+        c = min(range(bounds[-1], n_chunks + 1), key=lambda k: (abs(start(k) - target), k))
+        bounds.append(c)
+    bounds.append(n_chunks)
+    chunks = [(bounds[q], bounds[q + 1]) for q in range(world)]
+    rows = [(start(c0), start(c1) - start(c0)) for c0, c1 in chunks]
+    return rows, chunks
 
 
 def row_partition(n_rows: int, world: int) -> List[Tuple[int, int]]:
@@ -70,6 +103,19 @@ class GpuOps:
     def merkle_tree(self, hashes: torch.Tensor, n_leaves: int) -> None:
         _lib.check(self.lib.lcpc_dev_merkle_tree(self.enc.ctx.handle, hashes.data_ptr(), n_leaves))
 
+    def hash_chunk_range(self, mat: torch.Tensor, row_base: int, n_rows_total: int, n_cols: int, chunk0: int,
+                         chunk_end: int) -> torch.Tensor:
+        """BLAKE3 chaining values of chunks [chunk0, chunk_end) of every column's leaf, from this rank's encoded rows:
+        [chunk_end - chunk0, n_cols, 32] bytes."""
+        out = torch.empty((chunk_end - chunk0) * n_cols * 32, dtype=torch.uint8, device=self.device)
+        if chunk_end > chunk0:
+            _lib.check(self.lib.lcpc_dev_hash_chunk_range(self.enc.ctx.handle, self.fid, mat.data_ptr(), row_base, n_rows_total,
+                                                          n_cols, n_cols, chunk0, chunk_end, out.data_ptr()))
+        return out
+
+    def hash_merge(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, out: torch.Tensor) -> None:
+        _lib.check(self.lib.lcpc_dev_hash_merge(self.enc.ctx.handle, cvs.data_ptr(), n_cols, n_chunks, out.data_ptr()))
+
     def fold(self, mat: torch.Tensor, n_rows: int, width: int, row_stride: int, tensors: torch.Tensor,
              n_tensors: int) -> torch.Tensor:
         out = torch.zeros(n_tensors * width * self.L, dtype=torch.int64, device=self.device)
@@ -93,7 +139,11 @@ class ShardedLigeroCommitter:
     the top of the tree and the root.
     """
 
-    def __init__(self, enc, n_rows_total: int, group=None, ops=None, fused: Optional[bool] = None):
+    def __init__(self, enc, n_rows_total: int, group=None, ops=None, fused: Optional[bool] = None, hashing: str = "columns"):
+        """hashing="columns" (default): the encoded matrix is re-sharded to column blocks and every rank hashes whole
+        columns.  hashing="rows": every rank hashes the BLAKE3 chunks of ALL columns that its own rows make up
+        (chunk-aligned row blocks, chunk_row_partition) and only the 32-byte chunk chaining values are re-sharded to
+        column blocks -- 3 % of the volume for 8-byte elements; the encoded matrix stays row-sharded."""
         self.enc = enc
         self.group = group
         self.world = dist.get_world_size(group)
@@ -108,6 +158,19 @@ class ShardedLigeroCommitter:
         # the PADDED leaf range is sharded, so padding (all-zero) leaves fall in the last shards
         self.cb = self.np2 // self.world
         self.rows = row_partition(n_rows_total, self.world)
+        self.hashing, self.chunks = "columns", None
+        if hashing == "rows":
+            part = chunk_row_partition(self.L, n_rows_total, self.world) if self.np2 == self.n_cols else None
+            if part is None:
+                raise ValueError("hashing='rows' needs power-of-two n_cols, elements that divide a 1024-byte chunk and "
+                                 "leaves of at least two chunks")
+            self.rows, self.chunks = part
+            self.hashing = "rows"
+            self.n_chunks = self.chunks[-1][1]
+            fused = False
+        elif hashing != "columns":
+            raise ValueError("hashing must be 'columns' or 'rows'")
+        self.comm_rows: Optional[torch.Tensor] = None   # hashing="rows": [rows_local, n_cols, L], my rows, all columns
         self.row0, self.rows_local = self.rows[self.rank]
         self.col0 = self.rank * self.cb
         self.cols_local = max(0, min(self.n_cols, self.col0 + self.cb) - self.col0)  # real columns in my block
@@ -170,6 +233,9 @@ class ShardedLigeroCommitter:
                 self.flush()
             return
         comm = self.ops.encode(coeffs_local, self.rows_local)  # [rows_local, n_cols, L]
+        if self.hashing == "rows":
+            self._commit_row_hashed(comm, dev)
+            return
         if W == 1:
             # a single rank owns every column: hash the encoded matrix where it is (row stride n_cols, no padding copy)
             self.comm_cols = comm
@@ -194,6 +260,29 @@ class ShardedLigeroCommitter:
         self.comm_cols = recv  # row-major [n_rows_total, cb, L] because row blocks arrive in rank order
         self._finish_tree(dev)
 
+    def _commit_row_hashed(self, comm: torch.Tensor, dev) -> None:
+        """Chunk chaining values of all columns from my rows, an all-to-all of those (32 bytes per chunk and column),
+        then the BLAKE3 parent tree per column of my column block, my Merkle subtree and the join of the roots."""
+        cb, W = self.cb, self.world
+        self.comm_rows = comm
+        c0, c1 = self.chunks[self.rank]
+        cvs = self.ops.hash_chunk_range(comm, self.row0, self.n_rows, self.n_cols, c0, c1)  # [c1 - c0, n_cols, 32]
+        if W > 1:
+            send = cvs.view(c1 - c0, W, cb * 32).transpose(0, 1).contiguous()  # one slab per destination column block
+            recv = torch.empty(self.n_chunks * cb * 32, dtype=torch.uint8, device=dev)
+            in_splits = [(c1 - c0) * cb * 32] * W
+            out_splits = [(b - a) * cb * 32 for a, b in self.chunks]
+            dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=self.group)
+        else:
+            recv = cvs
+        # chunk order = rank order, so recv is [n_chunks, cb, 32]: the chaining-value store of my column block
+        if self.subtree is None or self.subtree.device != dev:
+            self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
+            self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
+            self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
+        self.ops.hash_merge(recv, cb, self.n_chunks, self.subtree)
+        self._join_subtrees()
+
     def flush(self) -> None:
         """Finish the deferred commit, if any (collective: every rank calls it at the same point)."""
         if self._pending is None:
@@ -213,6 +302,10 @@ class ShardedLigeroCommitter:
             self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
         if self.cols_local:
             self.ops.hash_columns(recv, self.n_rows, self.col_stride, self.cols_local, self.subtree)
+        self._join_subtrees()
+
+    def _join_subtrees(self) -> None:
+        cb, W = self.cb, self.world
         self.ops.merkle_tree(self.subtree, cb)
         # only the subtree roots travel (32 bytes per rank); rank 0 joins them
         my_root = self.subtree[-32:]
@@ -295,7 +388,9 @@ class ShardedLigeroCommitter:
                 from .lcpc2d import ProverError
 
                 raise ProverError("ColumnNumber", "bad column number")
-        dev = self.comm_cols.device
+        by_rows = self.hashing == "rows"  # the encoded matrix is row-sharded: values come from every rank, paths from the owner
+        dev = (self.comm_rows if by_rows else self.comm_cols).device
+        val_w = 0 if by_rows else self.n_rows * L  # words of column values in an owner's payload
         depth = log2(self.n_cols)
         depth_sub = min(depth, log2(cb))  # path levels inside a subtree
         owners = [c // cb for c in cols]
@@ -303,8 +398,11 @@ class ShardedLigeroCommitter:
 
         def my_payload():
             idx = torch.tensor([c - self.col0 for c in mine], dtype=torch.long, device=dev)
-            m3 = self.comm_cols.view(self.n_rows, self.col_stride, L)
-            vals = m3.index_select(1, idx).transpose(0, 1).contiguous().view(len(mine), -1)  # [k, n_rows*L]
+            if by_rows:
+                vals = torch.empty(len(mine), 0, dtype=torch.int64, device=dev)
+            else:
+                m3 = self.comm_cols.view(self.n_rows, self.col_stride, L)
+                vals = m3.index_select(1, idx).transpose(0, 1).contiguous().view(len(mine), -1)  # [k, n_rows*L]
             sub = self.subtree.view(-1, 32)
             parts, off, n, node = [], 0, cb, idx.clone()
             for _ in range(depth_sub):
@@ -316,8 +414,23 @@ class ShardedLigeroCommitter:
             # one int64 buffer per rank: values, then the path bytes (32-byte digests = 4 words each)
             return torch.cat([vals, paths.contiguous().view(torch.int64).view(len(mine), -1)], dim=1).contiguous()
 
-        width = self.n_rows * L + depth_sub * 4
+        width = val_w + depth_sub * 4
         payload = my_payload() if mine else torch.empty(0, width, dtype=torch.int64, device=dev)
+        gathered = None
+        if by_rows:
+            # every rank contributes its rows of the requested columns, padded to the longest row block
+            max_rows = max(cnt for _, cnt in self.rows)
+            part = torch.zeros(max_rows, len(cols), L, dtype=torch.int64, device=dev)
+            if self.rows_local:
+                idx_all = torch.tensor(list(cols), dtype=torch.long, device=dev)
+                part[:self.rows_local] = self.comm_rows.view(self.rows_local, self.n_cols, L).index_select(1, idx_all)
+            if W > 1:
+                parts_all = [torch.empty_like(part) for _ in range(W)] if self.rank == 0 else None
+                dist.gather(part, parts_all, dst=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+            else:
+                parts_all = [part]
+            if self.rank == 0:
+                gathered = torch.cat([parts_all[q][:cnt] for q, (_, cnt) in enumerate(self.rows)], dim=0).cpu().numpy()
         counts = [sum(1 for o in owners if o == q) for q in range(W)]
         if self.rank == 0:
             bufs = [payload] + [torch.empty(counts[q], width, dtype=torch.int64, device=dev) for q in range(1, W)]
@@ -332,11 +445,14 @@ class ShardedLigeroCommitter:
         host = [b.cpu().numpy() for b in bufs]
         top = self.top.cpu().numpy().reshape(-1, 32)
         out, seen = [], [0] * W
-        for c, q in zip(cols, owners):
+        for k, (c, q) in enumerate(zip(cols, owners)):
             row = host[q][seen[q]]
             seen[q] += 1
-            col = row[:self.n_rows * L].view(np.uint64).reshape(self.n_rows, L)
-            path = [row[self.n_rows * L:].view(np.uint8).reshape(depth_sub, 32)] if depth_sub else []
+            if by_rows:
+                col = np.ascontiguousarray(gathered[:, k]).view(np.uint64).reshape(self.n_rows, L)
+            else:
+                col = row[:val_w].view(np.uint64).reshape(self.n_rows, L)
+            path = [row[val_w:].view(np.uint8).reshape(depth_sub, 32)] if depth_sub else []
             off, n, node = 0, W, q
             for _ in range(depth - depth_sub):  # siblings among / above the subtree roots
                 path.append(top[off + (node ^ 1)][None])

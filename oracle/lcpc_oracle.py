@@ -756,3 +756,46 @@ def pack_bytes31(data: bytes) -> np.ndarray:
         if v >= p:
             raise ValueError("Ft253_192::from_data_bytes: group not below the modulus")
     return out
+
+
+# ---- pieces of hash_columns for a row-sharded commit (test double of lcpc_dev_hash_chunk_range / lcpc_dev_hash_merge) ----
+
+def leaf_chunks(fid: int, n_rows: int) -> int:
+    """Number of 1024-byte BLAKE3 chunks of a leaf: 32 zero bytes + n_rows reprs (lib.rs:749-764)."""
+    return (32 + n_rows * 8 * LIMBS[fid] + 1023) // 1024
+
+
+def hash_chunk_cvs(fid: int, rows: np.ndarray, row_base: int, n_rows_total: int, chunk0: int, chunk_end: int) -> np.ndarray:
+    """Chaining values of chunks [chunk0, chunk_end) of every column's leaf stream, computed from the row window
+    `rows` ([n_local, n_cols, LIMBS], first row = global row `row_base`).  Returns [chunk_end - chunk0, n_cols, 32]."""
+    w = 8 * LIMBS[fid]
+    n_local, n_cols = rows.shape[0], rows.shape[1]
+    total = 32 + n_rows_total * w
+    out = np.zeros((chunk_end - chunk0, n_cols, 32), dtype=np.uint8)
+    buf = (C.c_uint8 * 32)()
+    for j in range(n_cols):
+        col = fe_to_repr(fid, np.ascontiguousarray(rows[:, j]))  # bytes of the local rows of this column
+        for c in range(chunk0, chunk_end):
+            lo, hi = 1024 * c, min(1024 * (c + 1), total)
+            piece = bytearray()
+            if lo < 32:
+                piece += bytes(32 - lo)
+                lo = 32
+            a, b = lo - 32 - row_base * w, hi - 32 - row_base * w  # offsets into `col`
+            assert 0 <= a <= b <= n_local * w, "chunk range reaches outside the row window"
+            piece += col[a:b]
+            lib().orc_b3_chunk_cv(bytes(piece), C.c_size_t(len(piece)), C.c_uint64(c), buf)
+            out[c - chunk0, j] = np.frombuffer(bytes(buf), dtype=np.uint8)
+    return out
+
+
+def hash_merge(cvs: np.ndarray) -> np.ndarray:
+    """Leaves from chunk chaining values [n_chunks >= 2, n_cols, 32] -> [n_cols, 32]."""
+    n_chunks, n_cols = cvs.shape[0], cvs.shape[1]
+    out = np.zeros((n_cols, 32), dtype=np.uint8)
+    buf = (C.c_uint8 * 32)()
+    for j in range(n_cols):
+        col = np.ascontiguousarray(cvs[:, j])
+        lib().orc_b3_merge_cvs(col.ctypes.data_as(u8p), C.c_size_t(n_chunks), buf)
+        out[j] = np.frombuffer(bytes(buf), dtype=np.uint8)
+    return out

@@ -164,3 +164,51 @@ void orc_blake3(const void *data, size_t len, uint8_t out[ORC_B3_OUT]) {
     orc_b3_update(&h, data, len);
     orc_b3_finalize(&h, out);
 }
+
+/* ---- pieces of the tree, for checking a row-sharded hash (one rank computes the chaining values of the chunks whose
+ * bytes it owns, another joins them): the public BLAKE3 spec's chunk chaining value and parent tree ------------- */
+
+static void cv_bytes(const uint32_t cv[8], uint8_t out[32]) {
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)cv[i];
+        out[4 * i + 1] = (uint8_t)(cv[i] >> 8);
+        out[4 * i + 2] = (uint8_t)(cv[i] >> 16);
+        out[4 * i + 3] = (uint8_t)(cv[i] >> 24);
+    }
+}
+
+/* chaining value (not a root) of chunk number `chunk_index` holding `len` <= 1024 bytes */
+void orc_b3_chunk_cv(const void *data, size_t len, uint64_t chunk_index, uint8_t out[32]) {
+    orc_b3_hasher h;
+    uint32_t cv[8];
+    chunk_reset(&h, chunk_index);
+    chunk_update(&h, (const uint8_t *)data, len);
+    chunk_cv(&h, cv);
+    cv_bytes(cv, out);
+}
+
+/* root hash from the chaining values of chunks 0 .. n-1, n >= 2 (the stack discipline of orc_b3_update / finalize) */
+void orc_b3_merge_cvs(const uint8_t *cvs, size_t n, uint8_t out[32]) {
+    uint32_t stack[ORC_B3_MAX_DEPTH][8], cv[8];
+    int sp = 0;
+    for (size_t c = 0; c < n; c++) {
+        for (int i = 0; i < 8; i++) {
+            const uint8_t *b = cvs + 32 * c + 4 * i;
+            cv[i] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+        }
+        if (c + 1 == n) break;
+        uint64_t t = c + 1;
+        while ((t & 1) == 0) {
+            sp--;
+            parent_cv(stack[sp], cv, 0, cv);
+            t >>= 1;
+        }
+        memcpy(stack[sp++], cv, 32);
+    }
+    while (sp > 1) {
+        parent_cv(stack[sp - 1], cv, 0, cv);
+        sp--;
+    }
+    parent_cv(stack[0], cv, F_ROOT, cv);
+    cv_bytes(cv, out);
+}

@@ -35,5 +35,8 @@ void orc_b3_update(orc_b3_hasher *h, const void *data, size_t len);
 void orc_b3_finalize(const orc_b3_hasher *h, uint8_t out[ORC_B3_OUT]);
 /* one-shot */
 void orc_blake3(const void *data, size_t len, uint8_t out[ORC_B3_OUT]);
+/* pieces of the tree (row-sharded hashing): non-root chaining value of one chunk; root from n >= 2 chunk values */
+void orc_b3_chunk_cv(const void *data, size_t len, uint64_t chunk_index, uint8_t out[32]);
+void orc_b3_merge_cvs(const uint8_t *cvs, size_t n, uint8_t out[32]);
 
 #endif

@@ -183,3 +183,116 @@ def test_sharded_commit_two_gpus(fused):
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+# ----------------------------------------------------------------------------- row-sharded hashing (lower traffic)
+
+@pytest.mark.parametrize("fid,n_rows,n_per_row,n_cols,split_chunk", [
+    (0, 300, 64, 128, 1),     # 3 chunks: 124 rows | 128 + 48 rows
+    (0, 700, 64, 128, 3),     # 6 chunks, last one partial
+    (0, 512, 2048, 4096, 2),  # the bench's rows per GPU: 4 full chunks + a 32-byte tail chunk
+    (1, 130, 64, 128, 2),     # 16-byte elements
+    (3, 70, 64, 128, 1),      # 32-byte elements: 31 rows in chunk 0
+    (4, 70, 64, 128, 2),      # Ft253_192: big-endian repr
+])
+def test_hash_chunk_range_and_merge_one_gpu(oracle, fid, n_rows, n_per_row, n_cols, split_chunk):
+    """lcpc_dev_hash_chunk_range over two row windows that meet on a chunk boundary + lcpc_dev_hash_merge
+    == hash_columns over the whole matrix (what two ranks of a row-hashed commit compute between them)."""
+    import torch
+
+    import lcpc_proof_of_storage_b200 as P
+    from lcpc_proof_of_storage_b200.sharded import GpuOps
+
+    O = oracle
+    L = O.LIMBS[fid]
+    w = 8 * L
+    enc = P.LigeroEncoding(fid, n_per_row, n_cols)
+    ops = GpuOps(enc)
+    coeffs = O.random_field_elements(fid, 17, n_rows * n_per_row)
+    exp = O.commit(coeffs, O.LigeroEncoding(fid, n_per_row, n_cols))
+    comm = ops.encode(torch.from_numpy(coeffs.view(np.int64).reshape(-1).copy()).cuda(), n_rows)
+    assert np.array_equal(comm.cpu().numpy().view(np.uint64).reshape(n_rows, n_cols, L), exp.comm)
+    n_chunks = O.leaf_chunks(fid, n_rows)
+    row_split = (1024 - 32) // w + (split_chunk - 1) * (1024 // w)
+    lo = comm[:row_split * n_cols * L].clone()   # separate allocations, as on two ranks
+    hi = comm[row_split * n_cols * L:].clone()
+    cv_lo = ops.hash_chunk_range(lo, 0, n_rows, n_cols, 0, split_chunk)
+    cv_hi = ops.hash_chunk_range(hi, row_split, n_rows, n_cols, split_chunk, n_chunks)
+    exp_cvs = O.hash_chunk_cvs(fid, exp.comm[:, :8], 0, n_rows, 0, n_chunks)  # the oracle's values for 8 columns
+    got_cvs = torch.cat([cv_lo, cv_hi]).cpu().numpy().reshape(n_chunks, n_cols, 32)
+    assert np.array_equal(got_cvs[:, :8], exp_cvs)
+    leaves = torch.zeros(n_cols * 32, dtype=torch.uint8, device="cuda")
+    ops.hash_merge(torch.cat([cv_lo, cv_hi]), n_cols, n_chunks, leaves)
+    assert np.array_equal(leaves.cpu().numpy().reshape(n_cols, 32), exp.hashes[:n_cols])
+    with pytest.raises(P.LcpcError):  # the chunk range must start inside the row window
+        ops.hash_chunk_range(hi, row_split, n_rows, n_cols, split_chunk - 1, n_chunks)
+
+
+def _worker_rows(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import lcpc_proof_of_storage_b200 as P
+        from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter
+        from oracle import lcpc_oracle as O
+
+        ok = True
+        for fid, n_rows, n_per_row, n_cols in [(0, 700, 2048, 4096), (3, 70, 512, 1024)]:
+            L = O.LIMBS[fid]
+            n = n_rows * n_per_row - 11
+            coeffs = np.zeros((n_rows * n_per_row, L), dtype=np.uint64)
+            coeffs[:n] = O.random_field_elements(fid, 5, n)
+            ctx = P.Context(rank, stream=torch.cuda.current_stream().cuda_stream)
+            enc = P.LigeroEncoding(fid, n_per_row, n_cols, ctx=ctx)
+            sc = ShardedLigeroCommitter(enc, n_rows, None, hashing="rows")
+            assert sc.hashing == "rows" and not sc.fused
+            r0, cnt = sc.rows[rank]
+            local = torch.from_numpy(coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
+            for _ in range(2):
+                sc.commit(local)
+            hashes = sc.gather_hashes()
+            tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, L)
+            folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda())
+            cols = [0, n_cols - 1, n_cols // 2, n_cols // 2 - 1]
+            opened = sc.open_columns(cols)
+            if rank == 0:
+                exp = O.commit(coeffs[:n], O.LigeroEncoding(fid, n_per_row, n_cols))
+                ok &= sc.root() == exp.get_root()
+                ok &= np.array_equal(hashes.cpu().numpy().reshape(-1, 32), exp.hashes)
+                f = folded.cpu().numpy().view(np.uint64).reshape(2, n_per_row, L)
+                for t in range(2):
+                    ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+                for c, col in zip(cols, opened):
+                    e = O.open_column(exp, c)
+                    ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)
+        if rank == 0:
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_hashed_commit_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_rows, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

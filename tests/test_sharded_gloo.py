@@ -43,6 +43,16 @@ class OracleOps:
         arr = hashes.numpy().reshape(-1, 32)
         hashes[:] = torch.from_numpy(self.O.merkle_tree(arr[:n_leaves].copy()).reshape(-1))
 
+    def hash_chunk_range(self, mat, row_base, n_rows_total, n_cols, chunk0, chunk_end):
+        n_local = mat.numel() // (n_cols * self.L)
+        m = self._np(mat).reshape(n_local, n_cols, self.L)
+        cvs = self.O.hash_chunk_cvs(self.fid, m, row_base, n_rows_total, chunk0, chunk_end)
+        return torch.from_numpy(cvs.reshape(-1).copy())
+
+    def hash_merge(self, cvs, n_cols, n_chunks, out):
+        leaves = self.O.hash_merge(cvs.numpy().reshape(n_chunks, n_cols, 32))
+        out[:n_cols * 32] = torch.from_numpy(leaves.reshape(-1))
+
     def fold(self, mat, n_rows, width, row_stride, tensors, n_tensors):
         m = self._np(mat).reshape(n_rows, row_stride, self.L)[:, :width]
         t = self._np(tensors).reshape(n_tensors, n_rows, self.L)
@@ -62,7 +72,7 @@ class _Enc:
         self.fid, self.n_per_row, self.n_cols = fid, n_per_row, n_cols
 
 
-def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q, brakedown_seed=None):
+def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q, brakedown_seed=None, hashing="columns"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -81,8 +91,10 @@ def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q, brakedown_seed
             oenc = O.SdigEncoding(fid, n_per_row, brakedown_seed)
             n_cols = oenc.n_cols
         enc = _Enc(fid, n_per_row, n_cols)
-        sc = ShardedLigeroCommitter(enc, n_rows, None, ops=OracleOps(O, fid, n_per_row, n_cols, oenc))
-        r0, cnt = row_partition(n_rows, world)[rank]
+        sc = ShardedLigeroCommitter(enc, n_rows, None, ops=OracleOps(O, fid, n_per_row, n_cols, oenc), hashing=hashing)
+        r0, cnt = sc.rows[rank]
+        if hashing == "columns":
+            assert (r0, cnt) == row_partition(n_rows, world)[rank]
         local = coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt]
         sc.commit(torch.from_numpy(np.ascontiguousarray(local).view(np.int64).reshape(-1)))
         hashes = sc.gather_hashes()
@@ -143,6 +155,43 @@ def test_sharded_brakedown_commit_matches_single_process(oracle, world, fid, n_r
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+@pytest.mark.parametrize("world,fid,n_rows,n_per_row,n_cols", [
+    (1, 0, 300, 8, 16),     # one rank: 3 chunks, no exchange
+    (2, 0, 300, 8, 16),     # 124 + 128 + 48 rows: ranks own 1 and 2 chunks
+    (4, 0, 700, 8, 16),     # 6 chunks over 4 ranks
+    (4, 0, 130, 8, 16),     # 2 chunks over 4 ranks: two ranks own nothing
+    (2, 3, 70, 8, 16),      # 32-byte elements: 31 rows in chunk 0, 32 per chunk after
+    (2, 1, 130, 8, 16),     # 16-byte elements
+])
+def test_row_hashed_commit_matches_single_process(oracle, world, fid, n_rows, n_per_row, n_cols):
+    """hashing="rows": chunk-aligned row blocks, chunk chaining values computed where the rows are, only those
+    re-sharded (the lower-traffic exchange).  Root, tree, folds and openings equal the single-process commit."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fid, n_rows, n_per_row, n_cols, q, None, "rows")) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_chunk_row_partition():
+    from lcpc_proof_of_storage_b200.sharded import chunk_row_partition
+
+    rows, chunks = chunk_row_partition(1, 4096, 8)  # the 8-GPU bench shape: 124 + 31 * 128 + 4 rows = 33 chunks
+    assert chunks == [(0, 4), (4, 8), (8, 12), (12, 16), (16, 20), (20, 24), (24, 28), (28, 33)]
+    assert rows == [(0, 508)] + [(508 + 512 * i, 512) for i in range(6)] + [(3580, 516)]
+    rows, chunks = chunk_row_partition(4, 300, 4)   # 32-byte elements: 31 rows, then 32 per chunk
+    assert sum(c for _, c in rows) == 300 and chunks[-1][1] == (32 + 300 * 32 + 1023) // 1024
+    for (r0, cnt), (c0, c1) in zip(rows, chunks):
+        assert r0 == (0 if c0 == 0 else 31 + 32 * (c0 - 1))
+    assert chunk_row_partition(3, 100, 2) is None   # 24-byte elements straddle chunk boundaries
+    assert chunk_row_partition(1, 100, 2) is None   # single-chunk leaf
 
 
 def test_row_partition():
