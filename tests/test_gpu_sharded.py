@@ -206,7 +206,9 @@ def test_hash_chunk_range_and_merge_one_gpu(oracle, fid, n_rows, n_per_row, n_co
     O = oracle
     L = O.LIMBS[fid]
     w = 8 * L
-    enc = P.LigeroEncoding(fid, n_per_row, n_cols)
+    # GpuOps works on torch tensors: the library context must run on torch's current stream (as sharded.py's callers do)
+    ctx = P.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    enc = P.LigeroEncoding(fid, n_per_row, n_cols, ctx=ctx)
     ops = GpuOps(enc)
     coeffs = O.random_field_elements(fid, 17, n_rows * n_per_row)
     exp = O.commit(coeffs, O.LigeroEncoding(fid, n_per_row, n_cols))
