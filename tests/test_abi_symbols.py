@@ -83,3 +83,45 @@ def test_sass_has_no_short_cs2r_consumer():
     assert len(found) > 100  # the parser still recognises the listing
     bad = [f for f in found if f[0] < 7]
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_links_from_a_c_client(tmp_path):
+    """include/lcpc_b200.h is the whole boundary: it must compile as C11 (what cgo / bindgen / a C FFI shim would read)
+    and a C program linked against the library must be able to call it.  Only entry points that need no device are run."""
+    import os
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.dirname(_lib.library_path()) if hasattr(_lib, "library_path") else os.path.join(
+        root, "lcpc_proof_of_storage_b200", "_lib")
+    _lib.load()
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "lcpc_b200.h"
+int main(void) {
+    uint64_t p[4], one[4], root[4];
+    int32_t s = 0, bits = 0;
+    if (lcpc_abi_version() != 1) return 1;
+    if (lcpc_field_limbs(LCPC_FT63) != 1 || lcpc_field_limbs(LCPC_FT253_192) != 4) return 2;
+    if (lcpc_field_constants(LCPC_FT63, p, one, root, &s, &bits) != LCPC_OK) return 3;
+    if (p[0] != 0x46d0760000000001ull || s != 41 || bits != 63) return 4;
+    if (lcpc_field_constants(99, p, one, root, &s, &bits) == LCPC_OK) return 5;
+    if (strlen(lcpc_last_error()) == 0) return 6;
+    lcpc_ctx *ctx = NULL;
+    int32_t rc = lcpc_ctx_create(0, &ctx);   /* LCPC_ERR_CUDA without a device: no CPU fallback */
+    if (rc == LCPC_OK) lcpc_ctx_destroy(ctx);
+    printf("ctx_create rc=%d\n", (int)rc);
+    return 0;
+}
+''')
+    exe = tmp_path / "client"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    str(src), "-o", str(exe), "-L", lib_dir, "-llcpc_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+    assert "ctx_create rc=" in res.stdout
