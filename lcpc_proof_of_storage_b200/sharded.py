@@ -160,10 +160,9 @@ class ShardedLigeroCommitter:
         self.rows = row_partition(n_rows_total, self.world)
         self.hashing, self.chunks = "columns", None
         if hashing == "rows":
-            part = chunk_row_partition(self.L, n_rows_total, self.world) if self.np2 == self.n_cols else None
+            part = chunk_row_partition(self.L, n_rows_total, self.world)
             if part is None:
-                raise ValueError("hashing='rows' needs power-of-two n_cols, elements that divide a 1024-byte chunk and "
-                                 "leaves of at least two chunks")
+                raise ValueError("hashing='rows' needs elements that divide a 1024-byte chunk and leaves of at least two chunks")
             self.rows, self.chunks = part
             self.hashing = "rows"
             self.n_chunks = self.chunks[-1][1]
@@ -268,19 +267,27 @@ class ShardedLigeroCommitter:
         c0, c1 = self.chunks[self.rank]
         cvs = self.ops.hash_chunk_range(comm, self.row0, self.n_rows, self.n_cols, c0, c1)  # [c1 - c0, n_cols, 32]
         if W > 1:
-            send = cvs.view(c1 - c0, W, cb * 32).transpose(0, 1).contiguous()  # one slab per destination column block
-            recv = torch.empty(self.n_chunks * cb * 32, dtype=torch.uint8, device=dev)
-            in_splits = [(c1 - c0) * cb * 32] * W
-            out_splits = [(b - a) * cb * 32 for a, b in self.chunks]
-            dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=self.group)
+            # one slab per destination = my chunks of that rank's REAL columns (the padded leaf range is what is split
+            # into column blocks, so with a non power-of-two n_cols the last blocks are short or empty)
+            width = [max(0, min(self.n_cols, (r + 1) * cb) - r * cb) for r in range(W)]
+            if self.np2 == self.n_cols:  # equal blocks: one strided copy
+                send = cvs.view(c1 - c0, W, cb * 32).transpose(0, 1).contiguous().view(-1)
+            else:
+                cvs3 = cvs.view(c1 - c0, self.n_cols, 32)
+                send = torch.cat([cvs3[:, r * cb:r * cb + width[r]].reshape(-1) for r in range(W)])
+            recv = torch.empty(self.n_chunks * self.cols_local * 32, dtype=torch.uint8, device=dev)
+            in_splits = [(c1 - c0) * width[r] * 32 for r in range(W)]
+            out_splits = [(b - a) * self.cols_local * 32 for a, b in self.chunks]
+            dist.all_to_all_single(recv, send, out_splits, in_splits, group=self.group)
         else:
             recv = cvs
-        # chunk order = rank order, so recv is [n_chunks, cb, 32]: the chaining-value store of my column block
+        # chunk order = rank order, so recv is [n_chunks, cols_local, 32]: the chaining-value store of my column block
         if self.subtree is None or self.subtree.device != dev:
             self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
             self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
             self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
-        self.ops.hash_merge(recv, cb, self.n_chunks, self.subtree)
+        if self.cols_local:  # padding leaves are never written: they stay zero
+            self.ops.hash_merge(recv, self.cols_local, self.n_chunks, self.subtree)
         self._join_subtrees()
 
     def flush(self) -> None:

@@ -180,6 +180,22 @@ def test_row_hashed_commit_matches_single_process(oracle, world, fid, n_rows, n_
     assert q.get(timeout=5) is True
 
 
+@pytest.mark.parametrize("world,fid,n_rows,n_per_row,seed", [(2, 0, 300, 150, 0), (4, 1, 140, 120, 1)])
+def test_row_hashed_brakedown_commit_matches_single_process(oracle, world, fid, n_rows, n_per_row, seed):
+    """hashing="rows" with a non power-of-two n_cols: the chaining values of the real columns are re-sharded over the
+    PADDED leaf range (short / empty last blocks), padding leaves stay zero."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fid, n_rows, n_per_row, 0, q, seed, "rows")) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_chunk_row_partition():
     from lcpc_proof_of_storage_b200.sharded import chunk_row_partition
 
