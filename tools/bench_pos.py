@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gib", type=float, default=4.0)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--hashing", default="columns", choices=["columns", "rows"])
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -43,7 +44,7 @@ def main():
     stream = torch.cuda.current_stream()
     ctx = P.Context(local, stream=stream.cuda_stream)
     enc = P.LigeroEncoding(P.FT63, pre, enc_cols, ctx=ctx)
-    sc = ShardedLigeroCommitter(enc, n_rows, None)
+    sc = ShardedLigeroCommitter(enc, n_rows, None, hashing=args.hashing)
     lo, hi = sc.byte_range(n_bytes)
     g = torch.Generator(device="cuda")
     g.manual_seed(4 + rank)

@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 import lcpc_proof_of_storage_b200 as P
-from lcpc_proof_of_storage_b200.sharded import ShardedCommitter, row_partition
+from lcpc_proof_of_storage_b200.sharded import ShardedCommitter
 
 MOD_TOP = {0: 0x46d07600, 3: 0x663c799b}
 
@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--log-n", dest="logs", type=int, nargs="*", default=[20, 22, 24, 26, 28])
     ap.add_argument("--schemes", nargs="*", default=["ligero63", "brakedown63", "brakedown255"])
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--hashing", default="columns", choices=["columns", "rows"],
+                    help="rows: hash BLAKE3 chunks where the rows are and re-shard chaining values (sharded.py)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -64,8 +66,11 @@ def main():
                 if rank == 0:
                     print(json.dumps({"case": f"{scheme}_2^{log_n}", "n_gpus": world, "skipped": "does not fit"}), flush=True)
                 continue
-            sc = ShardedCommitter(enc, n_rows, None)
-            r0, cnt = row_partition(n_rows, world)[rank]
+            try:
+                sc = ShardedCommitter(enc, n_rows, None, hashing=args.hashing)
+            except ValueError:  # rows mode needs multi-chunk leaves and elements that divide a chunk
+                sc = ShardedCommitter(enc, n_rows, None)
+            r0, cnt = sc.rows[rank]
             coeffs = rand_elems(fid, max(cnt, 1) * npr, 100 + log_n + rank)[:cnt * npr * L]
             n_dt = enc.get_n_degree_tests()
             tensors = [rand_elems(fid, n_rows, 7 + i) for i in range(n_dt + 1)]
