@@ -261,3 +261,37 @@ def test_field_random_is_masked_rejection_of_raw_limbs(oracle, fid):
         if v < p:
             exp.append(v)
     assert got == exp
+
+
+@pytest.mark.parametrize("n", [1025, 2048, 3000, 4128, 5000, 9 * 1024, 33 * 1024 + 5, 40 * 1024])
+def test_blake3_chunk_values_and_parent_tree_vs_blake3_package(oracle, n):
+    """The pieces a row-sharded hash is made of (orc_b3_chunk_cv per 1024-byte chunk, orc_b3_merge_cvs over them)
+    reproduce the `blake3` package's digest of the whole message."""
+    import ctypes as C
+
+    blake3_pkg = pytest.importorskip("blake3")
+    lib = oracle.lib()
+    data = bytes((i * 7 + 3) % 251 for i in range(n))
+    n_chunks = (n + 1023) // 1024
+    cvs = np.zeros((n_chunks, 32), dtype=np.uint8)
+    out = (C.c_uint8 * 32)()
+    for c in range(n_chunks):
+        chunk = data[c * 1024:(c + 1) * 1024]
+        lib.orc_b3_chunk_cv(chunk, C.c_size_t(len(chunk)), C.c_uint64(c), out)
+        cvs[c] = np.frombuffer(bytes(out), dtype=np.uint8)
+    lib.orc_b3_merge_cvs(cvs.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(n_chunks), out)
+    assert bytes(out) == blake3_pkg.blake3(data).digest()
+
+
+@pytest.mark.parametrize("fid,n_rows,n_cols", [(0, 300, 5), (1, 130, 3), (3, 70, 4), (4, 70, 2)])
+def test_row_windows_of_hash_columns(oracle, fid, n_rows, n_cols):
+    """hash_chunk_cvs over two row windows that meet on a chunk boundary + hash_merge == hash_columns (lib.rs:736-775)."""
+    O = oracle
+    comm = O.random_field_elements(fid, 3, n_rows * n_cols).reshape(n_rows, n_cols, -1)
+    n_chunks = O.leaf_chunks(fid, n_rows)
+    w = 8 * O.LIMBS[fid]
+    c_mid = n_chunks // 2
+    r_mid = (1024 - 32) // w + (c_mid - 1) * (1024 // w) if c_mid >= 1 else 0
+    a = O.hash_chunk_cvs(fid, comm[:r_mid], 0, n_rows, 0, c_mid)
+    b = O.hash_chunk_cvs(fid, comm[r_mid:], r_mid, n_rows, c_mid, n_chunks)
+    assert np.array_equal(O.hash_merge(np.concatenate([a, b])), O.hash_columns(fid, comm))
