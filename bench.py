@@ -260,9 +260,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hashing", default="columns", choices=["columns", "rows"],
+    ap.add_argument("--hashing", default="columns", choices=["columns", "rows", "rows-fused"],
                     help="N > 1 only: 'rows' hashes BLAKE3 chunks where the rows are and re-shards 32-byte chaining values "
-                         "instead of the encoded matrix (ShardedLigeroCommitter hashing='rows'; not the default yet)")
+                         "instead of the encoded matrix (ShardedLigeroCommitter hashing='rows'; not the default yet); "
+                         "'rows-fused' lets the hash kernel store them into the owners' stores over NVLink")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,7 +298,7 @@ def main() -> None:
     np2 = N_COLS
     # this rank's rows of the coefficient matrix (seed 2 stream, sliced by row block)
     row0, rows_local = rank * ROWS_PER_GPU, ROWS_PER_GPU
-    if world > 1 and args.hashing == "rows":  # chunk-aligned row blocks: 508 / 512 / ... / 516 rows at 8 GPUs
+    if world > 1 and args.hashing != "columns":  # chunk-aligned row blocks: 508 / 512 / ... / 516 rows at 8 GPUs
         from lcpc_proof_of_storage_b200.sharded import chunk_row_partition
 
         row0, rows_local = chunk_row_partition(1, n_rows_total, world)[0][rank]
@@ -324,7 +325,8 @@ def main() -> None:
     else:
         from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter
 
-        sc = ShardedLigeroCommitter(enc, n_rows_total, dist.group.WORLD, hashing=args.hashing)
+        sc = ShardedLigeroCommitter(enc, n_rows_total, dist.group.WORLD, hashing=args.hashing.split("-")[0],
+                                    fused=True if args.hashing == "rows-fused" else None)
         assert (sc.row0, sc.rows_local) == (row0, rows_local)
 
         def step():
@@ -525,8 +527,10 @@ def main() -> None:
                    "parallelism": "single GPU" if world == 1 else (
                        f"row shards x{world}; " + ("encode kernel stores into peer column blocks over NVLink (symmetric memory); commit k hashed "
                                                     "after commit k+1's encode is issued, all K finished inside the timed region"
-                                                   if sc.fused else ("BLAKE3 chunk chaining values hashed where the rows are, NCCL all-to-all of "
-                                                                     "32 B per chunk and column" if sc.hashing == "rows" else "NCCL all-to-all"))
+                                                   if sc.fused else ("BLAKE3 chunk chaining values hashed where the rows are, "
+                                                                     + ("stored by the hash kernel into the owners' stores over NVLink"
+                                                                        if sc.cv_fused else "NCCL all-to-all of 32 B per chunk and column")
+                                                                     if sc.hashing == "rows" else "NCCL all-to-all"))
                        + "; per-rank Merkle subtrees, roots all-gathered")},
         "algorithmic_GBps": step_gbs,
         "host_binding": numa,

@@ -300,6 +300,14 @@ int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_ma
 int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
                                   size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
                                   uint64_t chunk_end, uint8_t *d_cvs);
+/* lcpc_dev_hash_chunk_range with the exchange fused into the kernel: the chaining value of (chunk, column) is stored
+ * directly into the chaining-value store of the rank that owns the column.  peer_cvs[g] is rank g's store,
+ * [n_chunks_total][n_cols / n_peers][32 B] (this rank's own buffer or a peer-mapped pointer reached over NVLink);
+ * n_cols and n_peers are powers of two, n_peers <= 16.  The caller synchronises the ranks before anyone runs
+ * lcpc_dev_hash_merge on its store. */
+int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
+                                          size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
+                                          uint64_t chunk_end, uint8_t *const *peer_cvs, size_t n_peers);
 /* leaves[j] = BLAKE3 parent tree over d_cvs[(c * n_cols + j) * 32], c in [0, n_chunks), n_chunks >= 2: the second half
  * of hash_columns once every chunk's chaining value is in place. */
 int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves);

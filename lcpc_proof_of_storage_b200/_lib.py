@@ -110,6 +110,8 @@ _SIGNATURES = {
     "lcpc_dev_pack_bytes7": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lcpc_dev_hash_chunk_range": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_size_t, C.c_size_t,
                                               C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "lcpc_dev_hash_chunk_range_scatter": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_size_t, C.c_size_t,
+                                                      C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
     "lcpc_dev_hash_merge": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
 }
 

@@ -776,6 +776,34 @@ int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *
     return LCPC_OK;
 }
 
+int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
+                                          size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
+                                          uint64_t chunk_end, uint8_t *const *peer_cvs, size_t n_peers) {
+    if (!ctx || !d_mat || !peer_cvs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || n_cols == 0 || (n_cols & (n_cols - 1)) || n_cols % n_peers)
+        return fail(LCPC_ERR_DIMS, "n_cols and n_peers must be powers of two, n_peers <= 16");
+    const uint64_t w = 8ull * (uint64_t)limbs_of(field);
+    const uint64_t total = 32 + (uint64_t)n_rows_total * w, n_chunks = (total + 1023) / 1024;
+    if (1024 % w != 0) return fail(LCPC_ERR_DIMS, "elements straddle BLAKE3 chunk boundaries for this field");
+    if (n_chunks < 2) return fail(LCPC_ERR_DIMS, "single-chunk leaf: use lcpc_dev_hash_columns");
+    if (chunk0 > chunk_end || chunk_end > n_chunks) return fail(LCPC_ERR_INVALID_ARG, "chunk range outside the leaf");
+    const uint64_t first_row = chunk0 == 0 ? 0 : (chunk0 * 1024 - 32) / w;
+    if (chunk0 < chunk_end && first_row < row_base) return fail(LCPC_ERR_INVALID_ARG, "chunk range starts before row_base");
+    CvScatter sc{};
+    sc.log_cb = 0;
+    while (((size_t)1 << sc.log_cb) < n_cols / n_peers) sc.log_cb++;
+    for (size_t i = 0; i < n_peers; i++) {
+        if (!peer_cvs[i]) return fail(LCPC_ERR_INVALID_ARG, "null peer pointer");
+        sc.base[i] = reinterpret_cast<uint32_t *>(peer_cvs[i]);
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(hash_chunk_range_scatter(field, d_mat, (int64_t)row_base, n_rows_total, row_stride, n_cols, chunk0, chunk_end, total,
+                                n_chunks, sc, ctx->lc()));
+    return LCPC_OK;
+}
+
 int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves) {
     if (!ctx || !d_cvs || !d_leaves) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_chunks < 2) return fail(LCPC_ERR_DIMS, "a single chaining value is the leaf itself");

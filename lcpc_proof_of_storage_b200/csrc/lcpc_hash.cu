@@ -122,11 +122,10 @@ struct BlockElems {
 // `mat` may be a window of the matrix: its first row is global row `row_base`, rows in [0, n_rows) are
 // valid (the rest of the byte stream reads as zero), and only chunks [chunk0, chunk_end) are computed
 // (streaming commits hash chunks as their rows arrive; row edits re-hash only the chunks they touch).
-template <int FID>
-__global__ void __launch_bounds__(128)
-k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
-              const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks, uint32_t *__restrict__ out,
-              int64_t row_base, uint64_t chunk0, uint64_t chunk_end) {
+template <int FID, class Store>
+__device__ __forceinline__ void hash_chunks_body(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
+                                                 const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks,
+                                                 int64_t row_base, uint64_t chunk0, uint64_t chunk_end, Store store) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_cols) return;
     const size_t col = col_idx ? (size_t)col_idx[j] : j;
@@ -155,10 +154,35 @@ k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride
             b3::compress(cv, m, n_chunks == 1 ? 0 : c, len, flags);
             if constexpr (BlockElems<FID>::WHOLE) cur = nxt;
         }
-        uint4 *o = reinterpret_cast<uint4 *>(out + (c * n_cols + j) * 8);
+        uint4 *o = reinterpret_cast<uint4 *>(store(c, j));
         o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
         o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
     }
+}
+
+template <int FID>
+__global__ void __launch_bounds__(128)
+k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
+              const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks, uint32_t *__restrict__ out,
+              int64_t row_base, uint64_t chunk0, uint64_t chunk_end) {
+    hash_chunks_body<FID>(mat, n_rows, row_stride, n_cols, col_idx, total_bytes, n_chunks, row_base, chunk0, chunk_end,
+                          [=](uint64_t c, size_t j) { return out + (c * n_cols + j) * 8; });
+}
+
+// Row-sharded hashing across GPUs, exchange fused into the hash: the chaining value of (chunk c, column j) is stored
+// straight into the chaining-value store of the rank that owns column j -- local HBM for this rank's own column block,
+// peer HBM over NVLink for the others (32 bytes per chunk and column: 3 % of the encoded matrix for 8-byte elements).
+// Rank g owns columns [g << log_cb, (g + 1) << log_cb); its store is [n_chunks][1 << log_cb][32 B].
+template <int FID>
+__global__ void __launch_bounds__(128)
+k_hash_chunks_scatter(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t total_bytes,
+                      uint64_t n_chunks, int64_t row_base, uint64_t chunk0, uint64_t chunk_end,
+                      const __grid_constant__ CvScatter sc) {
+    hash_chunks_body<FID>(mat, n_rows, row_stride, n_cols, nullptr, total_bytes, n_chunks, row_base, chunk0, chunk_end,
+                          [&](uint64_t c, size_t j) {
+                              const size_t in_block = j & (((size_t)1 << sc.log_cb) - 1);
+                              return sc.base[j >> sc.log_cb] + ((c << sc.log_cb) + in_block) * 8;
+                          });
 }
 
 // One thread per column: BLAKE3 tree over the column's chunk chaining values
@@ -255,6 +279,27 @@ cudaError_t hash_chunk_range(int fid, const uint64_t *d_mat, int64_t row_base, s
     default: return cudaErrorInvalidValue;
     }
 #undef LCPC_HCR
+}
+
+cudaError_t hash_chunk_range_scatter(int fid, const uint64_t *d_mat, int64_t row_base, size_t n_rows_valid, size_t row_stride,
+                                     size_t n_cols, uint64_t chunk0, uint64_t chunk_end, uint64_t total_bytes,
+                                     uint64_t n_chunks_total, const CvScatter &sc, const Launch &lc) {
+    if (n_cols == 0 || chunk_end <= chunk0) return cudaSuccess;
+    const unsigned gx = (unsigned)((n_cols + 127) / 128);
+    const uint64_t todo = chunk_end - chunk0;
+    const unsigned gy = (unsigned)(todo < 65535 ? todo : 65535);
+    lc.begin("k_hash_chunks_scatter");
+#define LCPC_HCS(F) k_hash_chunks_scatter<F><<<dim3(gx, gy), 128, 0, lc.s>>>(d_mat, n_rows_valid, row_stride, n_cols, total_bytes, n_chunks_total, row_base, chunk0, chunk_end, sc)
+    switch (fid) {
+    case FT63: LCPC_HCS(FT63); break;
+    case FT127: LCPC_HCS(FT127); break;
+    case FT255: LCPC_HCS(FT255); break;
+    case FT253_192: LCPC_HCS(FT253_192); break;
+    default: return cudaErrorInvalidValue;  // 24-byte elements straddle chunk boundaries: no row-sharded hashing
+    }
+#undef LCPC_HCS
+    lc.end();
+    return cudaGetLastError();
 }
 
 cudaError_t hash_merge(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves, const Launch &lc) {

@@ -92,6 +92,15 @@ cudaError_t hash_chunk_range(int fid, const uint64_t *d_mat, int64_t row_base, s
                              size_t n_cols, uint64_t chunk0, uint64_t chunk_end, uint64_t total_bytes,
                              uint64_t n_chunks_total, uint8_t *d_cvs, const Launch &lc);
 cudaError_t hash_merge(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves, const Launch &lc);
+// hash_chunk_range with the exchange of a row-sharded commit fused in: every chaining value is stored into the store of
+// the rank that owns its column (base[g] = rank g's [n_chunks_total][1 << log_cb][32 B], local or peer-mapped memory)
+struct CvScatter {
+    uint32_t *base[16];
+    int log_cb;
+};
+cudaError_t hash_chunk_range_scatter(int fid, const uint64_t *d_mat, int64_t row_base, size_t n_rows_valid, size_t row_stride,
+                                     size_t n_cols, uint64_t chunk0, uint64_t chunk_end, uint64_t total_bytes,
+                                     uint64_t n_chunks_total, const CvScatter &sc, const Launch &lc);
 
 // d_out[c * out_col_stride + r] = canonical repr of d_mat[r][c] (proof-of-storage's column-major encoded file)
 cudaError_t emit_colmajor(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t *d_out,

@@ -113,6 +113,14 @@ class GpuOps:
                                                           n_cols, n_cols, chunk0, chunk_end, out.data_ptr()))
         return out
 
+    def hash_chunk_range_scatter(self, mat: torch.Tensor, row_base: int, n_rows_total: int, n_cols: int, chunk0: int,
+                                 chunk_end: int, peer_ptrs) -> None:
+        """Same values, stored by the kernel into the owning ranks' chaining-value stores (peer HBM over NVLink)."""
+        if chunk_end > chunk0:
+            _lib.check(self.lib.lcpc_dev_hash_chunk_range_scatter(self.enc.ctx.handle, self.fid, mat.data_ptr(), row_base,
+                                                                  n_rows_total, n_cols, n_cols, chunk0, chunk_end, peer_ptrs,
+                                                                  len(peer_ptrs)))
+
     def hash_merge(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, out: torch.Tensor) -> None:
         _lib.check(self.lib.lcpc_dev_hash_merge(self.enc.ctx.handle, cvs.data_ptr(), n_cols, n_chunks, out.data_ptr()))
 
@@ -166,10 +174,14 @@ class ShardedLigeroCommitter:
             self.rows, self.chunks = part
             self.hashing = "rows"
             self.n_chunks = self.chunks[-1][1]
+            # fused=True: k_hash_chunks_scatter stores the chaining values straight into the owners' stores (symmetric
+            # memory, below) instead of the NCCL all-to-all.  Opt-in until it has been timed at 4 and 8 GPUs.
+            self._cv_fused = bool(fused)
             fused = False
         elif hashing != "columns":
             raise ValueError("hashing must be 'columns' or 'rows'")
         self.comm_rows: Optional[torch.Tensor] = None   # hashing="rows": [rows_local, n_cols, L], my rows, all columns
+        self._cv_hdl = self._cv_peer_ptrs = self._cv_bufs = None
         self.row0, self.rows_local = self.rows[self.rank]
         self.col0 = self.rank * self.cb
         self.cols_local = max(0, min(self.n_cols, self.col0 + self.cb) - self.col0)  # real columns in my block
@@ -210,9 +222,33 @@ class ShardedLigeroCommitter:
                     raise
                 self._symm = self._hdl = self._peer_ptrs = self._scratch = None
 
+        if self.hashing == "rows" and self._cv_fused:
+            if not (isinstance(self.ops, GpuOps) and self.world > 1 and self.np2 == self.n_cols and self.world <= 16):
+                raise ValueError("fused chaining-value exchange needs the GPU back end, 2..16 ranks and power-of-two n_cols")
+            import ctypes as C
+
+            import torch.distributed._symmetric_memory as symm_mem
+
+            dev = torch.device("cuda", enc.ctx.device)
+            # Two chaining-value stores used alternately ([n_chunks][cb][32 B] each): commit k+2 writes the store commit k
+            # was merged from, and a rank can only issue that write after its barrier of commit k+1, which every rank
+            # reaches after its own merge of commit k (stream order): one barrier per commit is enough.
+            per = self.n_chunks * self.cb * 32
+            self._cv_symm = symm_mem.empty(2 * per, dtype=torch.uint8, device=dev)
+            self._cv_hdl = symm_mem.rendezvous(self._cv_symm, group if group is not None else dist.group.WORLD)
+            self._cv_peer_ptrs = [(C.c_void_p * self.world)(*[int(p) + b * per for p in self._cv_hdl.buffer_ptrs])
+                                  for b in range(2)]
+            self._cv_bufs = [self._cv_symm[b * per:(b + 1) * per] for b in range(2)]
+            self._cv_k = 0
+
     @property
     def fused(self) -> bool:
         return self._hdl is not None
+
+    @property
+    def cv_fused(self) -> bool:
+        """hashing="rows" with the chaining-value exchange done by the hash kernel's own peer stores."""
+        return self._cv_hdl is not None
 
     # ------------------------------------------------------------------ commit
     def commit(self, coeffs_local: torch.Tensor, defer: bool = False) -> None:
@@ -265,6 +301,26 @@ class ShardedLigeroCommitter:
         cb, W = self.cb, self.world
         self.comm_rows = comm
         c0, c1 = self.chunks[self.rank]
+        if self.cv_fused:
+            b = self._cv_k % 2
+            self._cv_k += 1
+            self.ops.hash_chunk_range_scatter(comm, self.row0, self.n_rows, self.n_cols, c0, c1, self._cv_peer_ptrs[b])
+            self._cv_hdl.barrier(channel=b)  # every rank's chaining values for my column block have landed
+            recv = self._cv_bufs[b]
+        else:
+            recv = self._exchange_chunk_values(comm, c0, c1, dev)
+        # chunk order = rank order, so recv is [n_chunks, cols_local, 32]: the chaining-value store of my column block
+        if self.subtree is None or self.subtree.device != dev:
+            self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
+            self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
+            self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
+        if self.cols_local:  # padding leaves are never written: they stay zero
+            self.ops.hash_merge(recv, self.cols_local, self.n_chunks, self.subtree)
+        self._join_subtrees()
+
+    def _exchange_chunk_values(self, comm: torch.Tensor, c0: int, c1: int, dev) -> torch.Tensor:
+        """NCCL form of the exchange: my chunks' chaining values of every column, all-to-all to the column owners."""
+        cb, W = self.cb, self.world
         cvs = self.ops.hash_chunk_range(comm, self.row0, self.n_rows, self.n_cols, c0, c1)  # [c1 - c0, n_cols, 32]
         if W > 1:
             # one slab per destination = my chunks of that rank's REAL columns (the padded leaf range is what is split
@@ -281,14 +337,7 @@ class ShardedLigeroCommitter:
             dist.all_to_all_single(recv, send, out_splits, in_splits, group=self.group)
         else:
             recv = cvs
-        # chunk order = rank order, so recv is [n_chunks, cols_local, 32]: the chaining-value store of my column block
-        if self.subtree is None or self.subtree.device != dev:
-            self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
-            self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
-            self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
-        if self.cols_local:  # padding leaves are never written: they stay zero
-            self.ops.hash_merge(recv, self.cols_local, self.n_chunks, self.subtree)
-        self._join_subtrees()
+        return recv
 
     def flush(self) -> None:
         """Finish the deferred commit, if any (collective: every rank calls it at the same point)."""

@@ -230,7 +230,7 @@ def test_hash_chunk_range_and_merge_one_gpu(oracle, fid, n_rows, n_per_row, n_co
         ops.hash_chunk_range(hi, row_split, n_rows, n_cols, split_chunk - 1, n_chunks)
 
 
-def _worker_rows(rank, world, port, q):
+def _worker_rows(rank, world, port, q, cv_fused=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -252,11 +252,11 @@ def _worker_rows(rank, world, port, q):
             coeffs[:n] = O.random_field_elements(fid, 5, n)
             ctx = P.Context(rank, stream=torch.cuda.current_stream().cuda_stream)
             enc = P.LigeroEncoding(fid, n_per_row, n_cols, ctx=ctx)
-            sc = ShardedLigeroCommitter(enc, n_rows, None, hashing="rows")
-            assert sc.hashing == "rows" and not sc.fused
+            sc = ShardedLigeroCommitter(enc, n_rows, None, hashing="rows", fused=cv_fused)
+            assert sc.hashing == "rows" and not sc.fused and sc.cv_fused == cv_fused
             r0, cnt = sc.rows[rank]
             local = torch.from_numpy(coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
-            for _ in range(2):
+            for _ in range(3):  # repeated commits rotate the chaining-value stores of the fused exchange
                 sc.commit(local)
             hashes = sc.gather_hashes()
             tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, L)
@@ -279,7 +279,10 @@ def _worker_rows(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_row_hashed_commit_two_gpus():
+@pytest.mark.parametrize("cv_fused", [False, True])
+def test_row_hashed_commit_two_gpus(cv_fused):
+    """cv_fused: the hash kernel stores the chaining values into the owners' stores over NVLink (k_hash_chunks_scatter,
+    symmetric memory + one barrier) instead of the NCCL all-to-all."""
     import torch
     import torch.multiprocessing as mp
 
@@ -291,10 +294,43 @@ def test_row_hashed_commit_two_gpus():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_rows, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_rows, args=(r, 2, port, q, cv_fused)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+@pytest.mark.parametrize("fid,n_rows,n_per_row,n_cols,n_peers", [(0, 512, 2048, 4096, 2), (0, 700, 64, 128, 4), (3, 70, 64, 128, 2),
+                                                                 (1, 130, 64, 128, 8)])
+def test_hash_chunk_range_scatter_one_gpu(oracle, fid, n_rows, n_per_row, n_cols, n_peers):
+    """k_hash_chunks_scatter with every "peer" store on the same GPU: store g must hold the chaining values of column
+    block g, [chunk][column in block], exactly as lcpc_dev_hash_chunk_range computes them."""
+    import ctypes as C
+
+    import torch
+
+    import lcpc_proof_of_storage_b200 as P
+    from lcpc_proof_of_storage_b200.sharded import GpuOps
+
+    O = oracle
+    ctx = P.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    enc = P.LigeroEncoding(fid, n_per_row, n_cols, ctx=ctx)
+    ops = GpuOps(enc)
+    coeffs = O.random_field_elements(fid, 23, n_rows * n_per_row)
+    comm = ops.encode(torch.from_numpy(coeffs.view(np.int64).reshape(-1).copy()).cuda(), n_rows)
+    n_chunks = O.leaf_chunks(fid, n_rows)
+    cb = n_cols // n_peers
+    ref = ops.hash_chunk_range(comm, 0, n_rows, n_cols, 0, n_chunks).view(n_chunks, n_cols, 32)
+    stores = [torch.zeros(n_chunks * cb * 32, dtype=torch.uint8, device="cuda") for _ in range(n_peers)]
+    ptrs = (C.c_void_p * n_peers)(*[s.data_ptr() for s in stores])
+    ops.hash_chunk_range_scatter(comm, 0, n_rows, n_cols, 0, n_chunks, ptrs)
+    for g in range(n_peers):
+        assert torch.equal(stores[g].view(n_chunks, cb, 32), ref[:, g * cb:(g + 1) * cb]), g
+    # and the leaves that come out of a store are the commitment's
+    exp = O.commit(coeffs, O.LigeroEncoding(fid, n_per_row, n_cols))
+    leaves = torch.zeros(cb * 32, dtype=torch.uint8, device="cuda")
+    ops.hash_merge(stores[n_peers - 1], cb, n_chunks, leaves)
+    assert np.array_equal(leaves.cpu().numpy().reshape(cb, 32), exp.hashes[(n_peers - 1) * cb:n_peers * cb])
