@@ -391,8 +391,9 @@ def main() -> None:
 
     # ---- end to end through the host-buffer C-ABI call (N = 1 path per rank) ----------------------
     e2e = None
-    h_comm = torch.empty(ROWS_PER_GPU * N_COLS, dtype=torch.int64).pin_memory()
-    h_hashes = torch.empty((2 * np2 - 1) * 32, dtype=torch.uint8).pin_memory()
+    if world == 1:  # host destinations of the full LcCommit (the sharded leg reads back the root only)
+        h_comm = torch.empty(ROWS_PER_GPU * N_COLS, dtype=torch.int64).pin_memory()
+        h_hashes = torch.empty((2 * np2 - 1) * 32, dtype=torch.uint8).pin_memory()
     n_local = rows_local * N_PER_ROW
     e2e_steps = max(1, min(steps, 20))
 
