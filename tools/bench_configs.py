@@ -3,7 +3,7 @@
 B200, device-resident, CUDA-event timed, with per-kernel timings.  Prints one JSON line per case.
 
     python tools/bench_configs.py [case ...]      cases: ligero63_20 ligero63_24 ligero63_28 ligero255_24
-                                                         brakedown63_24 brakedown255_24 pos_1g fold63_24 prove63_24
+                                                         brakedown63_24 brakedown255_24 pos_1g pos253_1g fold63_24 prove63_24
 """
 import json
 import os
@@ -24,7 +24,8 @@ stream = torch.cuda.current_stream()
 ctx = P.Context(0, stream=stream.cuda_stream)
 MOD = {0: 5102708120182849537,
        1: 146823888364060453008360742206866194433,
-       3: 46242760681095663677370860714659204618859642560429202607213929836750194081793}
+       3: 46242760681095663677370860714659204618859642560429202607213929836750194081793,
+       4: 14474011154664524421669271390699307717822958659997404088829842556525106692097}
 
 
 def rand_elems(fid, n, seed=1):
@@ -165,6 +166,34 @@ def main():
             ms, kt = timed(step, 5)
             print(json.dumps({"case": "pos_1GiB_file", "n_rows": n_rows, "ms": round(ms, 3), "file_GBps": n_bytes / ms / 1e6,
                               "kernels_ms": kt}), flush=True)
+
+
+        elif case == "pos253_1g":
+            # the reference's only proof-of-storage bench (benches/commit_to_different_shapes_bench.rs:25-58): a 1 GB random
+            # file committed over Ft253_192 with 2^16 -> 2^17 columns, throughput in bytes.  Groups are kept below the
+            # modulus (byte 24 of every 31-byte group masked to 5 bits; DESIGN.md section 8 explains why).  Wall clock
+            # through the host call, pageable file bytes in, root out (the commitment stays on the device).
+            n_bytes = 1 << 30
+            rng = np.random.default_rng(5)
+            data = rng.integers(0, 256, n_bytes, dtype=np.uint8)
+            data[24::31] &= 0x1F
+            enc = P.LigeroEncoding(4, 1 << 16, 1 << 17, ctx=ctx)
+            buf = data.tobytes()
+            res = []
+            for rep in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                c = P.LcCommit.commit_bytes(buf, enc, download=False)
+                root = c.get_root()
+                res.append(time.perf_counter() - t0)
+                del c
+            ctx.kernel_timing(True)
+            c = P.LcCommit.commit_bytes(buf, enc, download=False)
+            kt = ctx.kernel_timing_report()
+            ctx.kernel_timing(False)
+            print(json.dumps({"case": "pos253_1GB_file", "field": "Ft253_192", "shape": [c.n_rows, 1 << 16, 1 << 17],
+                              "ms_best": round(1e3 * min(res), 2), "file_GBps": n_bytes / min(res) / 1e9, "root": root.hex(),
+                              "kernels_ms": {k: round(v[1], 3) for k, v in kt.items()}}), flush=True)
 
 
 if __name__ == "__main__":
