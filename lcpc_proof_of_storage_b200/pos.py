@@ -16,8 +16,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import check
-from .lcpc2d import (FT63, Context, LcColumn, LcCommit, LigeroEncoding, ProverError, VerifierError, default_context,
-                     log2, next_pow2)
+from .lcpc2d import (FIELD_LIMBS, FT63, FT253_192, Context, LcColumn, LcCommit, LigeroEncoding, ProverError, VerifierError,
+                     default_context, log2, next_pow2)
 
 DATA_BYTE_CAPACITY = 7   # WriteableFt63: CAPACITY / 8 (fields/data_field.rs:20, writable_ft63.rs:30)
 WRITTEN_BYTES_WIDTH = 8  # size_of::<WriteableFt63>() (data_field.rs:22)
@@ -103,6 +103,15 @@ def get_column_indicies_from_random_seed(random_seed: int, number_of_columns_to_
 
 # ---- bytes <-> field elements ---------------------------------------------------------------------
 
+def data_byte_capacity(field: int) -> int:
+    """DataField::DATA_BYTE_CAPACITY (data_field.rs:22-24): bytes of file data one element carries."""
+    if field == FT63:
+        return DATA_BYTE_CAPACITY
+    if field == FT253_192:
+        return 31  # ft253_192.rs:15 `type DataBytes = [u8; 31]`
+    raise ValueError("not a DataField: only WriteableFt63 and Ft253_192 carry file bytes")
+
+
 def convert_byte_vec_to_field_elements_vec(data: bytes) -> np.ndarray:
     """DataField::from_byte_vec for WriteableFt63 (fields/data_field.rs:38-46, writable_ft63.rs:35-40):
     a pure byte shuffle -- the 7-byte little-endian integer IS the stored limb.  The commit path does
@@ -144,19 +153,22 @@ def _resolve_dims(data_len: int, dimensions) -> Tuple[int, int]:
 
 
 def convert_file_data_to_commit(data: Union[bytes, np.ndarray], what_to_extract, dimensions, ctx: Optional[Context] = None,
-                                download: bool = True):
-    """`data` is either the raw file bytes (packed on the device) or an (n, 1) uint64 element array.
+                                download: bool = True, field: int = FT63):
+    """`data` is either the raw file bytes (packed on the device) or an (n, LIMBS) uint64 element array.
     Returns an LcCommit (Commit), an (n, 32) uint8 array (Leaves), a list of LcColumn (ColumnsWithPath)
-    or a list of (n_rows, 1) arrays (ColumnsWithoutPath)."""
+    or a list of (n_rows, LIMBS) arrays (ColumnsWithoutPath).  `field` is the reference's `F: DataField` type parameter:
+    FT63 (WriteableFt63, 7 data bytes per element: the server's PoSField) or FT253_192 (31 data bytes per element: the
+    field of benches/commit_to_different_shapes_bench.rs)."""
+    capacity = data_byte_capacity(field)
     if isinstance(data, (bytes, bytearray, memoryview)):
-        data_len = (len(data) + DATA_BYTE_CAPACITY - 1) // DATA_BYTE_CAPACITY
+        data_len = (len(data) + capacity - 1) // capacity
     else:
-        data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 1)
+        data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, FIELD_LIMBS[field])
         data_len = data.shape[0]
     if data_len == 0:
         raise ValueError("Cannot convert empty file to commit")
     pre, enc_cols = _resolve_dims(data_len, dimensions)
-    enc = LigeroEncoding(FT63, pre, enc_cols, ctx=ctx or default_context())
+    enc = LigeroEncoding(field, pre, enc_cols, ctx=ctx or default_context())
     want_full = isinstance(what_to_extract, Commit)
     if isinstance(data, np.ndarray):
         comm = LcCommit.commit(data, enc, download=download and want_full)

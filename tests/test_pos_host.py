@@ -85,3 +85,16 @@ def test_encoded_file_metadata_json_round_trip(tmp_path):
     assert len(raw["ulid"]) == 26 and set(raw["ulid"]) <= set("0123456789ABCDEFGHJKMNPQRSTVWXYZ")
     with open(path, "rb") as f:
         assert EF.EncodedFileMetadata.read_from_file(f) == m
+
+
+def test_data_byte_capacity_per_data_field():
+    """DataField::DATA_BYTE_CAPACITY: 7 for WriteableFt63 (writable_ft63.rs:30), 31 for Ft253_192 (ft253_192.rs:15);
+    the other fields carry no file bytes."""
+    import pytest
+
+    from lcpc_proof_of_storage_b200 import pos
+    from lcpc_proof_of_storage_b200.lcpc2d import FT63, FT127, FT253_192
+
+    assert pos.data_byte_capacity(FT63) == 7 and pos.data_byte_capacity(FT253_192) == 31
+    with pytest.raises(ValueError):
+        pos.data_byte_capacity(FT127)
