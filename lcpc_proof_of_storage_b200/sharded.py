@@ -430,6 +430,36 @@ class ShardedLigeroCommitter:
         dist.all_gather_into_tensor(allp, part, group=self.group)
         return self.ops.add_partials(allp, self.world, n_t * self.n_per_row)
 
+    def fold_encoded(self, tensors: torch.Tensor) -> torch.Tensor:
+        """The proof-of-storage fold over the ENCODED matrix (verifiable_polynomial_evaluation,
+        proof-of-storage/src/lcpc_online.rs:454-484): out[t][j] = sum_r tensors[t][r] * comm[r][j] for all n_cols columns,
+        [n_tensors, n_cols, L] on every rank.  With column blocks each rank folds its own columns over all rows and the
+        blocks are concatenated; with row blocks (hashing="rows") it is the coefficient fold's scheme: partial sums over
+        the local rows, all-gather, modular sum."""
+        L, W, cb = self.L, self.world, self.cb
+        assert self._pending is None, "a deferred commit is pending: call flush() on every rank first"
+        n_t = tensors.numel() // (self.n_rows * L)
+        t3 = tensors.view(n_t, self.n_rows, L)
+        if self.hashing == "rows":
+            local_t = t3[:, self.row0:self.row0 + self.rows_local].contiguous()
+            part = self.ops.fold(self.comm_rows, self.rows_local, self.n_cols, self.n_cols, local_t, n_t)
+            if W == 1:
+                return part
+            allp = torch.empty(W * part.numel(), dtype=torch.int64, device=part.device)
+            dist.all_gather_into_tensor(allp, part, group=self.group)
+            return self.ops.add_partials(allp, W, n_t * self.n_cols)
+        dev = self.comm_cols.device
+        if W == 1:
+            return self.ops.fold(self.comm_cols, self.n_rows, self.n_cols, self.col_stride, t3.contiguous(), n_t)
+        block = torch.zeros(n_t, cb, L, dtype=torch.int64, device=dev)  # my column block, padded to the block width
+        if self.cols_local:
+            mine = self.ops.fold(self.comm_cols, self.n_rows, self.cols_local, self.col_stride, t3.contiguous(), n_t)
+            block[:, :self.cols_local] = mine.view(n_t, self.cols_local, L)
+        allb = torch.empty(W * block.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allb, block.view(-1), group=self.group)
+        out = allb.view(W, n_t, cb, L).permute(1, 0, 2, 3).reshape(n_t, W * cb, L)[:, :self.n_cols]
+        return out.contiguous().view(-1)
+
     # ------------------------------------------------------------------ open
     def open_columns(self, cols: Sequence[int]) -> Optional[List[LcColumn]]:
         """open_column (lcpc-2d/src/lib.rs:818-855) for each index.  The owner of a column block sends

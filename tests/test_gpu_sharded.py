@@ -75,7 +75,9 @@ def _worker(rank, world, port, fused, q):
         sc.commit(local)
         hashes = sc.gather_hashes()
         tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, 1)
-        folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda())
+        t_dev = torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda()
+        folded = sc.fold(t_dev)
+        folded_enc = sc.fold_encoded(t_dev)  # the proof-of-storage fold over the encoded matrix
         cols = [0, n_cols - 1, 4096, 4095]
         opened = sc.open_columns(cols)
         if rank == 0:
@@ -83,8 +85,10 @@ def _worker(rank, world, port, fused, q):
             ok = sc.root() == exp.get_root()
             ok &= np.array_equal(hashes.cpu().numpy().reshape(-1, 32), exp.hashes)
             f = folded.cpu().numpy().view(np.uint64).reshape(2, n_per_row, 1)
+            fe = folded_enc.cpu().numpy().view(np.uint64).reshape(2, n_cols, 1)
             for t in range(2):
                 ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+                ok &= np.array_equal(fe[t], O.collapse_columns(fid, exp.comm, tensors[t]))
             for c, col in zip(cols, opened):
                 e = O.open_column(exp, c)
                 ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)
@@ -260,7 +264,9 @@ def _worker_rows(rank, world, port, q, cv_fused=False):
                 sc.commit(local)
             hashes = sc.gather_hashes()
             tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, L)
-            folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda())
+            t_dev = torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()).cuda()
+            folded = sc.fold(t_dev)
+            folded_enc = sc.fold_encoded(t_dev)
             cols = [0, n_cols - 1, n_cols // 2, n_cols // 2 - 1]
             opened = sc.open_columns(cols)
             if rank == 0:
@@ -268,8 +274,10 @@ def _worker_rows(rank, world, port, q, cv_fused=False):
                 ok &= sc.root() == exp.get_root()
                 ok &= np.array_equal(hashes.cpu().numpy().reshape(-1, 32), exp.hashes)
                 f = folded.cpu().numpy().view(np.uint64).reshape(2, n_per_row, L)
+                fe = folded_enc.cpu().numpy().view(np.uint64).reshape(2, n_cols, L)
                 for t in range(2):
                     ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+                    ok &= np.array_equal(fe[t], O.collapse_columns(fid, exp.comm, tensors[t]))
                 for c, col in zip(cols, opened):
                     e = O.open_column(exp, c)
                     ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)

@@ -100,6 +100,7 @@ def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q, brakedown_seed
         hashes = sc.gather_hashes()
         tensors = O.random_field_elements(fid, 7, 2 * n_rows).reshape(2, n_rows, L)
         folded = sc.fold(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()))
+        folded_enc = sc.fold_encoded(torch.from_numpy(tensors.view(np.int64).reshape(-1).copy()))
         cols = [0, n_cols - 1, n_cols // 2, 3]
         opened = sc.open_columns(cols)
         if rank == 0:
@@ -107,8 +108,10 @@ def _worker(rank, world, port, fid, n_rows, n_per_row, n_cols, q, brakedown_seed
             ok = sc.root() == exp.get_root()
             ok &= np.array_equal(hashes.numpy().reshape(-1, 32), exp.hashes)
             f = folded.numpy().view(np.uint64).reshape(2, n_per_row, L)
+            fe = folded_enc.numpy().view(np.uint64).reshape(2, n_cols, L)
             for t in range(2):
                 ok &= np.array_equal(f[t], O.collapse_columns(fid, exp.coeffs, tensors[t]))
+                ok &= np.array_equal(fe[t], O.collapse_columns(fid, exp.comm, tensors[t]))  # lcpc_online.rs:454-484
             for c, col in zip(cols, opened):
                 e = O.open_column(exp, c)
                 ok &= np.array_equal(col.col, e.col) and np.array_equal(col.path, e.path)
