@@ -186,6 +186,46 @@ def kernel_algorithmic_bytes(name: str, n_rows: int) -> int:
     }.get(name, 0)
 
 
+# Integer-pipe model of the kernels ("Integer-pipe model"): per SM sub-partition a warp instruction
+# of the IMAD.WIDE class costs 4 issue cycles on the FMA pipe and holds the ALU side for 2; IMAD / IADD3 / LOP3 / SHF / PRMT
+# cost 2 on their pipe.  The table gives the ESSENTIAL instruction counts per unit of work (W = IMAD.WIDE, I = other FMA-
+# pipe integer ops, A = ALU-pipe ops), derived in DESIGN.md from the arithmetic alone -- no addressing, no loop control.
+# unit = one field element through the kernel (NTT) or one BLAKE3 compression (hashing).
+INT_PIPE_MODEL = {
+    # 12 of the 16 butterfly levels: 5.06 Montgomery products (6 W + 3 I + 8 A each) and 12 modular add/sub (1 I + 4 A each)
+    "k_ntt_block": {"unit": "element", "W": 30.4, "I": 27.2, "A": 88.5},
+    "k_ntt_block_scatter": {"unit": "element", "W": 30.4, "I": 27.2, "A": 88.5},
+    # top 4 levels of a rate-1/2 row: 2.0 products per element, 3 add/sub levels
+    "k_ntt_strided": {"unit": "element", "W": 12.0, "I": 9.0, "A": 28.0},
+    # 56 G functions: 6 adds on the FMA pipe, 4 XOR + 2 PRMT + 2 funnel shifts on the ALU pipe each; 8 final XORs;
+    # 8 de-Montgomery reductions (2 W + 1 I + 6 A each)
+    "k_hash_chunks": {"unit": "compression", "W": 16, "I": 360, "A": 504},
+}
+
+
+def int_pipe_floor_ms(name: str, units: float, n_sm: int, sm_mhz: float):
+    """Time the kernel would take if its binding integer pipe never idled: max(4W + 2I, 2W + 2A) issue cycles per warp
+    instruction group, 32 units per warp, 4 sub-partitions per SM."""
+    m = INT_PIPE_MODEL.get(name)
+    if not m or not sm_mhz:
+        return None
+    cycles = max(4 * m["W"] + 2 * m["I"], 2 * m["W"] + 2 * m["A"])
+    return cycles * (units / 32.0) / (4 * n_sm) / (sm_mhz * 1e3)
+
+
+def integer_pipe_report(kernels_ms_per_step: dict, n_sm: int, sm_mhz) -> dict:
+    """{kernel: {floor_ms, measured_ms, frac}} for the kernels the model covers (one launch of each per step)."""
+    units = {"element": ROWS_PER_GPU * N_COLS, "compression": N_COLS * ((32 + ROWS_PER_GPU * 8 + 63) // 64)}
+    out = {}
+    for k, ms in kernels_ms_per_step.items():
+        if k not in INT_PIPE_MODEL or not ms:
+            continue
+        f = int_pipe_floor_ms(k, units[INT_PIPE_MODEL[k]["unit"]], n_sm, sm_mhz)
+        if f:
+            out[k] = {"floor_ms": round(f, 4), "measured_ms": round(ms, 4), "frac": round(f / ms, 3)}
+    return out
+
+
 def run_reference(args, rank: int, world: int) -> None:
     """CPU arm: the oracle's restatement of the reference algorithm, all host threads."""
     if rank != 0:
@@ -484,6 +524,14 @@ def main() -> None:
                     "ms_per_step_with_launch_events": ms_total_timed / steps,
                     "kernels_ms_per_step": {k: v[1] / steps for k, v in kt.items()},
                     "note": "integer-pipe bound (64-bit Montgomery + BLAKE3 ARX on 32-bit IMAD/ALU), see DESIGN.md"}
+        # second roofline: the integer pipes (what actually binds these kernels), from the model above and the live clock
+        try:
+            n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            roofline["integer_pipe"] = integer_pipe_report(roofline["kernels_ms_per_step"], n_sm, sampler.summary()["sm_mhz"])
+            roofline["integer_pipe_note"] = ("floor = essential IMAD.WIDE / IMAD / ALU instruction counts of the arithmetic "
+                                             "(DESIGN.md section 3) at the sampled SM clock; frac = floor / measured")
+        except Exception as e:  # the model is commentary: it must never cost the line
+            roofline["integer_pipe"] = {"error": repr(e)}
     step_gbs = algorithmic_bytes(n_total, n_rows_total) / (ms_per_step * 1e-3) / 1e9
 
     # ---- CPU baseline: oracle on the same input, all host threads; also the parity gate ------------
