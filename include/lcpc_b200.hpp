@@ -1,0 +1,338 @@
+// C++17 host mirror of the reference's interface for the commitment path, over the C ABI of lcpc_b200.h.
+//
+// The reference is Rust (lcpc-2d / lcpc-ligero-pc); this image has no cargo, so the compiled-language client of the
+// boundary is C++: the same names, argument meaning and error behaviour as the Rust items cited per declaration
+// (paths relative to the reference checkout), header-only, nothing but the C ABI underneath.  The Python mirror
+// (lcpc_proof_of_storage_b200/lcpc2d.py) that the parity tests drive has the same shape.
+//
+//     lcpc_b200::Context ctx(0);
+//     auto enc  = lcpc_b200::LigeroEncoding::create(ctx, LCPC_FT63, coeffs.size());       // LigeroEncoding::new(len)
+//     auto comm = lcpc_b200::LcCommit::commit(coeffs, enc);                               // LcCommit::commit
+//     lcpc_b200::Transcript tr("protocol");  tr.append_message("polycommit", comm.get_root());
+//     auto proof = comm.prove(outer, enc, tr);                                            // LcCommit::prove
+//     auto value = proof.verify(comm.get_root(), outer, inner, enc, tr2);                 // LcEvalProof::verify
+//
+// Elements are LIMBS x uint64_t Montgomery limbs, least-significant first (the memory image of the reference's
+// #[derive(PrimeField)] newtypes); a std::vector<uint64_t> of n elements holds n * LIMBS words.
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "lcpc_b200.h"
+
+namespace lcpc_b200 {
+
+using Digest = std::array<uint8_t, LCPC_DIGEST_BYTES>;
+
+// lcpc_2d::ProverError (lcpc-2d/src/lib.rs:113-132) and VerifierError (:139-167): `code` is the lcpc_status,
+// `variant()` the Rust variant name.  Dimension assert!s of the reference (lib.rs:659-661) arrive as LCPC_ERR_DIMS.
+class Error : public std::runtime_error {
+public:
+    Error(int32_t code, const std::string &msg) : std::runtime_error(variant_of(code) + ": " + msg), code(code) {}
+    const int32_t code;
+    std::string variant() const { return variant_of(code); }
+    bool is_verifier_error() const { return code <= LCPC_VERR_NUM_COL_OPENS && code >= LCPC_VERR_ENCODE; }
+    static std::string variant_of(int32_t c) {
+        switch (c) {
+        case LCPC_ERR_TOO_BIG: return "ProverError::TooBig";
+        case LCPC_ERR_ENCODE: return "ProverError::Encode";
+        case LCPC_ERR_COMMIT: return "ProverError::Commit";
+        case LCPC_ERR_COLUMN_NUMBER: return "ProverError::ColumnNumber";
+        case LCPC_ERR_OUTER_TENSOR: return "ProverError::OuterTensor";
+        case LCPC_ERR_DIMS: return "Dims";
+        case LCPC_ERR_INVALID_ARG: return "InvalidArg";
+        case LCPC_ERR_CUDA: return "Cuda";
+        case LCPC_ERR_NOMEM: return "NoMem";
+        case LCPC_VERR_NUM_COL_OPENS: return "VerifierError::NumColOpens";
+        case LCPC_VERR_COLUMN_PATH: return "VerifierError::ColumnPath";
+        case LCPC_VERR_COLUMN_EVAL: return "VerifierError::ColumnEval";
+        case LCPC_VERR_COLUMN_DEGREE: return "VerifierError::ColumnDegree";
+        case LCPC_VERR_OUTER_TENSOR: return "VerifierError::OuterTensor";
+        case LCPC_VERR_INNER_TENSOR: return "VerifierError::InnerTensor";
+        case LCPC_VERR_ENCODING_DIMS: return "VerifierError::EncodingDims";
+        case LCPC_VERR_ENCODE: return "VerifierError::Encode";
+        default: return "lcpc_status(" + std::to_string(c) + ")";
+        }
+    }
+};
+
+inline void check(int32_t status) {
+    if (status != LCPC_OK) throw Error(status, lcpc_last_error());
+}
+
+inline size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+// lcpc-2d/src/lib.rs:857-859
+inline size_t log2(size_t v) {
+    size_t p = next_pow2(v), l = 0;
+    while ((size_t(1) << l) < p) l++;
+    return l;
+}
+// lcpc-2d/src/lib.rs:642-645
+inline size_t n_degree_tests(size_t lambda, size_t len, size_t flog2) {
+    const size_t den = flog2 - log2(len);
+    return (lambda + den - 1) / den;
+}
+
+struct FieldInfo {
+    int32_t id, limbs, num_bits, two_adicity;
+    explicit FieldInfo(int32_t field) : id(field), limbs(lcpc_field_limbs(field)), num_bits(0), two_adicity(0) {
+        if (limbs == 0) throw Error(LCPC_ERR_INVALID_ARG, "unknown field id");
+        check(lcpc_field_constants(field, nullptr, nullptr, nullptr, &two_adicity, &num_bits));
+    }
+    size_t flog2() const { return (size_t)num_bits - 1; }  // FLOG2, lcpc-2d/src/lib.rs:69-72
+};
+
+// one device + stream; there is no CPU fallback: construction throws (Cuda) when no device is present
+class Context {
+public:
+    explicit Context(int32_t device = 0) { check(lcpc_ctx_create(device, &h_)); }
+    Context(int32_t device, void *cuda_stream) { check(lcpc_ctx_create_on_stream(device, cuda_stream, &h_)); }
+    ~Context() { if (h_) lcpc_ctx_destroy(h_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    lcpc_ctx *handle() const { return h_; }
+    void synchronize() const { check(lcpc_ctx_synchronize(h_)); }
+private:
+    lcpc_ctx *h_ = nullptr;
+};
+
+// merlin::Transcript (merlin 2.0), host-side
+class Transcript {
+public:
+    explicit Transcript(const std::string &label) {
+        check(lcpc_transcript_new(reinterpret_cast<const uint8_t *>(label.data()), label.size(), &h_));
+    }
+    Transcript(const Transcript &o) { check(lcpc_transcript_clone(o.h_, &h_)); }
+    Transcript &operator=(const Transcript &) = delete;
+    ~Transcript() { if (h_) lcpc_transcript_free(h_); }
+    void append_message(const std::string &label, const uint8_t *msg, size_t len) {
+        check(lcpc_transcript_append_message(h_, reinterpret_cast<const uint8_t *>(label.data()), label.size(), msg, len));
+    }
+    void append_message(const std::string &label, const Digest &d) { append_message(label, d.data(), d.size()); }
+    void challenge_bytes(const std::string &label, uint8_t *dest, size_t len) {
+        check(lcpc_transcript_challenge_bytes(h_, reinterpret_cast<const uint8_t *>(label.data()), label.size(), dest, len));
+    }
+    lcpc_transcript *handle() const { return h_; }
+private:
+    lcpc_transcript *h_ = nullptr;
+};
+
+// trait LcEncoding (lcpc-2d/src/lib.rs:75-105): encode / get_dims / dims_ok / get_n_col_opens / get_n_degree_tests
+class LcEncoding {
+public:
+    virtual ~LcEncoding() { if (plan_) lcpc_plan_destroy(plan_); }
+    LcEncoding(const LcEncoding &) = delete;
+    LcEncoding &operator=(const LcEncoding &) = delete;
+    LcEncoding(LcEncoding &&o) noexcept : field(o.field), n_per_row(o.n_per_row), n_cols(o.n_cols), plan_(o.plan_) { o.plan_ = nullptr; }
+
+    // encode one or more rows in place: each row n_cols elements, the first n_per_row the message, the rest zero
+    void encode(std::vector<uint64_t> &rows) const {
+        const size_t per = n_cols * (size_t)field.limbs;
+        if (per == 0 || rows.size() % per) throw Error(LCPC_ERR_ENCODE, "row length must be n_cols");
+        check(lcpc_encode_rows(plan_, rows.data(), rows.size() / per));
+    }
+    // (n_rows, n_per_row, n_cols)
+    std::array<size_t, 3> get_dims(size_t len) const {
+        std::array<size_t, 3> d{};
+        check(lcpc_plan_get_dims(plan_, len, &d[0], &d[1], &d[2]));
+        return d;
+    }
+    virtual bool dims_ok(size_t npr, size_t nc) const { return npr == n_per_row && nc == n_cols; }
+    virtual size_t get_n_col_opens() const = 0;
+    virtual size_t get_n_degree_tests() const = 0;
+    lcpc_plan *plan() const { return plan_; }
+
+    const FieldInfo field;
+    const size_t n_per_row, n_cols;
+protected:
+    LcEncoding(int32_t f, size_t npr, size_t nc) : field(f), n_per_row(npr), n_cols(nc) {}
+    lcpc_plan *plan_ = nullptr;
+};
+
+// LigeroEncodingRho<Ft, Rn, Rd> (lcpc-ligero-pc/src/lib.rs:31-186); rho = 1/2 is the crate's LigeroEncoding alias (:189)
+class LigeroEncoding : public LcEncoding {
+public:
+    static constexpr size_t LAMBDA = 128;  // :45
+
+    // new_from_dims (:138-148)
+    LigeroEncoding(const Context &ctx, int32_t field, size_t n_per_row, size_t n_cols, unsigned rho_num = 1, unsigned rho_den = 2,
+                   const uint64_t *root_of_unity_mont = nullptr)
+        : LcEncoding(field, n_per_row, n_cols), rho_num(rho_num), rho_den(rho_den) {
+        if (!dims_ok_static(n_per_row, n_cols)) throw Error(LCPC_ERR_DIMS, "assertion failed: Self::_dims_ok(n_per_row, n_cols)");
+        check(lcpc_plan_ligero(ctx.handle(), field, n_per_row, n_cols, root_of_unity_mont, &plan_));
+    }
+    // new(len) (:121-124)
+    static LigeroEncoding create(const Context &ctx, int32_t field, size_t len, unsigned rho_num = 1, unsigned rho_den = 2) {
+        const auto d = get_dims_for_len(FieldInfo(field), len, rho_num, rho_den);
+        return LigeroEncoding(ctx, field, d[1], d[2], rho_num, rho_den);
+    }
+    // _n_col_opens (:61-64)
+    static size_t n_col_opens(unsigned rho_num, unsigned rho_den) {
+        const double rho = (double)rho_num / (double)rho_den;
+        return (size_t)std::ceil(-(double)LAMBDA / std::log2((1.0 + rho) / 2.0));
+    }
+    // _get_dims (:70-112): the narrower of two candidate widths by proof size
+    static std::array<size_t, 3> get_dims_for_len(const FieldInfo &f, size_t len, unsigned rho_num = 1, unsigned rho_den = 2) {
+        const double rho = (double)rho_num / (double)rho_den;
+        const size_t opens = n_col_opens(rho_num, rho_den);
+        const double lncf = (double)(opens * len);
+        const double ndt = (double)n_degree_tests(LAMBDA, (size_t)std::ceil(std::sqrt(lncf) / rho), f.flog2());
+        const size_t nc1 = next_pow2((size_t)std::ceil(std::sqrt(lncf / ndt) / rho));
+        if (f.two_adicity < 64 && nc1 > (size_t(1) << f.two_adicity)) throw Error(LCPC_ERR_TOO_BIG, "called `Option::unwrap()` on a `None` value");
+        const size_t np1 = nc1 * rho_num / rho_den, nr1 = (len + np1 - 1) / np1, nd1 = n_degree_tests(LAMBDA, nc1, f.flog2());
+        const size_t nc2 = nc1 / 2, np2 = np1 / 2, nr2 = (len + np2 - 1) / np2, nd2 = n_degree_tests(LAMBDA, nc2, f.flog2());
+        const size_t sz1 = opens * nr1 + (1 + nd1) * np1, sz2 = opens * nr2 + (1 + nd2) * np2;
+        return sz1 < sz2 ? std::array<size_t, 3>{nr1, np1, nc1} : std::array<size_t, 3>{nr2, np2, nc2};
+    }
+    static bool dims_ok_static(size_t npr, size_t nc) { return npr < nc && nc > 0 && (nc & (nc - 1)) == 0; }  // :114-118
+    bool dims_ok(size_t npr, size_t nc) const override { return dims_ok_static(npr, nc) && LcEncoding::dims_ok(npr, nc); }
+    size_t get_n_col_opens() const override { return n_col_opens(rho_num, rho_den); }
+    size_t get_n_degree_tests() const override { return n_degree_tests(LAMBDA, n_cols, field.flog2()); }  // :66-68
+
+    const unsigned rho_num, rho_den;
+};
+
+// LcColumn (lcpc-2d/src/lib.rs:426-439): the opened column and its Merkle path, leaf level first
+struct LcColumn {
+    std::vector<uint64_t> col;
+    std::vector<Digest> path;
+};
+
+class LcEvalProof;
+
+// LcCommit (lcpc-2d/src/lib.rs:174-191): comm, coeffs and hashes are the struct's public fields (host copies); the
+// commitment also stays resident on the device, so prove / fold / open never re-upload
+class LcCommit {
+public:
+    // LcCommit::commit (lib.rs:314 -> :651-700)
+    static LcCommit commit(const std::vector<uint64_t> &coeffs, const LcEncoding &enc) {
+        const size_t L = (size_t)enc.field.limbs;
+        if (coeffs.empty() || coeffs.size() % L) throw Error(LCPC_ERR_DIMS, "coefficient vector must hold whole elements");
+        LcCommit c;
+        const auto d = enc.get_dims(coeffs.size() / L);
+        c.n_rows = d[0]; c.n_per_row = d[1]; c.n_cols = d[2]; c.limbs = L;
+        const size_t np2 = next_pow2(c.n_cols);
+        c.coeffs.resize(c.n_rows * c.n_per_row * L);
+        c.comm.resize(c.n_rows * c.n_cols * L);
+        c.hashes.resize(2 * np2 - 1);
+        check(lcpc_commit_host(enc.plan(), coeffs.data(), coeffs.size() / L, c.coeffs.data(), c.comm.data(),
+                               reinterpret_cast<uint8_t *>(c.hashes.data()), &c.h_));
+        return c;
+    }
+    // proof-of-storage: DataField::from_byte_vec + commit (proof-of-storage/src/lcpc_online.rs:81-143)
+    static LcCommit commit_bytes(const std::vector<uint8_t> &file, const LcEncoding &enc) {
+        const size_t L = (size_t)enc.field.limbs, per = enc.field.id == LCPC_FT253_192 ? 31 : 7;
+        if (file.empty()) throw Error(LCPC_ERR_DIMS, "Cannot convert empty file to commit");
+        LcCommit c;
+        const auto d = enc.get_dims((file.size() + per - 1) / per);
+        c.n_rows = d[0]; c.n_per_row = d[1]; c.n_cols = d[2]; c.limbs = L;
+        c.coeffs.resize(c.n_rows * c.n_per_row * L);
+        c.comm.resize(c.n_rows * c.n_cols * L);
+        c.hashes.resize(2 * next_pow2(c.n_cols) - 1);
+        check(lcpc_commit_bytes_host(enc.plan(), file.data(), file.size(), c.coeffs.data(), c.comm.data(),
+                                     reinterpret_cast<uint8_t *>(c.hashes.data()), &c.h_));
+        return c;
+    }
+    ~LcCommit() { if (h_) lcpc_commit_free(h_); }
+    LcCommit(LcCommit &&o) noexcept { *this = std::move(o); }
+    LcCommit &operator=(LcCommit &&o) noexcept {
+        if (this != &o) {
+            if (h_) lcpc_commit_free(h_);
+            comm = std::move(o.comm); coeffs = std::move(o.coeffs); hashes = std::move(o.hashes);
+            n_rows = o.n_rows; n_cols = o.n_cols; n_per_row = o.n_per_row; limbs = o.limbs; h_ = o.h_; o.h_ = nullptr;
+        }
+        return *this;
+    }
+    LcCommit(const LcCommit &) = delete;
+    LcCommit &operator=(const LcCommit &) = delete;
+
+    // get_root (lib.rs:291-296): the last digest of the flat tree
+    Digest get_root() const { return hashes.back(); }
+    // collapse_columns (lib.rs:1126-1154) over the coefficients, or over the encoded matrix (lcpc_online.rs:454-484)
+    std::vector<uint64_t> fold(const std::vector<uint64_t> &tensor, bool encoded = false) const {
+        if (tensor.size() != n_rows * limbs) throw Error(LCPC_ERR_OUTER_TENSOR, "outer tensor length must be n_rows");
+        std::vector<uint64_t> out((encoded ? n_cols : n_per_row) * limbs);
+        check(lcpc_fold_host(h_, encoded ? 1 : 0, tensor.data(), 1, out.data()));
+        return out;
+    }
+    // open_column (lib.rs:818-855)
+    LcColumn open_column(size_t column) const {
+        const uint64_t idx = column;
+        const size_t depth = log2(n_cols);
+        LcColumn c;
+        c.col.resize(n_rows * limbs);
+        c.path.resize(depth);
+        check(lcpc_open_columns_host(h_, &idx, 1, c.col.data(), reinterpret_cast<uint8_t *>(c.path.data())));
+        return c;
+    }
+    // prove (lib.rs:319 -> :1034-1123)
+    inline LcEvalProof prove(const std::vector<uint64_t> &outer_tensor, const LcEncoding &enc, Transcript &tr) const;
+
+    std::vector<uint64_t> comm, coeffs;
+    std::vector<Digest> hashes;
+    size_t n_rows = 0, n_cols = 0, n_per_row = 0, limbs = 0;
+private:
+    LcCommit() = default;
+    lcpc_commit *h_ = nullptr;
+};
+
+// LcEvalProof (lcpc-2d/src/lib.rs:516-529)
+class LcEvalProof {
+public:
+    size_t n_cols = 0, n_rows = 0, limbs = 0;
+    std::vector<uint64_t> p_eval;                       // n_per_row elements
+    std::vector<std::vector<uint64_t>> p_random_vec;    // n_degree_tests x n_per_row elements
+    std::vector<LcColumn> columns;                      // n_col_opens opened columns
+
+    // verify (lib.rs:547 -> :862-982): returns sum_j inner[j] * p_eval[j]; throws the VerifierError variant otherwise
+    std::vector<uint64_t> verify(const Digest &root, const std::vector<uint64_t> &outer_tensor,
+                                 const std::vector<uint64_t> &inner_tensor, const LcEncoding &enc, Transcript &tr) const {
+        const size_t L = (size_t)enc.field.limbs, npr = p_eval.size() / L;
+        std::vector<uint64_t> p_random, cols;
+        std::vector<Digest> paths;
+        for (const auto &v : p_random_vec) p_random.insert(p_random.end(), v.begin(), v.end());
+        const size_t path_len = columns.empty() ? 0 : columns[0].path.size();
+        for (const auto &c : columns) {
+            if (c.col.size() != n_rows * L || c.path.size() != path_len) throw Error(LCPC_VERR_COLUMN_PATH, "ragged proof columns");
+            cols.insert(cols.end(), c.col.begin(), c.col.end());
+            paths.insert(paths.end(), c.path.begin(), c.path.end());
+        }
+        std::vector<uint64_t> result(L);
+        check(lcpc_verify(enc.plan(), root.data(), outer_tensor.data(), outer_tensor.size() / L, inner_tensor.data(),
+                          inner_tensor.size() / L, n_cols, p_eval.data(), npr, p_random.data(), p_random_vec.size(), cols.data(),
+                          n_rows, reinterpret_cast<const uint8_t *>(paths.data()), path_len, columns.size(),
+                          enc.get_n_col_opens(), enc.get_n_degree_tests(), tr.handle(), result.data()));
+        return result;
+    }
+};
+
+inline LcEvalProof LcCommit::prove(const std::vector<uint64_t> &outer_tensor, const LcEncoding &enc, Transcript &tr) const {
+    const size_t L = limbs, n_dt = enc.get_n_degree_tests(), n_open = enc.get_n_col_opens(), depth = log2(n_cols);
+    LcEvalProof p;
+    p.n_cols = n_cols; p.n_rows = n_rows; p.limbs = L;
+    p.p_eval.resize(n_per_row * L);
+    std::vector<uint64_t> p_random(n_dt * n_per_row * L), cols(n_open * n_rows * L);
+    std::vector<Digest> paths(n_open * depth);
+    check(lcpc_prove(h_, outer_tensor.data(), outer_tensor.size() / L, n_dt, n_open, tr.handle(), p.p_eval.data(), p_random.data(),
+                     nullptr, cols.data(), reinterpret_cast<uint8_t *>(paths.data())));
+    for (size_t t = 0; t < n_dt; t++)
+        p.p_random_vec.emplace_back(p_random.begin() + t * n_per_row * L, p_random.begin() + (t + 1) * n_per_row * L);
+    for (size_t i = 0; i < n_open; i++) {
+        LcColumn c;
+        c.col.assign(cols.begin() + i * n_rows * L, cols.begin() + (i + 1) * n_rows * L);
+        c.path.assign(paths.begin() + i * depth, paths.begin() + (i + 1) * depth);
+        p.columns.push_back(std::move(c));
+    }
+    return p;
+}
+
+}  // namespace lcpc_b200
