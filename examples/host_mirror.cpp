@@ -28,6 +28,17 @@ int main() {
     if (n_degree_tests(128, 4096, f63.flog2()) != 3) return fail("n_degree_tests");
     if (lcpc_b200::log2(size_t(5)) != 3 || lcpc_b200::log2(size_t(4096)) != 12) return fail("log2");
 
+    // --- Brakedown: SdigEncodingS::new(2^24, seed) over the 255-bit field: the shapes of SURVEY.md section 8 ---
+    {
+        const FieldInfo f255(LCPC_FT255);
+        if (SdigEncoding::n_col_opens(3) != 6593) return fail("Sdig n_col_opens");
+        const size_t npr = SdigEncoding::n_per_row_for_len(f255, size_t(1) << 24, 3);
+        if (npr != 166292) return fail("Sdig n_per_row for 2^24 over Ft255");
+        const auto mats = SdigEncoding::generate(LCPC_FT63, 150, /*seed=*/0, 3);  // small code, host-side generation
+        if (mats.first.empty() || mats.first.size() != mats.second.size() || mats.first[0].cols != 150) return fail("matgen shapes");
+        if (SdigEncoding::codeword_length(mats.first, mats.second) <= 150) return fail("codeword_length");
+    }
+
     // --- merlin's published test vector (merlin 2.0, `equivalence_simple`) through the C ABI transcript ---
     {
         Transcript tr("test protocol");

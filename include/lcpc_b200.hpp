@@ -201,6 +201,89 @@ public:
     const unsigned rho_num, rho_den;
 };
 
+// sprs::CsMat<F> in CSC storage, owning its arrays (lcpc-brakedown-pc keeps its pre/postcodes this way, matgen.rs:187)
+struct CscMatrix {
+    uint64_t rows = 0, cols = 0;
+    std::vector<uint64_t> indptr, indices, data;  // cols + 1, nnz, nnz * LIMBS
+    lcpc_csc view() const { return lcpc_csc{rows, cols, indptr.data(), indices.data(), data.data()}; }
+};
+
+// SdigEncodingS<Ft, S> (lcpc-brakedown-pc/src/lib.rs:38-176): the Brakedown expander code; matrices come from
+// matgen::generate (matgen.rs:28-53), restated in the library's host code (lcpc_sdig_get_dims / lcpc_sdig_gen_level)
+class SdigEncoding : public LcEncoding {
+public:
+    static constexpr size_t LAMBDA = 128;
+
+    // new_from_dims(n_per_row, n_cols, seed) (lib.rs:126-137); n_cols = 0 skips the codeword-length assertion
+    SdigEncoding(const Context &ctx, int32_t field, size_t n_per_row, size_t n_cols, uint64_t seed, int32_t code = 3)
+        : SdigEncoding(ctx, field, generate(field, n_per_row, seed, code), n_cols, code) {}
+
+    // new(len, seed) (lib.rs:93-100)
+    static SdigEncoding create(const Context &ctx, int32_t field, size_t len, uint64_t seed, int32_t code = 3) {
+        return SdigEncoding(ctx, field, n_per_row_for_len(FieldInfo(field), len, code), 0, seed, code);
+    }
+    // codeword_length (encode.rs:18-33)
+    static size_t codeword_length(const std::vector<CscMatrix> &pre, const std::vector<CscMatrix> &post) {
+        size_t n = pre.front().cols + post.back().cols;
+        for (size_t i = 0; i + 1 < pre.size(); i++) n += pre[i].rows;
+        for (const auto &m : post) n += m.rows;
+        return n;
+    }
+    // matgen::generate::<Ft, SdigCode<code>>(n_per_row, seed): (precodes, postcodes)
+    static std::pair<std::vector<CscMatrix>, std::vector<CscMatrix>> generate(int32_t field, size_t n_per_row, uint64_t seed,
+                                                                              int32_t code = 3) {
+        const size_t L = (size_t)FieldInfo(field).limbs;
+        uint64_t pre_d[3 * 64] = {0}, post_d[3 * 64] = {0};
+        int32_t n_levels = 0;
+        check(lcpc_sdig_get_dims(code, n_per_row, field, pre_d, post_d, 64, &n_levels));
+        std::pair<std::vector<CscMatrix>, std::vector<CscMatrix>> out;
+        for (int32_t lvl = 0; lvl < n_levels; lvl++) {
+            const uint64_t *pd = pre_d + 3 * lvl, *qd = post_d + 3 * lvl;  // (n = columns, m = rows, d = non-zeros per column)
+            CscMatrix a, b;
+            a.cols = pd[0]; a.rows = pd[1]; a.indptr.resize(pd[0] + 1); a.indices.resize(pd[0] * pd[2]); a.data.resize(pd[0] * pd[2] * L);
+            b.cols = qd[0]; b.rows = qd[1]; b.indptr.resize(qd[0] + 1); b.indices.resize(qd[0] * qd[2]); b.data.resize(qd[0] * qd[2] * L);
+            check(lcpc_sdig_gen_level(field, seed, (uint64_t)lvl, pd, qd, a.indptr.data(), a.indices.data(), a.data.data(),
+                                      b.indptr.data(), b.indices.data(), b.data.data()));
+            out.first.push_back(std::move(a));
+            out.second.push_back(std::move(b));
+        }
+        return out;
+    }
+    // _n_col_opens (lib.rs:57-61)
+    static size_t n_col_opens(int32_t code = 3) {
+        return (size_t)std::ceil(-(double)LAMBDA / std::log2(1.0 - lcpc_sdig_dist(code) / 3.0));
+    }
+    // new / _new_from_np1 (lib.rs:69-123): the row width that minimises the proof size
+    static size_t n_per_row_for_len(const FieldInfo &f, size_t len, int32_t code = 3) {
+        const size_t opens = n_col_opens(code);
+        const double lncf = (double)(opens * len);
+        const double ndt = (double)n_degree_tests(LAMBDA, (size_t)std::ceil(std::sqrt(lncf)) * 2, f.flog2());
+        size_t np1 = (size_t)std::ceil(std::sqrt(lncf / ndt));
+        if (np1 > len) np1 = len;
+        const size_t nr1 = (len + np1 - 1) / np1, nd1 = n_degree_tests(LAMBDA, np1 * 2, f.flog2());
+        const size_t np2 = np1 / 2, nr2 = (len + np2 - 1) / np2, nd2 = n_degree_tests(LAMBDA, np2 * 2, f.flog2());
+        const size_t sz1 = opens * nr1 + (1 + nd1) * np1, sz2 = opens * nr2 + (1 + nd2) * np2;
+        return sz1 < sz2 ? np1 : np2;
+    }
+    size_t get_n_col_opens() const override { return n_col_opens(code); }
+    size_t get_n_degree_tests() const override { return n_degree_tests(LAMBDA, n_cols, field.flog2()); }  // lib.rs:64-66
+
+    const int32_t code;
+    const std::vector<CscMatrix> precodes, postcodes;
+private:
+    SdigEncoding(const Context &ctx, int32_t field, std::pair<std::vector<CscMatrix>, std::vector<CscMatrix>> mats, size_t n_cols_expected,
+                 int32_t code)
+        : LcEncoding(field, mats.first.front().cols, codeword_length(mats.first, mats.second)), code(code),
+          precodes(std::move(mats.first)), postcodes(std::move(mats.second)) {
+        if (n_cols_expected && n_cols_expected != n_cols)
+            throw Error(LCPC_ERR_DIMS, "assertion failed: n_cols == codeword_length(&precodes, &postcodes)");
+        std::vector<lcpc_csc> pre, post;
+        for (const auto &m : precodes) pre.push_back(m.view());
+        for (const auto &m : postcodes) post.push_back(m.view());
+        check(lcpc_plan_brakedown(ctx.handle(), field, n_per_row, n_cols, pre.size(), pre.data(), post.data(), &plan_));
+    }
+};
+
 // LcColumn (lcpc-2d/src/lib.rs:426-439): the opened column and its Merkle path, leaf level first
 struct LcColumn {
     std::vector<uint64_t> col;
