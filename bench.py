@@ -181,6 +181,10 @@ def kernel_algorithmic_bytes(name: str, n_rows: int) -> int:
         "k_ntt_block": 2 * enc,                          # in place over the encoded matrix
         "k_ntt_block_scatter": 2 * enc,                  # same pass, stores go to the owning ranks' column blocks
         "k_hash_chunks": enc + ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32,
+        "k_hash_chunks_scatter": enc + ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32,
+        # leaf hashing + chunk-value merge + tree in one launch: reads the encoded matrix, writes the tree
+        "k_hash_tree": enc + (2 * N_COLS - 1) * 32,
+        "k_merge_tree": ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32 + (2 * N_COLS - 1) * 32,
         "k_hash_merge": ((32 + n_rows * 8 + 1023) // 1024) * N_COLS * 32 + N_COLS * 32,
         "k_merkle_levels": 2 * N_COLS * 32,
     }.get(name, 0)
@@ -200,6 +204,9 @@ INT_PIPE_MODEL = {
     # 56 G functions: 6 adds on the FMA pipe, 4 XOR + 2 PRMT + 2 funnel shifts on the ALU pipe each; 8 final XORs;
     # 8 de-Montgomery reductions (2 W + 1 I + 6 A each)
     "k_hash_chunks": {"unit": "compression", "W": 16, "I": 360, "A": 504},
+    "k_hash_chunks_scatter": {"unit": "compression", "W": 16, "I": 360, "A": 504},
+    # + per column 4 parent compressions (5 chunk values) and 1 Merkle node: 5 / 65 more compressions, no reductions
+    "k_hash_tree": {"unit": "compression", "W": 16, "I": 360 * 70 / 65, "A": 504 * 70 / 65},
 }
 
 
@@ -353,9 +360,9 @@ def main() -> None:
 
         def step():
             _lib.check(lib.lcpc_dev_encode(enc.plan, d_coeffs.data_ptr(), ROWS_PER_GPU, d_comm.data_ptr()))
-            _lib.check(lib.lcpc_dev_hash_columns(ctx.handle, FID, d_comm.data_ptr(), ROWS_PER_GPU, N_COLS, N_COLS,
-                                                 d_hashes.data_ptr()))
-            _lib.check(lib.lcpc_dev_merkle_tree(ctx.handle, d_hashes.data_ptr(), np2))
+            # merkleize: leaf hashing, the BLAKE3 parent tree per leaf and the Merkle tree in one launch (k_hash_tree)
+            _lib.check(lib.lcpc_dev_merkleize(ctx.handle, FID, d_comm.data_ptr(), ROWS_PER_GPU, N_COLS, N_COLS,
+                                              d_hashes.data_ptr()))
 
         def root_hex():
             return bytes(d_hashes[-32:].cpu().numpy()).hex()

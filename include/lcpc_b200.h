@@ -109,6 +109,10 @@ int32_t lcpc_ctx_create(int32_t device, lcpc_ctx **out);
 /* Context that enqueues on a caller-owned cudaStream_t (e.g. torch's current stream). */
 int32_t lcpc_ctx_create_on_stream(int32_t device, void *cuda_stream, lcpc_ctx **out);
 int32_t lcpc_ctx_synchronize(lcpc_ctx *ctx);
+/* The cudaStream_t every call on this context enqueues on (borrowed).  A caller that mixes the device-pointer entry
+ * points with its own work on the same buffers must either enqueue that work on this stream or order the two streams
+ * with events: nothing else orders them. */
+int32_t lcpc_ctx_stream(const lcpc_ctx *ctx, void **cuda_stream_out);
 void lcpc_ctx_destroy(lcpc_ctx *ctx);
 
 /* ---- plans = encodings ------------------------------------------------------------ */
@@ -311,6 +315,17 @@ int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const ui
 /* leaves[j] = BLAKE3 parent tree over d_cvs[(c * n_cols + j) * 32], c in [0, n_chunks), n_chunks >= 2: the second half
  * of hash_columns once every chunk's chaining value is in place. */
 int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves);
+/* lcpc_dev_hash_merge and lcpc_dev_merkle_tree in ONE launch: d_hashes is the flat tree [n_leaves | n_leaves/2 | ... | 1]
+ * (n_leaves a power of two >= n_cols); leaves [0, n_cols) come from the chaining values (n_chunks >= 2) or are already in
+ * d_hashes (n_chunks == 1, d_cvs may be NULL), leaves [n_cols, n_leaves) are written as zero (lib.rs:685-695), then
+ * every level above.  The last CTA to finish its tile builds the top levels, so no second launch exists. */
+int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes,
+                                 size_t n_leaves);
+/* merkleize (lib.rs:720-734) of a device matrix in one launch: leaf hashing of columns [0, n_cols) (row stride
+ * `row_stride` elements), the BLAKE3 parent tree per leaf and the Merkle tree over next_power_of_two(n_cols) leaves
+ * into d_hashes ((2*np2-1)*32 bytes). */
+int32_t lcpc_dev_merkleize(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
+                           size_t n_cols, uint8_t *d_hashes);
 /* merkle_tree (lib.rs:777-815) in place over [n_leaves | n_leaves/2 | ... | 1]; n_leaves a power of two. */
 int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves);
 /* collapse_columns on device buffers; d_out has n_tensors*width elements. */

@@ -382,7 +382,13 @@ public:
         const size_t L = (size_t)enc.field.limbs, npr = p_eval.size() / L;
         std::vector<uint64_t> p_random, cols;
         std::vector<Digest> paths;
-        for (const auto &v : p_random_vec) p_random.insert(p_random.end(), v.begin(), v.end());
+        for (const auto &v : p_random_vec) {
+            // flat buffer of n_per_row elements per vector: a vector of another length would misalign it.  The reference
+            // feeds every element of the vector to the transcript (lib.rs:920-922), which changes the challenges and
+            // fails the degree test; same variant here
+            if (v.size() != npr * L) throw Error(LCPC_VERR_COLUMN_DEGREE, "p_random vector of the wrong length");
+            p_random.insert(p_random.end(), v.begin(), v.end());
+        }
         const size_t path_len = columns.empty() ? 0 : columns[0].path.size();
         for (const auto &c : columns) {
             if (c.col.size() != n_rows * L || c.path.size() != path_len) throw Error(LCPC_VERR_COLUMN_PATH, "ragged proof columns");

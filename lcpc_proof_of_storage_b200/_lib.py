@@ -51,6 +51,7 @@ _SIGNATURES = {
     "lcpc_ctx_create": (C.c_int32, [C.c_int32, vpp]),
     "lcpc_ctx_create_on_stream": (C.c_int32, [C.c_int32, C.c_void_p, vpp]),
     "lcpc_ctx_synchronize": (C.c_int32, [C.c_void_p]),
+    "lcpc_ctx_stream": (C.c_int32, [C.c_void_p, vpp]),
     "lcpc_ctx_destroy": (None, [C.c_void_p]),
     "lcpc_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "lcpc_ctx_kernel_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
@@ -102,6 +103,8 @@ _SIGNATURES = {
                                             C.POINTER(C.c_void_p), C.c_size_t]),
     "lcpc_dev_hash_columns": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_merkle_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "lcpc_dev_hash_merge_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "lcpc_dev_merkleize": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_fold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
     "lcpc_dev_add_partials": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),

@@ -82,12 +82,11 @@ int32_t upload_csr(const lcpc_csc &a, int fid, int L, DevCsr &out) {
     return LCPC_OK;
 }
 
-// d_cvs_keep: where the chunk chaining values go when the caller keeps them (a commit handle); a
-// stream-ordered scratch buffer otherwise
-int32_t merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_rows, size_t n_cols, size_t np2,
-                      uint8_t *d_hashes, uint8_t **d_cvs_keep = nullptr) {
-    // padding leaves n_cols..np2 stay all-zero (lib.rs:685-695)
-    if (np2 > n_cols) CU(cudaMemsetAsync(d_hashes + n_cols * 32, 0, (np2 - n_cols) * 32, ctx->stream));
+}  // namespace
+
+// One launch (k_hash_tree) where the grid limits allow, else chunk hashing + merge + tree levels
+int32_t lcpc::abi::merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_rows, size_t row_stride, size_t n_cols,
+                                 size_t np2, uint8_t *d_hashes, uint8_t **d_cvs_keep) {
     DevBuf scratch;
     uint8_t *cvs = nullptr;
     const size_t cv_bytes = hash_scratch_bytes(fid, n_rows, n_cols);
@@ -98,10 +97,20 @@ int32_t merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_r
         CU(scratch.alloc(cv_bytes, ctx->stream));
         cvs = scratch.as<uint8_t>();
     }
-    CU(hash_columns(fid, d_comm, n_rows, n_cols, n_cols, nullptr, d_hashes, cvs, ctx->lc()));
+    if (hash_tree_supported(fid, n_rows, np2)) {
+        unsigned *tk = nullptr;
+        CU(ctx->tickets(hash_tree_tickets(np2), &tk));
+        CU(hash_tree(fid, d_comm, n_rows, row_stride, n_cols, np2, d_hashes, cvs, tk, ctx->lc()));
+        return LCPC_OK;
+    }
+    // padding leaves n_cols..np2 stay all-zero (lib.rs:685-695)
+    if (np2 > n_cols) CU(cudaMemsetAsync(d_hashes + n_cols * 32, 0, (np2 - n_cols) * 32, ctx->stream));
+    CU(hash_columns(fid, d_comm, n_rows, row_stride, n_cols, nullptr, d_hashes, cvs, ctx->lc()));
     CU(merkle_tree(d_hashes, np2, ctx->lc()));
     return LCPC_OK;
 }
+
+namespace {
 
 // Handles are reference counted (ctx <- plan <- commit), so the order in which a caller
 // (e.g. a garbage collector) destroys them does not matter.
@@ -113,6 +122,7 @@ void ctx_unref(lcpc_ctx *ctx) {
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     for (auto e : ctx->events) cudaEventDestroy(e);
+    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     delete ctx->timer;
     delete ctx;
 }
@@ -153,7 +163,7 @@ int32_t commit_finish(lcpc_plan *plan, lcpc_commit *c, uint64_t *coeffs_out, uin
     CU(cudaMallocAsync((void **)&c->d_hashes, (2 * c->np2 - 1) * 32, ctx->stream));
     int32_t rc = encode_dev(plan, c->d_coeffs, c->n_rows, c->d_comm);
     if (rc != LCPC_OK) return rc;
-    rc = merkleize_dev(ctx, plan->fid, c->d_comm, c->n_rows, c->n_cols, c->np2, c->d_hashes, &c->d_cvs);
+    rc = merkleize_dev(ctx, plan->fid, c->d_comm, c->n_rows, c->n_cols, c->n_cols, c->np2, c->d_hashes, &c->d_cvs);
     if (rc != LCPC_OK) return rc;
     if (coeffs_out)
         CU(cudaMemcpyAsync(coeffs_out, c->d_coeffs, c->n_rows * c->n_per_row * wbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -210,7 +220,7 @@ int32_t commit_host_pipelined(lcpc_plan *plan, lcpc_commit *c, const uint64_t *h
         if (coeffs_out)
             CU(cudaMemcpyAsync(coeffs_out + e0 * L, c->d_coeffs + e0 * L, (e1 - e0) * wbytes, cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    int32_t rc = merkleize_dev(ctx, plan->fid, c->d_comm, n_rows, n_cols, c->np2, c->d_hashes, &c->d_cvs);
+    int32_t rc = merkleize_dev(ctx, plan->fid, c->d_comm, n_rows, n_cols, n_cols, c->np2, c->d_hashes, &c->d_cvs);
     if (rc != LCPC_OK) return rc;
     if (hashes_out)
         CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -302,6 +312,12 @@ int32_t lcpc_ctx_synchronize(lcpc_ctx *ctx) {
     if (!ctx) return fail(LCPC_ERR_INVALID_ARG, "null context");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_ctx_stream(const lcpc_ctx *ctx, void **cuda_stream_out) {
+    if (!ctx || !cuda_stream_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    *cuda_stream_out = (void *)ctx->stream;
     return LCPC_OK;
 }
 
@@ -811,6 +827,31 @@ int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, 
     CU(cudaSetDevice(ctx->device));
     CU(hash_merge(d_cvs, n_cols, n_chunks, d_leaves, ctx->lc()));
     return LCPC_OK;
+}
+
+int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes,
+                                 size_t n_leaves) {
+    if (!ctx || !d_hashes || (!d_cvs && n_chunks > 1)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1)) || n_cols > n_leaves) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two >= n_cols");
+    if (n_chunks == 0) return fail(LCPC_ERR_DIMS, "a leaf has at least one chunk");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    unsigned *tk = nullptr;
+    CU(ctx->tickets(1, &tk));
+    CU(merge_tree(d_cvs, n_cols, n_chunks, d_hashes, n_leaves, tk, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_merkleize(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols,
+                           uint8_t *d_hashes) {
+    if (!ctx || !d_mat || !d_hashes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
+    if (n_cols == 0 || n_cols > row_stride) return fail(LCPC_ERR_DIMS, "bad column window");
+    const size_t np2 = next_pow2(n_cols);
+    if (np2 == 0) return fail(LCPC_ERR_TOO_BIG, "n_cols is too large");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    return merkleize_dev(ctx, field, d_mat, n_rows, row_stride, n_cols, np2, d_hashes, nullptr);
 }
 
 int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves) {

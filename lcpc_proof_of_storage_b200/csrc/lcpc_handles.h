@@ -52,6 +52,23 @@ struct lcpc_ctx {
     // both PCIe directions and the kernels overlap
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
+    // zeroed ticket counters of the one-launch hash + tree kernels (they leave them zeroed); grown on demand
+    unsigned *d_tickets = nullptr;
+    size_t n_tickets = 0;
+    cudaError_t tickets(size_t n, unsigned **out) {
+        if (n > n_tickets) {
+            const size_t cap = n < 4096 ? 4096 : n;
+            unsigned *p = nullptr;
+            cudaError_t e = cudaMallocAsync((void **)&p, cap * sizeof(unsigned), stream);
+            if (e != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(p, 0, cap * sizeof(unsigned), stream)) != cudaSuccess) return e;
+            if (d_tickets) cudaFreeAsync(d_tickets, stream);
+            d_tickets = p;
+            n_tickets = cap;
+        }
+        *out = d_tickets;
+        return cudaSuccess;
+    }
     lcpc::Launch lc() { return lcpc::Launch{stream, &launches, timer}; }
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) {
@@ -136,6 +153,11 @@ struct DevBuf {
     template <class T>
     T *as() { return reinterpret_cast<T *>(p); }
 };
+
+// merkleize (lib.rs:720-734) of a device matrix: leaves of columns [0, n_cols) into d_hashes, padding leaves zero, tree
+// above them.  d_cvs_keep: where the chunk chaining values go when the caller keeps them (a commit handle)
+int32_t merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_rows, size_t row_stride, size_t n_cols,
+                      size_t np2, uint8_t *d_hashes, uint8_t **d_cvs_keep = nullptr);
 
 // encode rows already on the device (Ligero reads d_coeffs with stride n_per_row; Brakedown widens first)
 int32_t encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);

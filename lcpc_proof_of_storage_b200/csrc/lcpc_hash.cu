@@ -122,6 +122,35 @@ struct BlockElems {
 // `mat` may be a window of the matrix: its first row is global row `row_base`, rows in [0, n_rows) are
 // valid (the rest of the byte stream reads as zero), and only chunks [chunk0, chunk_end) are computed
 // (streaming commits hash chunks as their rows arrive; row edits re-hash only the chunks they touch).
+// Chaining value of chunk `c` of column `col` (the leaf itself when the whole message is a single chunk).
+template <int FID>
+__device__ __forceinline__ void chunk_cv(uint32_t cv[8], const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride,
+                                         size_t col, uint64_t total_bytes, uint64_t n_chunks, int64_t row_base, uint64_t c) {
+    const uint64_t chunk_bytes = (c + 1 == n_chunks) ? total_bytes - c * b3::CHUNK_BYTES : b3::CHUNK_BYTES;
+    const uint32_t nb = (uint32_t)((chunk_bytes + b3::BLOCK_BYTES - 1) / b3::BLOCK_BYTES);
+    b3::set_iv(cv);
+    BlockElems<FID> cur, nxt;
+    if constexpr (BlockElems<FID>::WHOLE) cur.load(mat, n_rows, row_stride, col, c * 16, row_base);
+    for (uint32_t b = 0; b < nb; b++) {
+        uint32_t m[16];
+        if constexpr (BlockElems<FID>::WHOLE) {
+            if (b + 1 < nb) nxt.load(mat, n_rows, row_stride, col, c * 16 + b + 1, row_base);
+            cur.words(m);
+        } else {
+            load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b, row_base);
+        }
+        uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
+        uint32_t len = b3::BLOCK_BYTES;
+        if (b + 1 == nb) {
+            flags |= b3::CHUNK_END;
+            if (n_chunks == 1) flags |= b3::ROOT;
+            len = (uint32_t)(chunk_bytes - (uint64_t)b * b3::BLOCK_BYTES);
+        }
+        b3::compress(cv, m, n_chunks == 1 ? 0 : c, len, flags);
+        if constexpr (BlockElems<FID>::WHOLE) cur = nxt;
+    }
+}
+
 template <int FID, class Store>
 __device__ __forceinline__ void hash_chunks_body(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
                                                  const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks,
@@ -130,30 +159,8 @@ __device__ __forceinline__ void hash_chunks_body(const uint64_t *__restrict__ ma
     if (j >= n_cols) return;
     const size_t col = col_idx ? (size_t)col_idx[j] : j;
     for (uint64_t c = chunk0 + blockIdx.y; c < chunk_end; c += gridDim.y) {
-        const uint64_t chunk_bytes = (c + 1 == n_chunks) ? total_bytes - c * b3::CHUNK_BYTES : b3::CHUNK_BYTES;
-        const uint32_t nb = (uint32_t)((chunk_bytes + b3::BLOCK_BYTES - 1) / b3::BLOCK_BYTES);
         uint32_t cv[8];
-        b3::set_iv(cv);
-        BlockElems<FID> cur, nxt;
-        if constexpr (BlockElems<FID>::WHOLE) cur.load(mat, n_rows, row_stride, col, c * 16, row_base);
-        for (uint32_t b = 0; b < nb; b++) {
-            uint32_t m[16];
-            if constexpr (BlockElems<FID>::WHOLE) {
-                if (b + 1 < nb) nxt.load(mat, n_rows, row_stride, col, c * 16 + b + 1, row_base);
-                cur.words(m);
-            } else {
-                load_block_words<FID>(m, mat, n_rows, row_stride, col, c * 16 + b, row_base);
-            }
-            uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
-            uint32_t len = b3::BLOCK_BYTES;
-            if (b + 1 == nb) {
-                flags |= b3::CHUNK_END;
-                if (n_chunks == 1) flags |= b3::ROOT;
-                len = (uint32_t)(chunk_bytes - (uint64_t)b * b3::BLOCK_BYTES);
-            }
-            b3::compress(cv, m, n_chunks == 1 ? 0 : c, len, flags);
-            if constexpr (BlockElems<FID>::WHOLE) cur = nxt;
-        }
+        chunk_cv<FID>(cv, mat, n_rows, row_stride, col, total_bytes, n_chunks, row_base, c);
         uint4 *o = reinterpret_cast<uint4 *>(store(c, j));
         o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
         o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
@@ -217,6 +224,176 @@ k_hash_merge(const uint32_t *__restrict__ cvs, size_t n_cols, uint64_t n_chunks,
     uint4 *o = reinterpret_cast<uint4 *>(leaves + j * 8);
     o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// ------------------------------------------------------------------ fused leaf merge + Merkle tree
+
+// BLAKE3 parent tree over the chunk chaining values of column j (n_chunks >= 2), values read through L2 (they may have
+// been written by other CTAs of the same launch)
+__device__ __forceinline__ void merge_column(uint32_t cv[8], const uint32_t *cvs, size_t n_cols, uint64_t n_chunks, size_t j) {
+    uint32_t stack[40][8];
+    int sp = 0;
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const uint4 *in = reinterpret_cast<const uint4 *>(cvs + (c * n_cols + j) * 8);
+        const uint4 a = __ldcg(in), b = __ldcg(in + 1);
+        cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w;
+        cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
+        if (c + 1 == n_chunks) break;
+        uint64_t total = c + 1;
+        while ((total & 1) == 0) {
+            sp--;
+            b3::parent_cv(stack[sp], cv, 0, cv);
+            total >>= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) stack[sp][i] = cv[i];
+        sp++;
+    }
+    while (sp > 0) {
+        sp--;
+        b3::parent_cv(stack[sp], cv, sp == 0 ? b3::ROOT : 0u, cv);
+    }
+}
+
+// first digest of tree level l in the flat array [np2 | np2/2 | ... | 1]
+__device__ __forceinline__ size_t level_offset(size_t np2, int l) { return l == 0 ? 0 : 2 * np2 - (np2 >> (l - 1)); }
+
+// The Merkle levels above one tile of T = blockDim.x adjacent leaves (thread t holds leaf tile*T + t in `leaf`): the
+// leaf level and the log2(T) levels inside the tile are written to the flat tree; then the LAST tile of the launch to
+// get here (ticket counter, left at zero again) computes the levels above the tile roots.  One launch builds the tree.
+template <int T>
+__device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, uint8_t *hashes, size_t np2, unsigned *ticket,
+                                          unsigned n_tiles, uint32_t (*buf)[T][8], unsigned *s_flag) {
+    const unsigned t = threadIdx.x;
+    const size_t tile_n = np2 < (size_t)T ? np2 : (size_t)T;
+    int lt = 0;
+    while (((size_t)1 << lt) < tile_n) lt++;
+    if (t < tile_n) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) buf[0][t][k] = leaf[k];
+        uint4 *g = reinterpret_cast<uint4 *>(hashes + (tile * T + t) * 32);
+        g[0] = make_uint4(leaf[0], leaf[1], leaf[2], leaf[3]);
+        g[1] = make_uint4(leaf[4], leaf[5], leaf[6], leaf[7]);
+    }
+    __syncthreads();
+    int src = 0;
+    for (int l = 1; l <= lt; l++) {
+        const size_t n_out = tile_n >> l;
+        if (t < n_out) {
+            uint32_t o[8];
+            b3::hash_pair(buf[src][2 * t], buf[src][2 * t + 1], o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) buf[src ^ 1][t][k] = o[k];
+            uint4 *g = reinterpret_cast<uint4 *>(hashes + (level_offset(np2, l) + tile * n_out + t) * 32);
+            g[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            g[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        __syncthreads();
+        src ^= 1;
+    }
+    if (n_tiles <= 1) return;
+    // publish this tile's root, then take a ticket: the last tile continues with the top of the tree
+    __threadfence();
+    if (t == 0) {
+        const unsigned old = atomicAdd(ticket, 1u);
+        *s_flag = (old == n_tiles - 1) ? 1u : 0u;
+        if (old == n_tiles - 1) *ticket = 0;  // ready for the next launch on this context (stream-ordered)
+    }
+    __syncthreads();
+    if (*s_flag == 0) return;
+    __threadfence();
+    int depth = 0;
+    while (((size_t)1 << depth) < np2) depth++;
+    for (int l = lt + 1; l <= depth; l++) {
+        const size_t n_out = np2 >> l;
+        const uint4 *in = reinterpret_cast<const uint4 *>(hashes + level_offset(np2, l - 1) * 32);
+        uint4 *out = reinterpret_cast<uint4 *>(hashes + level_offset(np2, l) * 32);
+        for (size_t i = t; i < n_out; i += T) {
+            const uint4 a0 = __ldcg(in + 4 * i), a1 = __ldcg(in + 4 * i + 1), b0 = __ldcg(in + 4 * i + 2), b1 = __ldcg(in + 4 * i + 3);
+            const uint32_t lft[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const uint32_t rgt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t o[8];
+            b3::hash_pair(lft, rgt, o);
+            __stcg(out + 2 * i, make_uint4(o[0], o[1], o[2], o[3]));
+            __stcg(out + 2 * i + 1, make_uint4(o[4], o[5], o[6], o[7]));
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// Everything after the chunk chaining values in ONE launch: per column the BLAKE3 parent tree over its chunk values
+// (-> leaf; with n_chunks == 1 the leaves are already in place), then the whole Merkle tree (merkleize, lib.rs:720-734:
+// leaves n_cols..np2 are all-zero).  grid = np2 / T tiles.
+constexpr int MT_TILE = 256;
+__global__ void __launch_bounds__(MT_TILE)
+k_merge_tree(const uint32_t *cvs, size_t n_cols, uint64_t n_chunks, uint8_t *hashes, size_t np2, unsigned *ticket) {
+    __shared__ uint32_t buf[2][MT_TILE][8];
+    __shared__ unsigned s_flag;
+    const size_t j = (size_t)blockIdx.x * MT_TILE + threadIdx.x;
+    uint32_t leaf[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) leaf[k] = 0;
+    if (j < n_cols) {
+        if (n_chunks > 1) {
+            merge_column(leaf, cvs, n_cols, n_chunks, j);
+        } else {
+            const uint4 *in = reinterpret_cast<const uint4 *>(hashes + j * 32);
+            const uint4 a = __ldcg(in), b = __ldcg(in + 1);
+            leaf[0] = a.x; leaf[1] = a.y; leaf[2] = a.z; leaf[3] = a.w;
+            leaf[4] = b.x; leaf[5] = b.y; leaf[6] = b.z; leaf[7] = b.w;
+        }
+    }
+    tile_tree<MT_TILE>(leaf, blockIdx.x, hashes, np2, ticket, gridDim.x, buf, &s_flag);
+}
+
+// The whole of merkleize (lib.rs:720-734) in ONE launch: grid = (chunks, tiles of 128 columns over the PADDED leaf range).
+// CTA (c, tile) hashes chunk c of its columns; the last of a tile's CTAs to finish (per-tile ticket) merges the chunk
+// values into the tile's leaves and builds the tile's 7 tree levels, and the last tile to finish builds the top of the
+// tree.  Chunks are the fast grid dimension, so tiles complete one after another while later tiles are still hashing:
+// the merge and the lower tree levels hide behind the hashing, and only the top levels remain as a serial tail.
+// tickets: 1 + n_tiles zeroed counters, left zeroed.
+constexpr int HT_TILE = 128;
+template <int FID>
+__global__ void __launch_bounds__(HT_TILE, 8)
+k_hash_tree(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t total_bytes,
+            uint64_t n_chunks, uint32_t *cvs, uint8_t *hashes, size_t np2, unsigned *tickets) {
+    __shared__ uint32_t buf[2][HT_TILE][8];
+    __shared__ unsigned s_flag;
+    const uint64_t c = blockIdx.x;
+    const size_t tile = blockIdx.y;
+    const size_t j = tile * HT_TILE + threadIdx.x;
+    uint32_t leaf[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) leaf[k] = 0;
+    if (tile * HT_TILE >= n_cols) {
+        // a tile of padding leaves only: nothing to hash, chunk 0's CTA builds its (all-zero-leaf) levels
+        if (c != 0) return;
+    } else {
+        if (j < n_cols) chunk_cv<FID>(leaf, mat, n_rows, row_stride, j, total_bytes, n_chunks, 0, c);
+        if (n_chunks > 1) {
+            if (j < n_cols) {
+                uint4 *o = reinterpret_cast<uint4 *>(cvs + (c * n_cols + j) * 8);
+                __stcg(o, make_uint4(leaf[0], leaf[1], leaf[2], leaf[3]));
+                __stcg(o + 1, make_uint4(leaf[4], leaf[5], leaf[6], leaf[7]));
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned old = atomicAdd(&tickets[1 + tile], 1u);
+                s_flag = (old == (unsigned)n_chunks - 1) ? 1u : 0u;
+                if (old == (unsigned)n_chunks - 1) tickets[1 + tile] = 0;
+            }
+            __syncthreads();
+            if (s_flag == 0) return;
+            __threadfence();
+#pragma unroll
+            for (int k = 0; k < 8; k++) leaf[k] = 0;
+            if (j < n_cols) merge_column(leaf, cvs, n_cols, n_chunks, j);
+            __syncthreads();  // s_flag is reused by tile_tree
+        }
+    }
+    tile_tree<HT_TILE>(leaf, tile, hashes, np2, tickets, (unsigned)((np2 + HT_TILE - 1) / HT_TILE), buf, &s_flag);
 }
 
 static uint64_t leaf_bytes(int fid, size_t n_rows) { return 32 + (uint64_t)n_rows * 8 * field_consts(fid).limbs; }
@@ -313,6 +490,48 @@ cudaError_t hash_merge(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, u
                                                                   reinterpret_cast<uint32_t *>(d_leaves));
     lc.end();
     return cudaGetLastError();
+}
+
+// cvs (n_chunks >= 2) or leaves already in d_hashes (n_chunks == 1) -> leaves + the whole tree, one launch
+cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes, size_t np2, unsigned *d_ticket,
+                       const Launch &lc) {
+    if (np2 == 0 || n_cols > np2) return cudaErrorInvalidValue;
+    const unsigned tiles = (unsigned)((np2 + MT_TILE - 1) / MT_TILE);
+    lc.begin("k_merge_tree");
+    k_merge_tree<<<tiles, MT_TILE, 0, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, n_chunks, d_hashes, np2, d_ticket);
+    lc.end();
+    return cudaGetLastError();
+}
+
+size_t hash_tree_tickets(size_t np2) { return 1 + (np2 + HT_TILE - 1) / HT_TILE; }
+
+bool hash_tree_supported(int fid, size_t n_rows, size_t np2) {
+    return leaf_chunks(fid, n_rows) <= 65535 && (np2 + HT_TILE - 1) / HT_TILE <= 65535;
+}
+
+template <int FID>
+static cudaError_t hash_tree_t(const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, size_t np2,
+                               uint8_t *d_hashes, uint8_t *d_cvs, unsigned *d_tickets, const Launch &lc) {
+    const uint64_t total = leaf_bytes(FID, n_rows), nc = leaf_chunks(FID, n_rows);
+    const dim3 grid((unsigned)nc, (unsigned)((np2 + HT_TILE - 1) / HT_TILE));
+    lc.begin("k_hash_tree");
+    k_hash_tree<FID><<<grid, HT_TILE, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, total, nc, reinterpret_cast<uint32_t *>(d_cvs),
+                                               d_hashes, np2, d_tickets);
+    lc.end();
+    return cudaGetLastError();
+}
+
+cudaError_t hash_tree(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, size_t np2,
+                      uint8_t *d_hashes, uint8_t *d_cvs, unsigned *d_tickets, const Launch &lc) {
+    if (n_cols == 0 || np2 == 0 || n_cols > np2 || !hash_tree_supported(fid, n_rows, np2)) return cudaErrorInvalidValue;
+    switch (fid) {
+    case FT63: return hash_tree_t<FT63>(d_mat, n_rows, row_stride, n_cols, np2, d_hashes, d_cvs, d_tickets, lc);
+    case FT127: return hash_tree_t<FT127>(d_mat, n_rows, row_stride, n_cols, np2, d_hashes, d_cvs, d_tickets, lc);
+    case FT191: return hash_tree_t<FT191>(d_mat, n_rows, row_stride, n_cols, np2, d_hashes, d_cvs, d_tickets, lc);
+    case FT255: return hash_tree_t<FT255>(d_mat, n_rows, row_stride, n_cols, np2, d_hashes, d_cvs, d_tickets, lc);
+    case FT253_192: return hash_tree_t<FT253_192>(d_mat, n_rows, row_stride, n_cols, np2, d_hashes, d_cvs, d_tickets, lc);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 uint64_t hash_leaf_bytes(int fid, size_t n_rows) { return leaf_bytes(fid, n_rows); }

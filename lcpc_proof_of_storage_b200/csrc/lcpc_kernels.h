@@ -108,6 +108,17 @@ cudaError_t emit_colmajor(int fid, const uint64_t *d_mat, size_t n_rows, size_t 
 
 cudaError_t merkle_tree(uint8_t *d_hashes, size_t n_leaves, const Launch &lc);
 
+// One-launch tails.  merge_tree: chunk chaining values (n_chunks >= 2; with n_chunks == 1 the leaves are already in
+// d_hashes) -> leaves and the whole tree over the padded leaf range (padding leaves written as zero).  d_ticket: one
+// zeroed counter, left zeroed.  hash_tree: the whole of merkleize (leaf hashing + merge + tree) for columns [0, n_cols)
+// of a matrix; d_cvs needs hash_scratch_bytes(), d_tickets hash_tree_tickets(np2) zeroed counters (left zeroed).
+cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes, size_t np2, unsigned *d_ticket,
+                       const Launch &lc);
+size_t hash_tree_tickets(size_t np2);
+bool hash_tree_supported(int fid, size_t n_rows, size_t np2);
+cudaError_t hash_tree(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, size_t np2,
+                      uint8_t *d_hashes, uint8_t *d_cvs, unsigned *d_tickets, const Launch &lc);
+
 // out[t][j] = sum_r tensors[t][r] * mat[r][j].  d_scratch needs fold_scratch_bytes().
 size_t fold_scratch_bytes(int fid, size_t n_rows, size_t width, size_t n_tensors);
 cudaError_t fold(int fid, const uint64_t *d_mat, size_t n_rows, size_t width, size_t row_stride,

@@ -43,6 +43,26 @@ void expand_tensor(host::Transcript &t, int fid, size_t n_rows, uint64_t *out) {
     for (size_t i = 0; i < n_rows; i++) host::field_random(fid, rng, out + i * L);
 }
 
+// Every element below the modulus?  The kernels assume reduced operands (ff_derive's from_repr rejects anything else,
+// so the reference's verifier never sees such a value): to_canon(x + p) == to_canon(x) would give a non-canonical
+// alias the same leaf hash and transcript bytes as the honest element while the dot products go wrong.
+bool all_reduced(int fid, const uint64_t *v, size_t n) {
+    const FieldConsts fc = field_consts(fid);
+    const int L = fc.limbs;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t *a = v + i * L;
+        bool lt = false;
+        for (int l = L - 1; l >= 0; l--) {
+            if (a[l] != fc.p[l]) {
+                lt = a[l] < fc.p[l];
+                break;
+            }
+        }
+        if (!lt) return false;
+    }
+    return true;
+}
+
 void expand_columns(host::Transcript &t, size_t n_cols, size_t n, uint64_t *out) {
     uint8_t key[32];
     t.challenge_bytes(LABEL_CO, 6, key, 32);
@@ -122,6 +142,7 @@ int32_t lcpc_verify_columns_host(lcpc_ctx *ctx, int32_t field, const uint64_t *c
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     if (paths && (!root || !ok_out)) return fail(LCPC_ERR_INVALID_ARG, "paths given without root / ok_out");
     if (n == 0) return LCPC_OK;
+    if (!all_reduced(field, columns, n * n_rows)) return fail(LCPC_ERR_INVALID_ARG, "column element not below the modulus");
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t wbytes = (size_t)limbs_of(field) * 8;
@@ -266,6 +287,14 @@ int32_t lcpc_verify(lcpc_plan *plan, const uint8_t root[LCPC_DIGEST_BYTES], cons
     if (!(n_per_row < proof_n_cols) || n_per_row != plan->n_per_row || proof_n_cols != plan->n_cols)
         return fail(LCPC_VERR_ENCODING_DIMS, "incorrect encoding dimensions");
     if (n_p_random < n_degree_tests) return fail(LCPC_ERR_INVALID_ARG, "proof holds fewer p_random vectors than degree tests");
+    if (n_degree_tests && !p_random) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    // untrusted limbs: the reference's deserialiser (PrimeField::from_repr) refuses elements that are not below the
+    // modulus, so its verifier never computes on them; here they are refused before any kernel sees them
+    if (!all_reduced(plan->fid, outer_tensor, outer_len) || !all_reduced(plan->fid, inner_tensor, inner_len) ||
+        !all_reduced(plan->fid, p_eval, n_per_row) || !all_reduced(plan->fid, p_random, n_degree_tests * n_per_row))
+        return fail(LCPC_ERR_INVALID_ARG, "field element not below the modulus in the proof or the tensors");
+    if (!all_reduced(plan->fid, columns, n_columns * n_rows))
+        return fail(LCPC_VERR_COLUMN_EVAL, "column eval invalid (element not below the modulus)");
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);

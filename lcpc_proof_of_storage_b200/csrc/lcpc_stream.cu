@@ -286,9 +286,11 @@ int32_t lcpc_stream_finish(lcpc_stream *s, uint8_t *hashes_out, size_t *n_rows_o
         CU(hash_chunk_range(s->fid, s->d_pend[s->cur], (int64_t)s->pend_base, s->rows_total, s->n_cols, s->n_cols,
                             s->chunks_done, nc, total, nc, s->d_cvs, ctx->lc()));
         s->chunks_done = nc;
-        if (s->np2 > s->n_cols) CU(cudaMemsetAsync(s->d_hashes + s->n_cols * 32, 0, (s->np2 - s->n_cols) * 32, ctx->stream));
-        CU(hash_merge(s->d_cvs, s->n_cols, nc, s->d_hashes, ctx->lc()));
-        CU(merkle_tree(s->d_hashes, s->np2, ctx->lc()));
+        // leaf merge + the whole tree in one launch (a single-chunk leaf is its own chaining value: copied into place)
+        if (nc <= 1) CU(hash_merge(s->d_cvs, s->n_cols, nc, s->d_hashes, ctx->lc()));
+        unsigned *tk = nullptr;
+        CU(ctx->tickets(1, &tk));
+        CU(merge_tree(s->d_cvs, s->n_cols, nc, s->d_hashes, s->np2, tk, ctx->lc()));
         s->finished = true;
     }
     if (hashes_out) CU(cudaMemcpyAsync(hashes_out, s->d_hashes, (2 * s->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -303,63 +305,99 @@ void lcpc_stream_free(lcpc_stream *s) { stream_release(s); }
 static int32_t commit_write_rows(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows, bool allow_grow,
                                  uint64_t *comm_rows_out, uint8_t *hashes_out) {
     if (!c || !coeff_rows) return fail(LCPC_ERR_INVALID_ARG, "null argument");
-    if (n_rows == 0 || row0 + n_rows < row0 || row0 > c->n_rows) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
-    if (!allow_grow && row0 + n_rows > c->n_rows) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
-    if (allow_grow && row0 + n_rows < c->n_rows) return fail(LCPC_ERR_DIMS, "an append must reach the end of the commitment");
     lcpc_plan *plan = c->plan;
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g0(c->mu);
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
+    // the range is checked under the commit's lock: a concurrent append may have changed n_rows
+    if (n_rows == 0 || row0 + n_rows < row0 || row0 > c->n_rows) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
+    if (!allow_grow && row0 + n_rows > c->n_rows) return fail(LCPC_ERR_DIMS, "row range outside the commitment");
+    if (allow_grow && row0 + n_rows < c->n_rows) return fail(LCPC_ERR_DIMS, "an append must reach the end of the commitment");
     CU(cudaSetDevice(ctx->device));
     const int L = limbs_of(plan->fid);
     const size_t w = (size_t)L * 8, npr = c->n_per_row, n_cols = c->n_cols;
     const size_t old_rows = c->n_rows, new_rows = std::max(old_rows, row0 + n_rows);
     const uint64_t old_nc = hash_leaf_chunks(plan->fid, old_rows);
     const uint64_t total = hash_leaf_bytes(plan->fid, new_rows), nc = hash_leaf_chunks(plan->fid, new_rows);
-    if (new_rows > old_rows) {
-        // grow the resident matrices (the reference doubles the file's row capacity, encoded_file_writer.rs:429-462)
-        uint64_t *d_coeffs = nullptr, *d_comm = nullptr;
-        CU(cudaMallocAsync((void **)&d_coeffs, new_rows * npr * w, ctx->stream));
-        CU(cudaMallocAsync((void **)&d_comm, new_rows * n_cols * w, ctx->stream));
-        CU(cudaMemcpyAsync(d_coeffs, c->d_coeffs, old_rows * npr * w, cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(d_comm, c->d_comm, old_rows * n_cols * w, cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(cudaFreeAsync(c->d_coeffs, ctx->stream));
-        CU(cudaFreeAsync(c->d_comm, ctx->stream));
-        c->d_coeffs = d_coeffs;
-        c->d_comm = d_comm;
+    // Growth is staged: the grown matrices and chaining-value store are built beside the resident ones and published to
+    // the handle only after encode, hashing and the tree have succeeded, so a failure leaves the commitment as it was.
+    const bool grow = new_rows > old_rows;
+    uint64_t *d_coeffs = c->d_coeffs, *d_comm = c->d_comm;
+    uint8_t *d_cvs = c->d_cvs, *d_hashes = c->d_hashes;
+    const size_t tree_bytes = (2 * c->np2 - 1) * 32;
+    auto drop_staged = [&]() {
+        if (!grow) return;
+        if (d_coeffs && d_coeffs != c->d_coeffs) cudaFreeAsync(d_coeffs, ctx->stream);
+        if (d_comm && d_comm != c->d_comm) cudaFreeAsync(d_comm, ctx->stream);
+        if (d_cvs && d_cvs != c->d_cvs) cudaFreeAsync(d_cvs, ctx->stream);
+        if (d_hashes && d_hashes != c->d_hashes) cudaFreeAsync(d_hashes, ctx->stream);
+    };
+#define CUS(call)                                                  \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) {                                  \
+            drop_staged();                                         \
+            return ::lcpc::abi::cuda_fail(e__, #call);             \
+        }                                                          \
+    } while (0)
+    if (grow) {
+        // (the reference doubles the file's row capacity, encoded_file_writer.rs:429-462)
+        d_coeffs = d_comm = nullptr;
+        d_cvs = d_hashes = nullptr;
+        CUS(cudaMallocAsync((void **)&d_coeffs, new_rows * npr * w, ctx->stream));
+        CUS(cudaMallocAsync((void **)&d_comm, new_rows * n_cols * w, ctx->stream));
+        CUS(cudaMallocAsync((void **)&d_hashes, tree_bytes, ctx->stream));
+        CUS(cudaMemcpyAsync(d_coeffs, c->d_coeffs, old_rows * npr * w, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUS(cudaMemcpyAsync(d_comm, c->d_comm, old_rows * n_cols * w, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUS(cudaMemcpyAsync(d_hashes, c->d_hashes, tree_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         if (nc > 1) {
-            uint8_t *d_cvs = nullptr;
-            CU(cudaMallocAsync((void **)&d_cvs, (size_t)nc * n_cols * 32, ctx->stream));
-            if (c->d_cvs && old_nc > 1) CU(cudaMemcpyAsync(d_cvs, c->d_cvs, (size_t)old_nc * n_cols * 32, cudaMemcpyDeviceToDevice, ctx->stream));
-            if (c->d_cvs) CU(cudaFreeAsync(c->d_cvs, ctx->stream));
-            c->d_cvs = d_cvs;
+            CUS(cudaMallocAsync((void **)&d_cvs, (size_t)nc * n_cols * 32, ctx->stream));
+            if (c->d_cvs && old_nc > 1)
+                CUS(cudaMemcpyAsync(d_cvs, c->d_cvs, (size_t)old_nc * n_cols * 32, cudaMemcpyDeviceToDevice, ctx->stream));
         }
-        c->n_rows = new_rows;
     }
-    uint64_t *d_rows = c->d_coeffs + row0 * npr * L;
-    uint64_t *d_enc = c->d_comm + row0 * n_cols * L;
-    CU(cudaMemcpyAsync(d_rows, coeff_rows, n_rows * npr * w, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t *d_rows = d_coeffs + row0 * npr * L;
+    uint64_t *d_enc = d_comm + row0 * n_cols * L;
+    CUS(cudaMemcpyAsync(d_rows, coeff_rows, n_rows * npr * w, cudaMemcpyHostToDevice, ctx->stream));
     int32_t rc = encode_dev(plan, d_rows, n_rows, d_enc);
-    if (rc != LCPC_OK) return rc;
-    if (nc <= 1 || !c->d_cvs) {
+    if (rc != LCPC_OK) {
+        drop_staged();
+        return rc;
+    }
+    // an in-place edit that fails from here on leaves rows and tree out of step; re-hashing everything from the resident
+    // matrix (a second update of the same rows) repairs it -- only growth can be made atomic without a full copy
+    unsigned *tk = nullptr;
+    CUS(ctx->tickets(1, &tk));
+    if (nc <= 1 || !d_cvs) {
         DevBuf scratch;
-        CU(scratch.alloc(hash_scratch_bytes(plan->fid, c->n_rows, n_cols), ctx->stream));
-        CU(hash_columns(plan->fid, c->d_comm, c->n_rows, n_cols, n_cols, nullptr, c->d_hashes, scratch.as<uint8_t>(), ctx->lc()));
+        CUS(scratch.alloc(hash_scratch_bytes(plan->fid, new_rows, n_cols), ctx->stream));
+        CUS(hash_columns(plan->fid, d_comm, new_rows, n_cols, n_cols, nullptr, d_hashes, scratch.as<uint8_t>(), ctx->lc()));
+        CUS(merge_tree(nullptr, n_cols, 1, d_hashes, c->np2, tk, ctx->lc()));
     } else {
         // chunks that contain the written rows; when the leaf grew, also its former last chunk (it was hashed as a final,
         // possibly partial, possibly ROOT-flagged chunk)
         uint64_t c_lo = (32 + (uint64_t)row0 * w) / 1024;
-        if (new_rows > old_rows) c_lo = std::min<uint64_t>(c_lo, old_nc - 1);
+        if (grow) c_lo = std::min<uint64_t>(c_lo, old_nc - 1);
         const uint64_t c_hi = (32 + (uint64_t)(row0 + n_rows) * w - 1) / 1024 + 1;
-        CU(hash_chunk_range(plan->fid, c->d_comm, 0, c->n_rows, n_cols, n_cols, c_lo, std::min(c_hi, nc), total, nc, c->d_cvs,
-                            ctx->lc()));
-        CU(hash_merge(c->d_cvs, n_cols, nc, c->d_hashes, ctx->lc()));
+        CUS(hash_chunk_range(plan->fid, d_comm, 0, new_rows, n_cols, n_cols, c_lo, std::min(c_hi, nc), total, nc, d_cvs, ctx->lc()));
+        CUS(merge_tree(d_cvs, n_cols, nc, d_hashes, c->np2, tk, ctx->lc()));
     }
-    CU(merkle_tree(c->d_hashes, c->np2, ctx->lc()));
-    if (comm_rows_out) CU(cudaMemcpyAsync(comm_rows_out, d_enc, n_rows * n_cols * w, cudaMemcpyDeviceToHost, ctx->stream));
-    if (hashes_out) CU(cudaMemcpyAsync(hashes_out, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (comm_rows_out) CUS(cudaMemcpyAsync(comm_rows_out, d_enc, n_rows * n_cols * w, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hashes_out) CUS(cudaMemcpyAsync(hashes_out, d_hashes, tree_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUS(cudaStreamSynchronize(ctx->stream));
+#undef CUS
+    if (grow) {  // publish
+        cudaFreeAsync(c->d_coeffs, ctx->stream);
+        cudaFreeAsync(c->d_comm, ctx->stream);
+        cudaFreeAsync(c->d_hashes, ctx->stream);
+        if (c->d_cvs) cudaFreeAsync(c->d_cvs, ctx->stream);
+        c->d_coeffs = d_coeffs;
+        c->d_comm = d_comm;
+        c->d_hashes = d_hashes;
+        c->d_cvs = d_cvs;
+        c->n_rows = new_rows;
+    }
     return LCPC_OK;
 }
 

@@ -99,6 +99,13 @@ class Context:
     def synchronize(self) -> None:
         check(_lib.load().lcpc_ctx_synchronize(self._h))
 
+    @property
+    def stream(self) -> int:
+        """The cudaStream_t (as an integer) every call on this context enqueues on."""
+        out = C.c_void_p()
+        check(_lib.load().lcpc_ctx_stream(self._h, C.byref(out)))
+        return int(out.value or 0)
+
     def launch_count(self) -> int:
         return int(_lib.load().lcpc_ctx_launch_count(self._h))
 
@@ -670,6 +677,12 @@ def verify(root: bytes, outer_tensor: np.ndarray, inner_tensor: np.ndarray, proo
     paths = np.ascontiguousarray(np.stack([c.path for c in proof.columns])) if n_columns else np.empty((0, 0, 32), np.uint8)
     p_eval = _elems(proof.p_eval, L)
     n_pr = len(proof.p_random_vec)
+    # the C ABI takes the p_random vectors flat, n_per_row elements each.  The reference copies each vector into a
+    # zero row of n_cols (lib.rs:913-916) and feeds ALL its elements to the transcript, so a vector of another length
+    # changes the challenges and fails the degree test; report it as that instead of reading a misaligned buffer
+    for v in proof.p_random_vec:
+        if _elems(v, L).shape[0] != p_eval.shape[0]:
+            raise VerifierError("ColumnDegree", "column degree check failed")
     p_random = (np.ascontiguousarray(np.stack([_elems(v, L) for v in proof.p_random_vec]))
                 if n_pr else np.empty((0, p_eval.shape[0], L), np.uint64))
     rootb = np.frombuffer(root, dtype=np.uint8).copy()

@@ -192,10 +192,19 @@ def server_retreive_columns(comm: LcCommit, requested_columns: Sequence[int]) ->
 
 # ---- client-side verification (lcpc_online.rs:251-452) -------------------------------------------------
 
-def _verify_columns(ctx: Context, columns: Sequence[LcColumn], col_idx: Optional[Sequence[int]], root: Optional[bytes]):
-    n = len(columns)
-    n_rows = columns[0].col.shape[0]
-    cols = np.ascontiguousarray(np.stack([np.ascontiguousarray(c.col, dtype=np.uint64).reshape(n_rows, 1) for c in columns]))
+def _verify_columns(ctx: Context, columns: Sequence[LcColumn], col_idx: Optional[Sequence[int]], root: Optional[bytes],
+                    field: int = FT63):
+    from .lcpc2d import FIELD_LIMBS
+
+    n, L = len(columns), FIELD_LIMBS[field]
+    flat = [np.ascontiguousarray(c.col, dtype=np.uint64).reshape(-1) for c in columns]
+    n_rows = flat[0].shape[0] // L
+    # ragged columns / paths cannot be passed flat: the reference fails the affected column (lib.rs:985-1030)
+    if any(f.shape[0] != n_rows * L for f in flat) or flat[0].shape[0] % L:
+        raise VerifierError("ColumnEval", "column eval invalid")
+    if root is not None and any(np.asarray(c.path).shape != np.asarray(columns[0].path).shape for c in columns):
+        raise VerifierError("ColumnPath", "column path invalid")
+    cols = np.ascontiguousarray(np.stack([f.reshape(n_rows, L) for f in flat]))
     leaves = np.empty((n, 32), dtype=np.uint8)
     ok = np.zeros(n, dtype=np.uint32)
     paths = idx = rootb = None
@@ -206,25 +215,26 @@ def _verify_columns(ctx: Context, columns: Sequence[LcColumn], col_idx: Optional
         idx = np.ascontiguousarray(np.asarray(col_idx, dtype=np.uint64))
         rootb = np.frombuffer(root, dtype=np.uint8).copy()
     p = lambda a: None if a is None else a.ctypes.data
-    check(_lib.load().lcpc_verify_columns_host(ctx.handle, FT63, p(cols), n_rows, p(paths), path_len, p(idx), n, p(rootb),
+    check(_lib.load().lcpc_verify_columns_host(ctx.handle, field, p(cols), n_rows, p(paths), path_len, p(idx), n, p(rootb),
                                                p(leaves), p(ok)))
     return leaves, ok
 
 
-def hash_column_to_digest(column: LcColumn, ctx: Optional[Context] = None) -> bytes:
+def hash_column_to_digest(column: LcColumn, ctx: Optional[Context] = None, field: int = FT63) -> bytes:
     """lcpc_online.rs:431-452."""
-    leaves, _ = _verify_columns(ctx or default_context(), [column], None, None)
+    leaves, _ = _verify_columns(ctx or default_context(), [column], None, None, field)
     return leaves[0].tobytes()
 
 
 def client_online_verify_column_paths(commitment_root: bytes, requested_columns: Sequence[int],
-                                      received_columns: Sequence[LcColumn], ctx: Optional[Context] = None) -> None:
+                                      received_columns: Sequence[LcColumn], ctx: Optional[Context] = None,
+                                      field: int = FT63) -> None:
     """lcpc_online.rs:251-281: every received column must hash up its path to the root."""
     if len(received_columns) != len(requested_columns):
         raise VerifierError("ColumnEval")
     if not received_columns:
         return
-    _, ok = _verify_columns(ctx or default_context(), received_columns, requested_columns, commitment_root)
+    _, ok = _verify_columns(ctx or default_context(), received_columns, requested_columns, commitment_root, field)
     if not ok.all():
         raise VerifierError("ColumnEval")
 
@@ -240,7 +250,8 @@ def client_online_verify_column_leaves(locally_derived_column_leaves: np.ndarray
 
 def client_verify_commitment(commitment_root: bytes, locally_derived_column_leaves: np.ndarray,
                              requested_columns: Sequence[int], received_columns: Sequence[LcColumn],
-                             required_columns_for_soundness: int, ctx: Optional[Context] = None) -> None:
+                             required_columns_for_soundness: int, ctx: Optional[Context] = None,
+                             field: int = FT63) -> None:
     """lcpc_online.rs:370-398."""
     if (required_columns_for_soundness < len(locally_derived_column_leaves)
             or required_columns_for_soundness < len(requested_columns)
@@ -248,11 +259,11 @@ def client_verify_commitment(commitment_root: bytes, locally_derived_column_leav
         raise VerifierError("NumColOpens")
     ctx = ctx or default_context()
     if received_columns:
-        received_leaves, _ = _verify_columns(ctx, received_columns, None, None)
+        received_leaves, _ = _verify_columns(ctx, received_columns, None, None, field)
     else:
         received_leaves = np.empty((0, 32), dtype=np.uint8)
     client_online_verify_column_leaves(locally_derived_column_leaves, requested_columns, received_leaves)
-    client_online_verify_column_paths(commitment_root, requested_columns, received_columns, ctx)
+    client_online_verify_column_paths(commitment_root, requested_columns, received_columns, ctx, field)
 
 
 def verifiable_polynomial_evaluation(commitment: LcCommit, left_evaluation_column: np.ndarray) -> np.ndarray:

@@ -75,6 +75,15 @@ class GpuOps:
         self.fid = enc.fid
         self.L = FIELD_LIMBS[enc.fid]
         self.device = torch.device("cuda", enc.ctx.device)
+        # The lcpc_dev_* calls enqueue on the context's stream, the torch work around them (allocations, packs, NCCL
+        # collectives, symmetric-memory barriers) on torch's current stream, and nothing orders two different streams:
+        # the pack could read rows the encode has not written yet.  The context must have been created on the stream
+        # torch is using -- Context(device, stream=torch.cuda.current_stream().cuda_stream).
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        if enc.ctx.stream != cur:
+            raise ValueError("sharded commit: the encoding's Context enqueues on stream %#x but torch's current stream on %s "
+                             "is %#x; create it with Context(device, stream=torch.cuda.current_stream().cuda_stream)"
+                             % (enc.ctx.stream, self.device, cur))
 
     def encode(self, coeffs: torch.Tensor, n_rows: int) -> torch.Tensor:
         comm = torch.empty(n_rows * self.enc.n_cols * self.L, dtype=torch.int64, device=self.device)
@@ -124,6 +133,16 @@ class GpuOps:
     def hash_merge(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, out: torch.Tensor) -> None:
         _lib.check(self.lib.lcpc_dev_hash_merge(self.enc.ctx.handle, cvs.data_ptr(), n_cols, n_chunks, out.data_ptr()))
 
+    def hash_merge_tree(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, tree: torch.Tensor, n_leaves: int) -> None:
+        """hash_merge + merkle_tree in one launch (padding leaves written as zero by the kernel)."""
+        _lib.check(self.lib.lcpc_dev_hash_merge_tree(self.enc.ctx.handle, cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(),
+                                                     n_leaves))
+
+    def merkleize(self, mat: torch.Tensor, n_rows: int, row_stride: int, n_cols: int, tree: torch.Tensor) -> None:
+        """hash_columns + merkle_tree over next_pow2(n_cols) leaves in one launch."""
+        _lib.check(self.lib.lcpc_dev_merkleize(self.enc.ctx.handle, self.fid, mat.data_ptr(), n_rows, row_stride, n_cols,
+                                               tree.data_ptr()))
+
     def fold(self, mat: torch.Tensor, n_rows: int, width: int, row_stride: int, tensors: torch.Tensor,
              n_tensors: int) -> torch.Tensor:
         out = torch.zeros(n_tensors * width * self.L, dtype=torch.int64, device=self.device)
@@ -148,7 +167,11 @@ class ShardedLigeroCommitter:
     """
 
     def __init__(self, enc, n_rows_total: int, group=None, ops=None, fused: Optional[bool] = None, hashing: str = "columns"):
-        """hashing="columns" (default): the encoded matrix is re-sharded to column blocks and every rank hashes whole
+        """hashing="auto": row hashing with the chaining values stored into the owners' stores over NVLink when the shape
+        allows it (GPU back end, 2..16 ranks, power-of-two n_cols, leaves of at least two chunks, elements that divide a
+        chunk) -- 3 % of the exchange volume of column blocks and the measured winner from 2 GPUs up
+        (profiles/r02_scaling.md) -- else column blocks.
+        hashing="columns": the encoded matrix is re-sharded to column blocks and every rank hashes whole
         columns.  hashing="rows": every rank hashes the BLAKE3 chunks of ALL columns that its own rows make up
         (chunk-aligned row blocks, chunk_row_partition) and only the 32-byte chunk chaining values are re-sharded to
         column blocks -- 3 % of the volume for 8-byte elements; the encoded matrix stays row-sharded."""
@@ -167,6 +190,10 @@ class ShardedLigeroCommitter:
         self.cb = self.np2 // self.world
         self.rows = row_partition(n_rows_total, self.world)
         self.hashing, self.chunks = "columns", None
+        if hashing == "auto":
+            ok = (chunk_row_partition(self.L, n_rows_total, self.world) is not None and isinstance(self.ops, GpuOps)
+                  and 1 < self.world <= 16 and self.np2 == self.n_cols)
+            hashing, fused = ("rows", True) if ok else ("columns", None)
         if hashing == "rows":
             part = chunk_row_partition(self.L, n_rows_total, self.world)
             if part is None:
@@ -314,6 +341,11 @@ class ShardedLigeroCommitter:
             self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
             self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
             self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
+        if self.cols_local and hasattr(self.ops, "hash_merge_tree"):
+            # leaves of my column block from the chaining values + my whole subtree: one launch
+            self.ops.hash_merge_tree(recv, self.cols_local, self.n_chunks, self.subtree, cb)
+            self._join_subtrees(tree_done=True)
+            return
         if self.cols_local:  # padding leaves are never written: they stay zero
             self.ops.hash_merge(recv, self.cols_local, self.n_chunks, self.subtree)
         self._join_subtrees()
@@ -356,13 +388,18 @@ class ShardedLigeroCommitter:
             self.subtree = torch.zeros((2 * cb - 1) * 32, dtype=torch.uint8, device=dev)
             self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
             self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
+        if self.cols_local == cb and hasattr(self.ops, "merkleize"):
+            self.ops.merkleize(recv, self.n_rows, self.col_stride, cb, self.subtree)  # leaves + subtree: one launch
+            self._join_subtrees(tree_done=True)
+            return
         if self.cols_local:
             self.ops.hash_columns(recv, self.n_rows, self.col_stride, self.cols_local, self.subtree)
         self._join_subtrees()
 
-    def _join_subtrees(self) -> None:
+    def _join_subtrees(self, tree_done: bool = False) -> None:
         cb, W = self.cb, self.world
-        self.ops.merkle_tree(self.subtree, cb)
+        if not tree_done:
+            self.ops.merkle_tree(self.subtree, cb)
         # only the subtree roots travel (32 bytes per rank); rank 0 joins them
         my_root = self.subtree[-32:]
         if W > 1:

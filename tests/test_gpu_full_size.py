@@ -103,8 +103,35 @@ def test_ligero_ft63_2_28_invariants(P, oracle):
     assert np.array_equal(leaves, streamed[[0, 7, 262143]])
 
 
+def _check_rows_and_leaves_against_oracle(P, O, oenc, c, coeffs, sample_rows, sample_cols):
+    """Rows of the resident encoded matrix against the oracle's encode of the same coefficient rows (a wrong-but-linear
+    encode passes every invariant above: this does not), and the leaves / opened columns of sampled columns against the
+    oracle's hash of the same column.  A row of `comm` is read back as the encoded-matrix fold by a unit tensor."""
+    fid, L = c.enc.fid, c.enc.limbs
+    flat = np.zeros((c.n_rows * c.n_per_row, L), dtype=np.uint64)
+    flat[:coeffs.shape[0]] = coeffs
+    one = O.to_mont(fid, [1])[0]
+    units = np.zeros((len(sample_rows), c.n_rows, L), dtype=np.uint64)
+    for k, r in enumerate(sample_rows):
+        units[k, r] = one
+    got_rows = c.fold(units, encoded=True)                      # [k, n_cols, L] == comm[sample_rows]
+    msg = np.zeros((len(sample_rows), c.n_cols, L), dtype=np.uint64)
+    for k, r in enumerate(sample_rows):
+        msg[k, :c.n_per_row] = flat[r * c.n_per_row:(r + 1) * c.n_per_row]
+    exp_rows = oenc.encode_rows(msg)
+    assert np.array_equal(got_rows, exp_rows), "encoded rows differ from the oracle's encode"
+    opened = c.open_columns(sample_cols)
+    leaves = c.leaves(sample_cols)
+    for k, (j, col) in enumerate(zip(sample_cols, opened)):
+        colv = np.ascontiguousarray(col.col).reshape(c.n_rows, L)
+        for i, r in enumerate(sample_rows):
+            assert np.array_equal(colv[r], exp_rows[i, j])
+        assert O.hash_column(fid, colv) == leaves[k].tobytes(), "leaf differs from the oracle's column hash"
+
+
 def test_brakedown_ft255_2_24_invariants(P, oracle):
-    """BASELINE configs[2]: Brakedown code 3 over the 255-bit field, 101 x 166292 -> 252931."""
+    """BASELINE configs[2]: Brakedown code 3 over the 255-bit field, 101 x 166292 -> 252931; rows 0 / 50 / 100 of the
+    encoded matrix and six leaves against the oracle (encode.rs:36-94, lib.rs:736-775)."""
     O = oracle
     n = 1 << 24
     enc = P.SdigEncoding.new(3, n, seed=0)
@@ -113,6 +140,25 @@ def test_brakedown_ft255_2_24_invariants(P, oracle):
     c = P.LcCommit.commit(coeffs, enc, download=False)
     assert c.n_rows == 101
     _check_invariants(P, O, enc, c, coeffs, decode=False)
+    oenc = O.SdigEncoding(3, enc.n_per_row, 0)
+    assert oenc.n_cols == enc.n_cols
+    _check_rows_and_leaves_against_oracle(P, O, oenc, c, coeffs, [0, 50, 100],
+                                          [0, 166291, 166292, 200000, 252930, 12345])
+
+
+def test_brakedown_ft63_2_24_rows_and_leaves(P, oracle):
+    """BASELINE configs[4]'s Brakedown point over the 63-bit field: 101 x 166293 -> 252932."""
+    O = oracle
+    n = 1 << 24
+    enc = P.SdigEncoding.new(0, n, seed=0)
+    assert (enc.n_per_row, enc.n_cols) == (166293, 252932)
+    coeffs = _fast_rand(0, n - 77, 26, 1)  # ragged last row
+    c = P.LcCommit.commit(coeffs, enc, download=False)
+    assert c.n_rows == 101
+    _check_invariants(P, O, enc, c, coeffs, decode=False)
+    oenc = O.SdigEncoding(0, enc.n_per_row, 0)
+    _check_rows_and_leaves_against_oracle(P, O, oenc, c, coeffs, [0, 50, 100],
+                                          [0, 166292, 166293, 200000, 252931, 54321])
 
 
 def test_ligero_ft255_2_24_invariants(P, oracle):

@@ -125,6 +125,18 @@ def test_verify_rejects_tampering_with_reference_variants(P, oracle):
         # the degree check of the first column fails first (match order at lib.rs:968-973)
         (lambda pf: pf.p_eval.__setitem__((3, 0), pf.p_eval[3, 0] ^ np.uint64(1)), "ColumnDegree"),
     ]
+    # non-canonical alias x + p of a column element: same leaf bytes and transcript as the honest value, but not a value
+    # the reference's deserialiser (from_repr) would ever hand to its verifier -- refused before any kernel runs
+    pmod = np.uint64(O.MODULUS[fid])
+
+    def alias(pf):
+        with np.errstate(over="ignore"):
+            pf.columns[11].col[3, 0] = pf.columns[11].col[3, 0] + pmod
+    cases.append((alias, "ColumnEval"))
+    # a p_random vector of the wrong length (short or long) never reaches the flat C-ABI buffer
+    cases.append((lambda pf: pf.p_random_vec.__setitem__(1, pf.p_random_vec[1][:-1]), "ColumnDegree"))
+    cases.append((lambda pf: pf.p_random_vec.__setitem__(0, np.concatenate([pf.p_random_vec[0], pf.p_random_vec[0][:1]])),
+                  "ColumnDegree"))
     for mutate, variant in cases:
         with pytest.raises(P.VerifierError) as ei:
             run(mutate)
@@ -132,6 +144,13 @@ def test_verify_rejects_tampering_with_reference_variants(P, oracle):
     with pytest.raises(P.VerifierError) as ei:
         run(lambda pf: None, outer_=outer[:-1])
     assert ei.value.variant == "OuterTensor"
+    bad_inner = inner.copy()
+    with np.errstate(over="ignore"):
+        bad_inner[0, 0] = bad_inner[0, 0] + pmod
+    from lcpc_proof_of_storage_b200._lib import LcpcError
+    with pytest.raises(LcpcError) as ei2:
+        run(lambda pf: None, inner_=bad_inner)
+    assert ei2.value.variant == "InvalidArg"
     wrong_outer = outer.copy()
     wrong_outer[1, 0] ^= np.uint64(1)  # same transcript, wrong evaluation tensor: only the eval check fails
     with pytest.raises(P.VerifierError) as ei:
