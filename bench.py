@@ -7,12 +7,20 @@ Workload (BASELINE.json configs[1]): Ligero commit of a 2^24-coefficient polynom
 the 63-bit field, rho = 1/2, BLAKE3: 512 rows x 32768 -> 65536 columns.  One "step" is one
 commit: encode every row (batched NTT), hash every column, build the Merkle tree.
 At N > 1 the matrix has N x 512 rows of the same width (weak scaling); rows are sharded
-for encoding, an NCCL all-to-all re-shards to column blocks for hashing, every rank
-builds its Merkle subtree and rank 0 joins the N subtree roots.
+for encoding (chunk-aligned row blocks), every rank hashes the BLAKE3 chunks of ALL columns
+over its own rows and stores the 32-byte chaining values straight into the owning rank's
+store over NVLink (3 % of the encoded matrix), the owner merges them into leaves and builds
+its Merkle subtree, and rank 0 joins the N subtree roots.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM,
-CUDA events, max over ranks); `e2e` goes through the host-buffer C-ABI call
-(lcpc_commit_host: pinned host coefficients in, encoded matrix + Merkle tree out).
+CUDA events, max over ranks); `e2e` goes through the host-buffer path (pinned host
+coefficients in, encoded matrix + Merkle tree out; `e2e.root_only` is the same with only the
+32-byte root coming back).  At N = 1 the line also carries `configs`: the other BASELINE.json
+configurations (Ligero 2^28, Brakedown Ft255 2^24, the (n_dt+1)-tensor folds), each timed and
+checked against a committed known answer, and `integer_peak`: the integer-pipe issue rates
+measured on this device, the denominators of the second roofline.  At N > 1 small sharded cases
+(Brakedown, both hashing modes, folds, openings, the byte commit) are checked against committed
+known answers BEFORE the timed region (`parity_checks`); a mismatch is a non-zero exit.
 `--impl reference` times the CPU restatement of the reference's algorithm (oracle/) with
 all host threads on the same workload -- the Rust reference itself cannot be built here.
 """
@@ -36,8 +44,25 @@ FID = 0  # Ft63
 LOG_N = 24
 N_PER_ROW, N_COLS = 32768, 65536
 ROWS_PER_GPU = (1 << LOG_N) // N_PER_ROW  # 512
-METRIC = "ligero_commit_throughput_ft63_2^24"
+METRIC = "ligero_commit_throughput_ft63"  # the size is the workload's (config.workload): N x 2^24 coefficients at N GPUs
 UNIT = "field elements/s"
+
+
+# The other BASELINE.json configurations, timed at N = 1 after the headline workload (`configs` in the line); inputs are
+# the seeded streams of lcpc_proof_of_storage_b200/synth.py, known answers in tests/golden/bench_roots.json
+CONFIG_CASES = {
+    "ligero_ft63_2^28": {"seed": 28, "n_per_row": 131072, "n_cols": 262144},
+    "brakedown_ft255_2^24": {"seed": 3, "code_seed": 0, "n_per_row": 166292, "n_cols": 252931},
+    "fold_ft63_2^24": {"tensor_seed": 41, "n_tensors": 4},   # n_degree_tests + 1 = 4 at these widths
+    "fold_ft63_2^28": {"tensor_seed": 42, "n_tensors": 4},
+}
+# Small sharded cases checked at N > 1 before the timed region (`parity_checks` in the line); the row counts leave every
+# rank of 2, 4 or 8 at least one BLAKE3 chunk of rows
+PARITY_CASES = {
+    "ligero": {"seed": 7, "tensor_seed": 8, "n_rows": 1024, "n_per_row": 512, "n_cols": 1024, "open": [0, 5, 511, 512, 1023, 700, 5]},
+    "bytes": {"seed": 9, "n_rows": 1024, "n_per_row": 512, "n_cols": 1024, "n_bytes": 7 * 512 * 1024 - 13},
+    "brakedown": {"seed": 10, "code_seed": 0, "n_rows": 1024, "n_per_row": 3000, "n_cols": 4563},
+}
 
 
 def workload_name(n_gpus: int) -> str:
@@ -167,10 +192,6 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload
-# (profiles/r01e_summary.md); None for kernels that were not captured
-NCU_DRAM_TRAFFIC = {"k_ntt_strided": 134_726_656 + 212_986_368, "k_ntt_block": 268_538_368 + 212_768_512,
-                    "k_hash_chunks": 268_462_848 + 11_402_240}
 
 
 # per-kernel compulsory HBM bytes for one launch at this workload (DESIGN.md "Kernels")
@@ -210,27 +231,226 @@ INT_PIPE_MODEL = {
 }
 
 
-def int_pipe_floor_ms(name: str, units: float, n_sm: int, sm_mhz: float):
-    """Time the kernel would take if its binding integer pipe never idled: max(4W + 2I, 2W + 2A) issue cycles per warp
-    instruction group, 32 units per warp, 4 sub-partitions per SM."""
+def int_pipe_floor_ms(name: str, units: float, n_sm: int, sm_mhz: float, cyc: dict = None):
+    """Time the kernel would take if its binding integer pipe never idled: max(cW W + cI I, cW/2 W + cA A) issue cycles per
+    warp instruction group, 32 units per warp, 4 sub-partitions per SM.  cyc = measured cycles per warp instruction
+    (lcpc_ctx_measure_int_pipes); without it the round-1 figures 4 / 2 / 2 (profiles/r01c_int_pipes.txt)."""
     m = INT_PIPE_MODEL.get(name)
     if not m or not sm_mhz:
         return None
-    cycles = max(4 * m["W"] + 2 * m["I"], 2 * m["W"] + 2 * m["A"])
+    cw, ci, ca = (cyc["imad_wide"], cyc["imad"], cyc["lop3"]) if cyc else (4.0, 2.0, 2.0)
+    cycles = max(cw * m["W"] + ci * m["I"], cw / 2 * m["W"] + ca * m["A"])
     return cycles * (units / 32.0) / (4 * n_sm) / (sm_mhz * 1e3)
 
 
-def integer_pipe_report(kernels_ms_per_step: dict, n_sm: int, sm_mhz) -> dict:
+def integer_pipe_report(kernels_ms_per_step: dict, n_sm: int, sm_mhz, cyc: dict = None) -> dict:
     """{kernel: {floor_ms, measured_ms, frac}} for the kernels the model covers (one launch of each per step)."""
     units = {"element": ROWS_PER_GPU * N_COLS, "compression": N_COLS * ((32 + ROWS_PER_GPU * 8 + 63) // 64)}
     out = {}
     for k, ms in kernels_ms_per_step.items():
         if k not in INT_PIPE_MODEL or not ms:
             continue
-        f = int_pipe_floor_ms(k, units[INT_PIPE_MODEL[k]["unit"]], n_sm, sm_mhz)
+        f = int_pipe_floor_ms(k, units[INT_PIPE_MODEL[k]["unit"]], n_sm, sm_mhz, cyc)
         if f:
             out[k] = {"floor_ms": round(f, 4), "measured_ms": round(ms, 4), "frac": round(f / ms, 3)}
     return out
+
+
+def golden(section: str) -> dict:
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_roots.json")) as f:
+            return json.load(f).get(section, {})
+    except OSError:
+        return {}
+
+
+def dram_traffic(name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `name` from the round's `ncu --set full` capture of this
+    workload on the shipped build (profiles/r02_dram_traffic.json, written by tools/ncu_traffic.py); None when the kernel
+    is not in it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")) as f:
+            d = json.load(f)
+        v = d["kernels"].get(name)
+        return (v["dram_read_bytes"] + v["dram_write_bytes"], d.get("source")) if v else (None, None)
+    except Exception:
+        return None, None
+
+
+def _sha(t) -> str:
+    import hashlib
+
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
+
+
+def _time_steps(torch, stream, fn, steps: int, warmup: int) -> float:
+    for _ in range(warmup):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(steps):
+        fn()
+    b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def run_configs(torch, P, lib, _lib, ctx, stream, peak_gbs: float, d_coeffs_24) -> dict:
+    """The other BASELINE.json configurations on one GPU, device-resident, CUDA-event timed, each checked against its
+    committed known answer (tests/golden/bench_roots.json `configs`, computed by the CPU oracle on the same seeded
+    inputs).  Per case: ms, field elements / s, SURVEY 8(d) algorithmic GB/s and its fraction of the measured HBM peak."""
+    from lcpc_proof_of_storage_b200 import synth as S
+
+    want = golden("configs")
+    dev = torch.device("cuda", ctx.device)
+    out = {}
+
+    def entry(ms, n_elems, alg_bytes, ok, **extra):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        e = {"ms": ms, "elements_per_s": n_elems / (ms * 1e-3), "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs,
+             "matches_known_answer": ok}
+        e.update(extra)
+        return e
+
+    def fold_case(name, d_coeffs, n_rows, n_per_row):
+        k = CONFIG_CASES[name]
+        nt = k["n_tensors"]
+        tens = S.ft63_torch(k["tensor_seed"], nt * n_rows, dev)
+        d_out = torch.empty(nt * n_per_row, dtype=torch.int64, device=dev)
+
+        def fn():
+            _lib.check(lib.lcpc_dev_fold(ctx.handle, FID, d_coeffs.data_ptr(), n_rows, n_per_row, n_per_row, tens.data_ptr(),
+                                         nt, d_out.data_ptr()))
+
+        ms = _time_steps(torch, stream, fn, 20, 3)
+        ok = (_sha(d_out) == want.get(name, {}).get("sha256")) if name in want else None
+        # collapse_columns: the matrix is streamed once for all n_dt + 1 tensors (8 B per coefficient per pass)
+        return entry(ms, n_rows * n_per_row, n_rows * n_per_row * 8 + nt * (n_rows + n_per_row) * 8, ok,
+                     workload=f"collapse_columns, Ft63, {nt} tensors (n_degree_tests + 1) in one pass over {n_rows} x {n_per_row}")
+
+    out["fold_ft63_2^24"] = fold_case("fold_ft63_2^24", d_coeffs_24, ROWS_PER_GPU, N_PER_ROW)
+
+    # ---- Ligero Ft63, 2^28 coefficients: 2048 x 131072 -> 262144 (2 GiB in, 4 GiB encoded)
+    k = CONFIG_CASES["ligero_ft63_2^28"]
+    n, npr, nc = 1 << 28, k["n_per_row"], k["n_cols"]
+    n_rows = n // npr
+    enc = P.LigeroEncoding(FID, npr, nc, ctx=ctx)
+    d_c = S.ft63_torch(k["seed"], n, dev)
+    d_m = torch.empty(n_rows * nc, dtype=torch.int64, device=dev)
+    d_h = torch.zeros((2 * nc - 1) * 32, dtype=torch.uint8, device=dev)
+
+    def commit28():
+        _lib.check(lib.lcpc_dev_encode(enc.plan, d_c.data_ptr(), n_rows, d_m.data_ptr()))
+        _lib.check(lib.lcpc_dev_merkleize(ctx.handle, FID, d_m.data_ptr(), n_rows, nc, nc, d_h.data_ptr()))
+
+    ms = _time_steps(torch, stream, commit28, 5, 2)
+    root = bytes(d_h[-32:].cpu().numpy()).hex()
+    ok = (root == want.get("ligero_ft63_2^28", {}).get("root")) if "ligero_ft63_2^28" in want else None
+    out["ligero_ft63_2^28"] = entry(ms, n, n * 8 + n_rows * nc * 8 + (2 * nc - 1) * 32, ok, root=root,
+                                    workload=f"Ligero commit, Ft63, rho=1/2, BLAKE3, {n_rows} rows x {npr} -> {nc} cols")
+    del d_m, d_h
+    out["fold_ft63_2^28"] = fold_case("fold_ft63_2^28", d_c, n_rows, npr)
+    del d_c, enc
+    torch.cuda.empty_cache()
+
+    # ---- Brakedown code 3 over Ft255, 2^24 coefficients: 101 x 166292 -> 252931
+    k = CONFIG_CASES["brakedown_ft255_2^24"]
+    n = 1 << 24
+    enc = P.SdigEncoding.new(P.FT255, n, seed=k["code_seed"], ctx=ctx)
+    assert (enc.n_per_row, enc.n_cols) == (k["n_per_row"], k["n_cols"])
+    npr, nc = enc.n_per_row, enc.n_cols
+    n_rows = (n + npr - 1) // npr
+    np2 = P.next_pow2(nc)
+    d_c = torch.zeros(n_rows * npr * 4, dtype=torch.int64, device=dev)   # zero-padded last row (lib.rs:665-674)
+    d_c[:n * 4] = S.ft255_torch(k["seed"], n, dev)
+    d_m = torch.empty(n_rows * nc * 4, dtype=torch.int64, device=dev)
+    d_h = torch.zeros((2 * np2 - 1) * 32, dtype=torch.uint8, device=dev)
+
+    def commit_bd():
+        _lib.check(lib.lcpc_dev_encode(enc.plan, d_c.data_ptr(), n_rows, d_m.data_ptr()))
+        _lib.check(lib.lcpc_dev_merkleize(ctx.handle, P.FT255, d_m.data_ptr(), n_rows, nc, nc, d_h.data_ptr()))
+
+    ms = _time_steps(torch, stream, commit_bd, 5, 2)
+    root = bytes(d_h[-32:].cpu().numpy()).hex()
+    ok = (root == want.get("brakedown_ft255_2^24", {}).get("root")) if "brakedown_ft255_2^24" in want else None
+    out["brakedown_ft255_2^24"] = entry(ms, n, n * 32 + n_rows * nc * 32 + (2 * np2 - 1) * 32, ok, root=root,
+                                        workload=f"Brakedown (code 3) commit, Ft255, BLAKE3, {n_rows} rows x {npr} -> {nc} cols")
+    return out
+
+
+def sharded_parity_checks(torch, dist, P, ctx, rank: int, world: int) -> dict:
+    """Small sharded cases against committed known answers (tests/golden/bench_roots.json `parity`), run on every rank
+    before the timed region: both hashing modes and the fused exchange on a Ligero commit, the coefficient fold, the fold
+    over the encoded matrix, openings (values + paths, checked again by lcpc_verify_columns_host), the proof-of-storage
+    byte commit and a Brakedown commit (lcpc-brakedown-pc/src/encode.rs:36-94, lcpc-2d/src/lib.rs:736-775).
+    Returns {check: bool} on rank 0 ({} elsewhere)."""
+    import numpy as np
+
+    from lcpc_proof_of_storage_b200 import pos
+    from lcpc_proof_of_storage_b200 import synth as S
+    from lcpc_proof_of_storage_b200.sharded import ShardedCommitter
+
+    want = golden("parity")
+    dev = torch.device("cuda", ctx.device)
+    res = {}
+
+    def put(name, value):
+        if rank == 0:
+            res[name] = bool(value)
+
+    k = PARITY_CASES["ligero"]
+    enc = P.LigeroEncoding(FID, k["n_per_row"], k["n_cols"], ctx=ctx)
+    tens = S.ft63_torch(k["tensor_seed"], 2 * k["n_rows"], dev)
+    for mode in ("columns", "rows", "auto"):
+        sc = ShardedCommitter(enc, k["n_rows"], dist.group.WORLD, hashing=mode)
+        coeffs = S.ft63_torch(k["seed"], sc.rows_local * k["n_per_row"], dev, start=sc.row0 * k["n_per_row"])
+        sc.commit(coeffs)
+        label = {"columns": "ligero_columns", "rows": "ligero_rows_nccl", "auto": "ligero_rows_fused"}[mode]
+        put(label + "_root", rank != 0 or sc.root().hex() == want.get("ligero_root"))
+        f = sc.fold(tens)
+        fe = sc.fold_encoded(tens)
+        put(label + "_fold", _sha(f) == want.get("fold_sha256"))
+        put(label + "_fold_encoded", _sha(fe) == want.get("fold_encoded_sha256"))
+        opened = sc.open_columns(k["open"])
+        if rank == 0:
+            cols = np.stack([o.col for o in opened])
+            paths = np.stack([o.path for o in opened])
+            import hashlib
+
+            put(label + "_open_columns", hashlib.sha256(cols.tobytes()).hexdigest() == want.get("open_cols_sha256"))
+            put(label + "_open_paths", hashlib.sha256(np.ascontiguousarray(paths).tobytes()).hexdigest() == want.get("open_paths_sha256"))
+            try:
+                pos.client_online_verify_column_paths(sc.root(), k["open"], opened, ctx)
+                put(label + "_verify_columns", True)
+            except Exception:
+                put(label + "_verify_columns", False)
+        if mode == "auto":
+            put("auto_picks_fused_row_hashing", sc.hashing == "rows" and sc.cv_fused)
+        del sc
+    k = PARITY_CASES["bytes"]
+    enc_b = P.LigeroEncoding(FID, k["n_per_row"], k["n_cols"], ctx=ctx)
+    sc = ShardedCommitter(enc_b, k["n_rows"], dist.group.WORLD, hashing="auto")
+    lo, hi = sc.byte_range(k["n_bytes"])
+    lo8 = lo - lo % 8
+    data = S.bytes_torch(k["seed"], hi - lo8, dev, lo8)[lo - lo8:].clone()
+    sc.commit_bytes(data)
+    put("commit_bytes_root", rank != 0 or sc.root().hex() == want.get("bytes_root"))
+    del sc
+    k = PARITY_CASES["brakedown"]
+    enc_s = P.SdigEncoding.new_from_dims(FID, k["n_per_row"], k["n_cols"], seed=k["code_seed"], ctx=ctx)
+    n_total = k["n_rows"] * k["n_per_row"] - 5
+    for mode in ("columns", "rows"):
+        sc = ShardedCommitter(enc_s, k["n_rows"], dist.group.WORLD, hashing=mode)
+        e0, e1 = sc.row0 * k["n_per_row"], (sc.row0 + sc.rows_local) * k["n_per_row"]
+        coeffs = torch.zeros(sc.rows_local * k["n_per_row"], dtype=torch.int64, device=dev)
+        have = max(0, min(n_total, e1) - e0)
+        if have:
+            coeffs[:have] = S.ft63_torch(k["seed"], have, dev, start=e0)
+        sc.commit(coeffs)
+        put(f"brakedown_{mode}_root", rank != 0 or sc.root().hex() == want.get("brakedown_root"))
+        del sc
+    return res
 
 
 def run_reference(args, rank: int, world: int) -> None:
@@ -307,10 +527,13 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hashing", default="columns", choices=["columns", "rows", "rows-fused"],
-                    help="N > 1 only: 'rows' hashes BLAKE3 chunks where the rows are and re-shards 32-byte chaining values "
-                         "instead of the encoded matrix (ShardedLigeroCommitter hashing='rows'; not the default yet); "
-                         "'rows-fused' lets the hash kernel store them into the owners' stores over NVLink")
+    ap.add_argument("--hashing", default="rows-fused", choices=["columns", "rows", "rows-fused"],
+                    help="N > 1 only.  'rows-fused' (default, the measured winner from 2 GPUs up): BLAKE3 chunks are hashed "
+                         "where the rows are and the hash kernel stores the 32-byte chaining values into the owners' stores "
+                         "over NVLink; 'rows': the same values through an NCCL all-to-all; 'columns': the encoded matrix is "
+                         "re-sharded to column blocks (the NTT's last pass stores into peer HBM)")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the `configs` block (the other BASELINE.json cases)")
+    ap.add_argument("--no-parity-checks", action="store_true", help="N > 1: skip the sharded known-answer checks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -338,6 +561,17 @@ def main() -> None:
     lib = _lib.load()
     stream = torch.cuda.current_stream()
     ctx = P.Context(local_rank, stream=stream.cuda_stream)
+    parity_checks = None
+    if world > 1 and not args.no_parity_checks:
+        parity_checks = sharded_parity_checks(torch, dist, P, ctx, rank, world)
+        bad = torch.tensor([0 if all(parity_checks.values()) else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            if rank == 0:
+                sys.stderr.write("sharded parity checks FAILED: " + json.dumps(parity_checks) + "\n")
+            dist.destroy_process_group()
+            raise SystemExit(3)
+        torch.cuda.empty_cache()
     enc = P.LigeroEncoding(FID, N_PER_ROW, N_COLS, ctx=ctx)
 
     n_rows_total = ROWS_PER_GPU * world
@@ -349,7 +583,9 @@ def main() -> None:
         from lcpc_proof_of_storage_b200.sharded import chunk_row_partition
 
         row0, rows_local = chunk_row_partition(1, n_rows_total, world)[0][rank]
-    h_coeffs_np = make_coeffs(2, n_total)[row0 * N_PER_ROW:(row0 + rows_local) * N_PER_ROW]
+    from lcpc_proof_of_storage_b200 import synth as S
+
+    h_coeffs_np = S.ft63_np(2, rows_local * N_PER_ROW, start=row0 * N_PER_ROW)  # = make_coeffs(2, n_total)[my rows]
     h_coeffs = torch.from_numpy(h_coeffs_np.view(np.int64).reshape(-1)).pin_memory()
     d_coeffs = h_coeffs.cuda(non_blocking=True)
     torch.cuda.synchronize()
@@ -360,7 +596,7 @@ def main() -> None:
 
         def step():
             _lib.check(lib.lcpc_dev_encode(enc.plan, d_coeffs.data_ptr(), ROWS_PER_GPU, d_comm.data_ptr()))
-            # merkleize: leaf hashing, the BLAKE3 parent tree per leaf and the Merkle tree in one launch (k_hash_tree)
+            # merkleize: chunk hashing (k_hash_chunks), then leaf merge + the whole Merkle tree in one launch (k_merge_tree)
             _lib.check(lib.lcpc_dev_merkleize(ctx.handle, FID, d_comm.data_ptr(), ROWS_PER_GPU, N_COLS, N_COLS,
                                               d_hashes.data_ptr()))
 
@@ -436,6 +672,24 @@ def main() -> None:
     value = n_total / (ms_per_step * 1e-3)
     gpu_root = root_hex()
 
+    # single-commit latency: one commit at a time, nothing deferred or pipelined, every rank synchronised before and after
+    # (host clock around a device-synchronised region; median over the commits, max over ranks)
+    lat = []
+    for _ in range(min(steps, 20)):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            step()
+        else:
+            sc.commit(d_coeffs)
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    latency_ms = sorted(lat)[len(lat) // 2]
+    if dist is not None:
+        t = torch.tensor([latency_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        latency_ms = float(t.item())
+
     # ---- end to end through the host-buffer C-ABI call (N = 1 path per rank) ----------------------
     e2e = None
     if world == 1:  # host destinations of the full LcCommit (the sharded leg reads back the root only)
@@ -481,32 +735,57 @@ def main() -> None:
             resident_step()
         torch.cuda.synchronize()
         dt2 = time.perf_counter() - t0
-        e2e["resident_handle"] = {"value": n_local * e2e_steps / dt2, "ms_per_step": 1e3 * dt2 / e2e_steps,
-                                  "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": 32,
-                                  "api": "lcpc_commit_host(keep=handle) + lcpc_commit_root"}
+        e2e["shape"] = "full LcCommit out (comm + hashes)"
+        e2e["root_only"] = {"value": n_local * e2e_steps / dt2, "unit": UNIT, "ms_per_step": 1e3 * dt2 / e2e_steps,
+                            "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": 32,
+                            "api": "lcpc_commit_host(keep=handle) + lcpc_commit_root: the commitment stays resident in HBM"}
         assert bytes(root_buf.numpy()).hex() == gpu_root
     else:
-        # sharded end to end: pinned host rows in, root (32 B) out on rank 0
-        def e2e_sharded_step():
+        # sharded end to end, both shapes: pinned host row shards in; (a) the full LcCommit out -- every rank's encoded rows
+        # and Merkle subtree to its own pinned host buffers, the top of the tree on rank 0 -- and (b) the root only
+        by_rows = sc.hashing == "rows"
+        h_comm = torch.empty((rows_local if by_rows else n_rows_total) * (N_COLS if by_rows else sc.cb), dtype=torch.int64).pin_memory()
+        h_sub = torch.empty((2 * sc.cb - 1) * 32, dtype=torch.uint8).pin_memory()
+        h_top = torch.empty((2 * world - 1) * 32, dtype=torch.uint8).pin_memory()
+
+        def e2e_sharded_step(full: bool):
             d = h_coeffs.cuda(non_blocking=True)
             sc.commit(d)
-            if rank == 0:
+            if full:
+                h_comm.copy_(sc.comm_rows if by_rows else sc.comm_cols, non_blocking=True)
+                h_sub.copy_(sc.subtree, non_blocking=True)
+                if rank == 0:
+                    h_top.copy_(sc.top, non_blocking=True)
+                torch.cuda.synchronize()
+            elif rank == 0:
                 sc.root()  # device -> host read of the result
 
-        for _ in range(3):  # untimed, like the one-GPU leg: first-use allocations of the staging tensors
-            e2e_sharded_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_sharded_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {"value": n_total * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_local * 8 * world,
-               "d2h_bytes_per_step": 32, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-               "api": "ShardedLigeroCommitter.commit (pinned host row shards in; Merkle root out on rank 0)"}
+        def time_e2e(full: bool) -> float:
+            for _ in range(3):  # untimed, like the one-GPU leg: first-use allocations of the staging tensors
+                e2e_sharded_step(full)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_sharded_step(full)
+            barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        dt_full = time_e2e(True)
+        if rank == 0:
+            assert bytes(h_top[-32:].numpy()).hex() == gpu_root, "e2e root differs from the device-resident root"
+        dt_root = time_e2e(False)
+        d2h_full = n_rows_total * N_COLS * 8 + world * (2 * sc.cb - 1) * 32 + (2 * world - 1) * 32
+        e2e = {"value": n_total * e2e_steps / dt_full, "unit": UNIT, "h2d_bytes_per_step": n_local * 8 * world,
+               "d2h_bytes_per_step": d2h_full, "ms_per_step": 1e3 * dt_full / e2e_steps, "steps": e2e_steps,
+               "shape": "full LcCommit out (comm + hashes)",
+               "api": "ShardedLigeroCommitter.commit (pinned host row shards in; every rank's encoded rows and Merkle subtree "
+                      "to its pinned host buffers, top of the tree on rank 0)",
+               "root_only": {"value": n_total * e2e_steps / dt_root, "unit": UNIT, "ms_per_step": 1e3 * dt_root / e2e_steps,
+                             "h2d_bytes_per_step": n_local * 8 * world, "d2h_bytes_per_step": 32,
+                             "api": "ShardedLigeroCommitter.commit (pinned host row shards in; Merkle root out on rank 0)"}}
 
     if rank != 0:
         if dist is not None:
@@ -520,26 +799,43 @@ def main() -> None:
         dom = max(kt.items(), key=lambda kv: kv[1][1])
         name, (count, total_ms) = dom
         per_launch_ms = total_ms / count
-        alg = kernel_algorithmic_bytes(name, ROWS_PER_GPU if world == 1 else ROWS_PER_GPU)
+        alg = kernel_algorithmic_bytes(name, rows_local)
         ach = alg / (per_launch_ms * 1e-3) / 1e9 if alg else None
+        traffic, traffic_src = dram_traffic(name) if world == 1 else (None, None)
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach else None,
-                    "traffic": NCU_DRAM_TRAFFIC.get(name.replace("_scatter", "")) if world == 1 else None,
-                    "traffic_source": "ncu --set full, profiles/r01e_summary.md", "peak_source": peak_src,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                     "share_of_step": total_ms / ms_total_timed,
                     "ms_per_step_with_launch_events": ms_total_timed / steps,
                     "kernels_ms_per_step": {k: v[1] / steps for k, v in kt.items()},
                     "note": "integer-pipe bound (64-bit Montgomery + BLAKE3 ARX on 32-bit IMAD/ALU), see DESIGN.md"}
-        # second roofline: the integer pipes (what actually binds these kernels), from the model above and the live clock
+        # second roofline: the integer pipes (what actually binds these kernels): essential instruction counts of the
+        # arithmetic against the issue rates MEASURED on this device just now (lcpc_ctx_measure_int_pipes)
         try:
             n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
-            roofline["integer_pipe"] = integer_pipe_report(roofline["kernels_ms_per_step"], n_sm, sampler.summary()["sm_mhz"])
+            integer_peak = ctx.measure_int_pipes()
+            integer_peak["n_sm"] = n_sm
+            integer_peak["note"] = ("SM sub-partition cycles per warp instruction, all resident warps issuing: pure IMAD.WIDE / "
+                                    "IMAD / LOP3 streams and an IMAD + LOP3 mix (two pipes at once)")
+            roofline["integer_pipe"] = integer_pipe_report(roofline["kernels_ms_per_step"], n_sm, sampler.summary()["sm_mhz"],
+                                                           integer_peak["cycles_per_warp_instr"])
             roofline["integer_pipe_note"] = ("floor = essential IMAD.WIDE / IMAD / ALU instruction counts of the arithmetic "
-                                             "(DESIGN.md section 3) at the sampled SM clock; frac = floor / measured")
+                                             "(DESIGN.md section 3) x the measured cycles per instruction (integer_peak) at the "
+                                             "sampled SM clock; frac = floor / measured")
         except Exception as e:  # the model is commentary: it must never cost the line
+            integer_peak = None
             roofline["integer_pipe"] = {"error": repr(e)}
     step_gbs = algorithmic_bytes(n_total, n_rows_total) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- the other BASELINE.json configurations (N = 1) ----------------------------------------------
+    configs = None
+    if world == 1 and not args.no_configs:
+        del d_comm, d_hashes, h_comm, h_hashes
+        torch.cuda.empty_cache()
+        configs = run_configs(torch, P, lib, _lib, ctx, stream, peak, d_coeffs)
+        bad = [k for k, v in configs.items() if v["matches_known_answer"] is False]
+        assert not bad, f"configs differ from tests/golden/bench_roots.json: {bad}"
 
     # ---- CPU baseline: oracle on the same input, all host threads; also the parity gate ------------
     # (rank 0 at N = 1 only: at N > 1 the other ranks have left and the line carries no CPU leg)
@@ -588,10 +884,12 @@ def main() -> None:
                                                                         if sc.cv_fused else "NCCL all-to-all of 32 B per chunk and column")
                                                                      if sc.hashing == "rows" else "NCCL all-to-all"))
                        + "; per-rank Merkle subtrees, roots all-gathered")},
-        "algorithmic_GBps": step_gbs,
+        "algorithmic_GBps": step_gbs, "frac_of_hbm_peak_whole_commit": step_gbs / peak,
+        "single_commit_latency_ms": latency_ms,
         "host_binding": numa,
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
         "root": gpu_root, "root_matches_golden": (gpu_root == kat) if kat is not None else None,
+        "integer_peak": integer_peak if kt else None, "configs": configs, "parity_checks": parity_checks,
     }
     _emit(line)
     if dist is not None:

@@ -142,6 +142,14 @@ void lcpc_plan_destroy(lcpc_plan *plan);
  * entry (lcpc-2d/src/lib.rs:677-682; verifier use at :912-918, :944-950). */
 int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows);
 
+/* decode_row (proof-of-storage/src/lcpc_online.rs:568-573) = fffft::FieldFFT::ifft_oi on `n_rows` rows at once, in
+ * place, host memory: every row holds n_cols elements of a Ligero codeword in the encoder's (bit-reversed) output order
+ * and is replaced by the n_cols coefficients in natural order, scaled by 1/n_cols, so that
+ * decode(encode(x)) == x (lcpc_online.rs:588-601, lcpc-2d/src/tests.rs:223-233).  Used by the server's append
+ * (lcpc_online/file_handler.rs:370) and the encoded-file reader (encoded_file_reader.rs:66,83), which hold only encoded
+ * rows.  Ligero plans only: LCPC_ERR_ENCODE for a Brakedown plan (the reference has no decoder for it either). */
+int32_t lcpc_decode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows);
+
 /* ---- commit ----------------------------------------------------------------------- */
 
 /* LcCommit::commit (lcpc-2d/src/lib.rs:314 -> commit :651-700): pad, encode every row,
@@ -281,6 +289,8 @@ double lcpc_sdig_dist(int32_t code);
 /* rows [0, n_rows) of the padded coefficient matrix -> encoded rows.  d_coeffs has
  * row stride n_per_row, d_comm row stride n_cols.  d_coeffs may alias nothing in d_comm. */
 int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);
+/* lcpc_decode_rows on device memory, in place: n_rows rows of n_cols elements, row stride n_cols. */
+int32_t lcpc_dev_decode(lcpc_plan *plan, uint64_t *d_rows, size_t n_rows);
 /* Fused encode + re-shard for the one-process-per-GPU path (Ligero plans): like lcpc_dev_encode,
  * but the last pass of the transform stores every row block directly into the column-block matrix
  * of the rank that hashes those columns: peer_blocks[g] is rank g's [n_rows_total][n_cols/n_peers]
@@ -338,6 +348,11 @@ int32_t lcpc_dev_add_partials(lcpc_ctx *ctx, int32_t field, const uint64_t *d_pa
 /* strided gather of columns: d_out[i*n_rows + r] = d_mat[r*row_stride + cols[i]] (d_cols on device). */
 int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows,
                                 size_t row_stride, const uint64_t *d_cols, size_t n, uint64_t *d_out);
+/* Merkle paths of open_column (lib.rs:841-851) from a flat tree over n_leaves (a power of two) on the device:
+ * d_paths[(i * depth + l) * 32 ..] = level_l[(d_cols[i] >> l) ^ 1], depth = log2(n_leaves) digests per column, leaf
+ * level first.  Every index must be below n_leaves. */
+int32_t lcpc_dev_gather_paths(lcpc_ctx *ctx, const uint8_t *d_hashes, size_t n_leaves, const uint64_t *d_cols, size_t n,
+                              uint8_t *d_paths);
 /* 7-byte packing (WriteableFt63::from_data_bytes): n_elems = ceil(n_bytes/7) limbs written. */
 int32_t lcpc_dev_pack_bytes7(lcpc_ctx *ctx, const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems);
 
@@ -392,6 +407,13 @@ uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx);
  * valid until the next call). */
 int32_t lcpc_ctx_kernel_timing(lcpc_ctx *ctx, int32_t enable);
 const char *lcpc_ctx_kernel_timing_report(lcpc_ctx *ctx);
+
+/* Measures the integer-pipe issue rates of this device (a few milliseconds of microbenchmark kernels on the context's
+ * stream): SM sub-partition cycles per warp instruction, all resident warps issuing, for pure streams of
+ * [0] IMAD.WIDE.U32, [1] IMAD, [2] LOP3 (the ALU pipe) and [3] an equal mix of IMAD and LOP3 (two pipes at once);
+ * sm_ghz_out (nullable) receives the SM clock observed during the run.  These are the denominators of the integer
+ * roofline bench.py reports next to the HBM one: the commit kernels are bound by these pipes. */
+int32_t lcpc_ctx_measure_int_pipes(lcpc_ctx *ctx, double cycles_out[4], double *sm_ghz_out);
 
 #ifdef __cplusplus
 }

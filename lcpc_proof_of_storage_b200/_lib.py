@@ -52,6 +52,7 @@ _SIGNATURES = {
     "lcpc_ctx_create_on_stream": (C.c_int32, [C.c_int32, C.c_void_p, vpp]),
     "lcpc_ctx_synchronize": (C.c_int32, [C.c_void_p]),
     "lcpc_ctx_stream": (C.c_int32, [C.c_void_p, vpp]),
+    "lcpc_ctx_measure_int_pipes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lcpc_ctx_destroy": (None, [C.c_void_p]),
     "lcpc_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "lcpc_ctx_kernel_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
@@ -69,6 +70,8 @@ _SIGNATURES = {
     "lcpc_plan_get_dims": (C.c_int32, [C.c_void_p, C.c_size_t, szp, szp, szp]),
     "lcpc_plan_destroy": (None, [C.c_void_p]),
     "lcpc_encode_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "lcpc_decode_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "lcpc_dev_decode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "lcpc_commit_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, vpp]),
     "lcpc_commit_bytes_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, vpp]),
     "lcpc_commit_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, vpp]),
@@ -110,6 +113,7 @@ _SIGNATURES = {
     "lcpc_dev_add_partials": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_gather_columns": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                             C.c_size_t, C.c_void_p]),
+    "lcpc_dev_gather_paths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lcpc_dev_pack_bytes7": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lcpc_dev_hash_chunk_range": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_size_t, C.c_size_t,
                                               C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),

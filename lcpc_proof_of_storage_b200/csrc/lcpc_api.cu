@@ -97,10 +97,24 @@ int32_t lcpc::abi::merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm,
         CU(scratch.alloc(cv_bytes, ctx->stream));
         cvs = scratch.as<uint8_t>();
     }
-    if (hash_tree_supported(fid, n_rows, np2)) {
+    // mode 2: everything in one launch (k_hash_tree), chosen when the whole grid is resident at once; mode 1: chunk
+    // hashing, then leaf merge + tree in one launch (k_merge_tree); mode 0: the four-launch form.  LCPC_HASH_MODE
+    // overrides the choice (tools/bench_hash_tail.py).
+    int mode = hash_tree_preferred(fid, n_rows, np2) ? 2 : 1;
+    if (const char *e = getenv("LCPC_HASH_MODE")) mode = atoi(e);
+    if (mode == 2 && hash_tree_supported(fid, n_rows, np2)) {
         unsigned *tk = nullptr;
         CU(ctx->tickets(hash_tree_tickets(np2), &tk));
         CU(hash_tree(fid, d_comm, n_rows, row_stride, n_cols, np2, d_hashes, cvs, tk, ctx->lc()));
+        return LCPC_OK;
+    }
+    if (mode != 0) {
+        unsigned *tk = nullptr;
+        CU(ctx->tickets(1, &tk));
+        const uint64_t nc = hash_leaf_chunks(fid, n_rows);
+        if (nc > 1) CU(hash_chunk_range(fid, d_comm, 0, n_rows, row_stride, n_cols, 0, nc, hash_leaf_bytes(fid, n_rows), nc, cvs, ctx->lc()));
+        else CU(hash_columns(fid, d_comm, n_rows, row_stride, n_cols, nullptr, d_hashes, cvs, ctx->lc()));
+        CU(merge_tree(cvs, n_cols, nc, d_hashes, np2, tk, ctx->lc()));
         return LCPC_OK;
     }
     // padding leaves n_cols..np2 stay all-zero (lib.rs:685-695)
@@ -479,6 +493,36 @@ int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
         CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * L * sizeof(uint64_t), ctx->stream));
         CU(sdig_encode(plan->sdig, buf.as<uint64_t>(), n_rows, tmp.as<uint64_t>(), ctx->lc()));
     }
+    CU(cudaMemcpyAsync(rows, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_decode(lcpc_plan *plan, uint64_t *d_rows, size_t n_rows) {
+    if (!plan || (!d_rows && n_rows)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (plan->kind != 0) return fail(LCPC_ERR_ENCODE, "only Ligero (Reed-Solomon) rows have an inverse transform");
+    if (n_rows == 0) return LCPC_OK;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(ntt_decode(plan->ntt, d_rows, n_rows, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_decode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
+    if (!plan || (!rows && n_rows)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (plan->kind != 0) return fail(LCPC_ERR_ENCODE, "only Ligero (Reed-Solomon) rows have an inverse transform");
+    if (n_rows == 0) return LCPC_OK;
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = n_rows * plan->n_cols * limbs_of(plan->fid) * sizeof(uint64_t);
+    DevBuf buf;
+    CU(buf.alloc(bytes, ctx->stream));
+    CU(cudaMemcpyAsync(buf.p, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ntt_decode(plan->ntt, buf.as<uint64_t>(), n_rows, ctx->lc()));
     CU(cudaMemcpyAsync(rows, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LCPC_OK;
@@ -892,6 +936,16 @@ int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     CU(gather_columns(field, d_mat, n_rows, row_stride, d_cols, n, d_out, ctx->lc()));
+    return LCPC_OK;
+}
+
+int32_t lcpc_dev_gather_paths(lcpc_ctx *ctx, const uint8_t *d_hashes, size_t n_leaves, const uint64_t *d_cols, size_t n,
+                              uint8_t *d_paths) {
+    if (!ctx || !d_hashes || (n && (!d_cols || !d_paths))) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(gather_paths(d_hashes, n_leaves, d_cols, n, d_paths, ctx->lc()));
     return LCPC_OK;
 }
 

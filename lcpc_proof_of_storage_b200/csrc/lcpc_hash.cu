@@ -12,9 +12,15 @@
 // tree gives a second grid dimension (1024-byte chunks are independent), which is what
 // fills 148 SMs when n_cols alone is only 2^16; a second small kernel folds the chunk
 // chaining values per column.  Merkle levels are reduced 9 at a time inside one CTA.
+#include <cstdlib>
+
 #include "lcpc_blake3.cuh"
 #include "lcpc_field.cuh"
 #include "lcpc_kernels.h"
+
+#ifndef LCPC_HASH_CTAS1
+#define LCPC_HASH_CTAS1 7  // resident 128-thread CTAs per SM for the one-limb field (register budget 72: measured best of 5/7/8, profiles/r02_hash_tail.md)
+#endif
 
 namespace lcpc {
 
@@ -128,6 +134,55 @@ __device__ __forceinline__ void chunk_cv(uint32_t cv[8], const uint64_t *__restr
                                          size_t col, uint64_t total_bytes, uint64_t n_chunks, int64_t row_base, uint64_t c) {
     const uint64_t chunk_bytes = (c + 1 == n_chunks) ? total_bytes - c * b3::CHUNK_BYTES : b3::CHUNK_BYTES;
     const uint32_t nb = (uint32_t)((chunk_bytes + b3::BLOCK_BYTES - 1) / b3::BLOCK_BYTES);
+    if constexpr (BlockElems<FID>::WHOLE) {
+        // Interior fast path (a full chunk of a multi-chunk leaf whose rows all exist): no per-row bounds checks, flags
+        // and lengths are literals, and two blocks per trip through two buffers used alternately, so that the
+        // prefetched block is never copied.  The issue port binds this kernel (one warp instruction per cycle per
+        // sub-partition), so every instruction that is not a G function counts.
+        using E = typename Field<FID>::E;
+        constexpr int L = Field<FID>::LIMBS, WPE = 2 * L, EPB = BlockElems<FID>::EPB, K = BlockElems<FID>::K;
+        const int64_t row0 = (int64_t)(c * 16 * EPB) - K;  // row of element 0 of the chunk's first block
+        if (n_chunks > 1 && nb == 16 && (uint64_t)(row0 + 16 * EPB) <= n_rows) {
+            const uint64_t *base = mat + ((row0 - row_base) * (int64_t)row_stride + (int64_t)col) * L;
+            const size_t rs = row_stride * L;
+            auto words = [](uint32_t(&m)[16], const E(&e)[EPB]) {
+#pragma unroll
+                for (int i = 0; i < EPB; i++) {
+                    const E r = Field<FID>::to_repr(e[i]);
+#pragma unroll
+                    for (int l = 0; l < L; l++) {
+                        m[i * WPE + 2 * l] = (uint32_t)r.v[l];
+                        m[i * WPE + 2 * l + 1] = (uint32_t)(r.v[l] >> 32);
+                    }
+                }
+            };
+            E bufA[EPB], bufB[EPB];
+            if (c == 0) {  // the 32 zero bytes in front of row 0
+#pragma unroll
+                for (int i = 0; i < EPB; i++) bufA[i] = i < K ? Field<FID>::zero() : ld_fe<L>(base + (size_t)i * rs);
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPB; i++) bufA[i] = ld_fe<L>(base + (size_t)i * rs);
+            }
+            b3::set_iv(cv);
+#pragma unroll 1
+            for (int b = 0; b < 16; b += 2) {
+                const uint64_t *pb = base + (size_t)(b + 1) * EPB * rs;
+#pragma unroll
+                for (int i = 0; i < EPB; i++) bufB[i] = ld_fe<L>(pb + (size_t)i * rs);
+                uint32_t m[16];
+                words(m, bufA);
+                b3::compress(cv, m, c, b3::BLOCK_BYTES, b == 0 ? b3::CHUNK_START : 0u);
+                if (b + 2 < 16) {
+#pragma unroll
+                    for (int i = 0; i < EPB; i++) bufA[i] = ld_fe<L>(pb + (size_t)(EPB + i) * rs);
+                }
+                words(m, bufB);
+                b3::compress(cv, m, c, b3::BLOCK_BYTES, b + 2 == 16 ? b3::CHUNK_END : 0u);
+            }
+            return;
+        }
+    }
     b3::set_iv(cv);
     BlockElems<FID> cur, nxt;
     if constexpr (BlockElems<FID>::WHOLE) cur.load(mat, n_rows, row_stride, col, c * 16, row_base);
@@ -168,7 +223,7 @@ __device__ __forceinline__ void hash_chunks_body(const uint64_t *__restrict__ ma
 }
 
 template <int FID>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, Field<FID>::LIMBS == 1 ? LCPC_HASH_CTAS1 : 5)
 k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols,
               const uint64_t *__restrict__ col_idx, uint64_t total_bytes, uint64_t n_chunks, uint32_t *__restrict__ out,
               int64_t row_base, uint64_t chunk0, uint64_t chunk_end) {
@@ -181,7 +236,7 @@ k_hash_chunks(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride
 // peer HBM over NVLink for the others (32 bytes per chunk and column: 3 % of the encoded matrix for 8-byte elements).
 // Rank g owns columns [g << log_cb, (g + 1) << log_cb); its store is [n_chunks][1 << log_cb][32 B].
 template <int FID>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, Field<FID>::LIMBS == 1 ? LCPC_HASH_CTAS1 : 5)
 k_hash_chunks_scatter(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t total_bytes,
                       uint64_t n_chunks, int64_t row_base, uint64_t chunk0, uint64_t chunk_end,
                       const __grid_constant__ CvScatter sc) {
@@ -255,6 +310,9 @@ __device__ __forceinline__ void merge_column(uint32_t cv[8], const uint32_t *cvs
     }
 }
 
+// device-scope release / acquire around the ticket counters (MEMBAR.ALL.GPU instead of __threadfence()'s MEMBAR.SC.GPU)
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // first digest of tree level l in the flat array [np2 | np2/2 | ... | 1]
 __device__ __forceinline__ size_t level_offset(size_t np2, int l) { return l == 0 ? 0 : 2 * np2 - (np2 >> (l - 1)); }
 
@@ -281,7 +339,7 @@ __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, u
         const size_t n_out = tile_n >> l;
         if (t < n_out) {
             uint32_t o[8];
-            b3::hash_pair(buf[src][2 * t], buf[src][2 * t + 1], o);
+            b3::hash_pair<true>(buf[src][2 * t], buf[src][2 * t + 1], o);
 #pragma unroll
             for (int k = 0; k < 8; k++) buf[src ^ 1][t][k] = o[k];
             uint4 *g = reinterpret_cast<uint4 *>(hashes + (level_offset(np2, l) + tile * n_out + t) * 32);
@@ -293,7 +351,7 @@ __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, u
     }
     if (n_tiles <= 1) return;
     // publish this tile's root, then take a ticket: the last tile continues with the top of the tree
-    __threadfence();
+    fence_gpu();
     if (t == 0) {
         const unsigned old = atomicAdd(ticket, 1u);
         *s_flag = (old == n_tiles - 1) ? 1u : 0u;
@@ -301,7 +359,7 @@ __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, u
     }
     __syncthreads();
     if (*s_flag == 0) return;
-    __threadfence();
+    fence_gpu();
     int depth = 0;
     while (((size_t)1 << depth) < np2) depth++;
     for (int l = lt + 1; l <= depth; l++) {
@@ -313,12 +371,11 @@ __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, u
             const uint32_t lft[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const uint32_t rgt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint32_t o[8];
-            b3::hash_pair(lft, rgt, o);
+            b3::hash_pair<true>(lft, rgt, o);
             __stcg(out + 2 * i, make_uint4(o[0], o[1], o[2], o[3]));
             __stcg(out + 2 * i + 1, make_uint4(o[4], o[5], o[6], o[7]));
         }
-        __threadfence();
-        __syncthreads();
+        __syncthreads();  // orders this CTA's own stores before its own loads of the next level: no device-wide fence
     }
 }
 
@@ -355,13 +412,20 @@ k_merge_tree(const uint32_t *cvs, size_t n_cols, uint64_t n_chunks, uint8_t *has
 // tickets: 1 + n_tiles zeroed counters, left zeroed.
 constexpr int HT_TILE = 128;
 template <int FID>
-__global__ void __launch_bounds__(HT_TILE, 8)
+__global__ void __launch_bounds__(HT_TILE, LCPC_HASH_CTAS1)
 k_hash_tree(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, size_t n_cols, uint64_t total_bytes,
-            uint64_t n_chunks, uint32_t *cvs, uint8_t *hashes, size_t np2, unsigned *tickets) {
+            uint64_t n_chunks, uint32_t *cvs, uint8_t *hashes, size_t np2, unsigned *tickets, unsigned group) {
     __shared__ uint32_t buf[2][HT_TILE][8];
     __shared__ unsigned s_flag;
-    const uint64_t c = blockIdx.x;
-    const size_t tile = blockIdx.y;
+    // linear CTA id -> (group of `group` adjacent tiles, chunk, tile inside the group), tile fastest: consecutive CTAs
+    // read adjacent 1 KiB segments of the same rows (DRAM pages), and a group's tiles complete together
+    const unsigned n_tiles = (unsigned)((np2 + HT_TILE - 1) / HT_TILE);
+    const unsigned per_group = group * (unsigned)n_chunks;
+    const unsigned g_idx = blockIdx.x / per_group, rem = blockIdx.x % per_group;
+    const unsigned g_tiles = (g_idx + 1) * group <= n_tiles ? group : n_tiles - g_idx * group;  // last group may be short
+    const uint64_t c = rem / g_tiles;
+    const size_t tile = (size_t)g_idx * group + rem % g_tiles;
+    if (c >= n_chunks) return;
     const size_t j = tile * HT_TILE + threadIdx.x;
     uint32_t leaf[8];
 #pragma unroll
@@ -377,7 +441,7 @@ k_hash_tree(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, 
                 __stcg(o, make_uint4(leaf[0], leaf[1], leaf[2], leaf[3]));
                 __stcg(o + 1, make_uint4(leaf[4], leaf[5], leaf[6], leaf[7]));
             }
-            __threadfence();
+            fence_gpu();
             __syncthreads();
             if (threadIdx.x == 0) {
                 const unsigned old = atomicAdd(&tickets[1 + tile], 1u);
@@ -386,7 +450,7 @@ k_hash_tree(const uint64_t *__restrict__ mat, size_t n_rows, size_t row_stride, 
             }
             __syncthreads();
             if (s_flag == 0) return;
-            __threadfence();
+            fence_gpu();
 #pragma unroll
             for (int k = 0; k < 8; k++) leaf[k] = 0;
             if (j < n_cols) merge_column(leaf, cvs, n_cols, n_chunks, j);
@@ -506,17 +570,30 @@ cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, u
 size_t hash_tree_tickets(size_t np2) { return 1 + (np2 + HT_TILE - 1) / HT_TILE; }
 
 bool hash_tree_supported(int fid, size_t n_rows, size_t np2) {
-    return leaf_chunks(fid, n_rows) <= 65535 && (np2 + HT_TILE - 1) / HT_TILE <= 65535;
+    return leaf_chunks(fid, n_rows) * ((np2 + HT_TILE - 1) / HT_TILE + 64) < ((uint64_t)1 << 31);
+}
+
+// One launch pays when the whole grid is resident at once (small commitments: launch- and latency-bound); with several
+// waves of CTAs the per-tile tails run on a few warps while their CTA slots could hash, and two launches win
+// (2^24 Ft63: 0.175 ms against 0.188 ms; profiles/r02_hash_tail.md).
+bool hash_tree_preferred(int fid, size_t n_rows, size_t np2) {
+    return hash_tree_supported(fid, n_rows, np2) && leaf_chunks(fid, n_rows) * ((np2 + HT_TILE - 1) / HT_TILE) <= 148 * 7;
 }
 
 template <int FID>
 static cudaError_t hash_tree_t(const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, size_t np2,
                                uint8_t *d_hashes, uint8_t *d_cvs, unsigned *d_tickets, const Launch &lc) {
     const uint64_t total = leaf_bytes(FID, n_rows), nc = leaf_chunks(FID, n_rows);
-    const dim3 grid((unsigned)nc, (unsigned)((np2 + HT_TILE - 1) / HT_TILE));
+    const unsigned n_tiles = (unsigned)((np2 + HT_TILE - 1) / HT_TILE);
+    // tile-fastest over the whole grid measured best (profiles/r02_hash_tail.md); LCPC_HT_GROUP overrides for experiments
+    unsigned group = n_tiles;
+    if (const char *e = getenv("LCPC_HT_GROUP")) group = (unsigned)atoi(e);
+    if (group == 0 || group > n_tiles) group = n_tiles;
+    const unsigned n_groups = (n_tiles + group - 1) / group;
     lc.begin("k_hash_tree");
-    k_hash_tree<FID><<<grid, HT_TILE, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, total, nc, reinterpret_cast<uint32_t *>(d_cvs),
-                                               d_hashes, np2, d_tickets);
+    k_hash_tree<FID><<<n_groups * group * (unsigned)nc, HT_TILE, 0, lc.s>>>(d_mat, n_rows, row_stride, n_cols, total, nc,
+                                                                         reinterpret_cast<uint32_t *>(d_cvs), d_hashes, np2,
+                                                                         d_tickets, group);
     lc.end();
     return cudaGetLastError();
 }

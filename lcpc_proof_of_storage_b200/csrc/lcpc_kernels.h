@@ -51,6 +51,10 @@ struct NttPlan {
     uint64_t *d_tw = nullptr;  // all twiddle tables, device
     size_t tw_elems = 0;
     SmallTwRaw stw{};
+    // inverse transform: the same tables built from w^-1 (second half of the d_tw allocation), w16^-e, n^-1
+    uint64_t *d_tw_inv = nullptr;
+    SmallTwRaw stw_inv{};
+    uint64_t ninv[MAX_LIMBS] = {0, 0, 0, 0};
 };
 
 // Builds twiddle tables for a 2^log_n-point transform.  root_mont: LIMBS words (host), or
@@ -73,6 +77,9 @@ struct ScatterDst {
 // src == dst (with src_stride == n) is the in-place case.
 cudaError_t ntt_encode(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
                        uint64_t *dst, size_t n_rows, const Launch &lc, const ScatterDst *scatter = nullptr);
+
+// n_rows inverse transforms in place (row stride n): fffft's ifft_oi -- bit-reversed input, in-order output, 1/n scale
+cudaError_t ntt_decode(const NttPlan &plan, uint64_t *data, size_t n_rows, const Launch &lc);
 
 // Column hashing.  d_col_idx == nullptr hashes columns [0, n_cols); otherwise column
 // d_col_idx[j] for j < n_cols.  d_cv_scratch needs hash_scratch_bytes().
@@ -116,6 +123,7 @@ cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, u
                        const Launch &lc);
 size_t hash_tree_tickets(size_t np2);
 bool hash_tree_supported(int fid, size_t n_rows, size_t np2);
+bool hash_tree_preferred(int fid, size_t n_rows, size_t np2);
 cudaError_t hash_tree(int fid, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols, size_t np2,
                       uint8_t *d_hashes, uint8_t *d_cvs, unsigned *d_tickets, const Launch &lc);
 

@@ -11,6 +11,9 @@ template <int FID>
 cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *dst,
                      size_t n_rows, const Launch &lc, const ScatterDst *scatter);
 
+template <int FID>
+cudaError_t decode_t(const NttPlan &plan, uint64_t *data, size_t n_rows, const Launch &lc);
+
 #define LCPC_FIELD_SWITCH(fid, CALL)                  \
     switch (fid) {                                    \
     case FT63: return CALL(FT63);                     \
@@ -35,6 +38,12 @@ void ntt_plan_free(NttPlan &plan) {
 cudaError_t ntt_encode(const NttPlan &plan, const uint64_t *src, size_t src_stride, size_t src_valid,
                        uint64_t *dst, size_t n_rows, const Launch &lc, const ScatterDst *scatter) {
 #define CALL(F) encode_t<F>(plan, src, src_stride, src_valid, dst, n_rows, lc, scatter)
+    LCPC_FIELD_SWITCH(plan.fid, CALL)
+#undef CALL
+}
+
+cudaError_t ntt_decode(const NttPlan &plan, uint64_t *data, size_t n_rows, const Launch &lc) {
+#define CALL(F) decode_t<F>(plan, data, n_rows, lc)
     LCPC_FIELD_SWITCH(plan.fid, CALL)
 #undef CALL
 }

@@ -39,6 +39,38 @@ __device__ __forceinline__ unsigned bitrev_bits(unsigned x, int bits) {
 
 // ------------------------------------------------------------------ plan-time kernels
 
+// inverse transform constants: w^-1 = w^(n-1) and n^-1 = (2^-1)^log_n, 2^-1 = (p + 1) / 2 brought into Montgomery form
+template <int FID>
+__global__ void k_init_inverse(const uint64_t *w_in, int log_n, uint64_t *winv_out, uint64_t *ninv_out) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const E w = ld_fe<L>(w_in);
+    st_fe<L>(winv_out, F::pow(w, ((uint64_t)1 << log_n) - 1));
+    E half, r2;  // (p + 1) / 2: p is odd, so (p >> 1) + 1
+    uint64_t carry = 0;
+#pragma unroll
+    for (int i = L - 1; i >= 0; i--) {
+        const uint64_t pi = F::P(i);
+        half.v[i] = (pi >> 1) | (carry << 63);
+        carry = pi & 1;
+    }
+    uint64_t c = 1;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const uint64_t v = half.v[i] + c;
+        c = v < c ? 1 : 0;
+        half.v[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < L; i++) r2.v[i] = field_consts(FID).r2[i];
+    const E half_m = F::mul(half, r2);
+    E acc = F::one();
+    for (int i = 0; i < log_n; i++) acc = F::mul(acc, half_m);
+    st_fe<L>(ninv_out, acc);
+}
+
 template <int FID>
 __global__ void k_init_root(const uint64_t *root_in, int log_n, uint64_t *w_out, uint64_t *stw_out) {
     using F = Field<FID>;
@@ -357,6 +389,157 @@ k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *
     }
 }
 
+// ------------------------------------------------------------------ inverse transform (fffft ifft_oi)
+
+// Undoes radix_dif: x[j] holds the entry of index bitrev_R(j) on entry, natural order on exit; the factor 1/2 of every
+// butterfly is left out (the caller scales by n^-1 once).  twi = powers of w16^-1.
+template <int FID, int R>
+__device__ __forceinline__ void radix_dit_inv(typename Field<FID>::E (&x)[1 << R], const SmallTw<FID> &twi) {
+    using F = Field<FID>;
+    using E = typename F::E;
+#pragma unroll
+    for (int t = R - 1; t >= 0; t--) {
+        const int gap = 1 << (R - 1 - t);
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++) {
+            if ((j & gap) == 0) {
+                const int e16 = ((j & (gap - 1)) << t) << (4 - R);
+                const E a = x[j];
+                const E b = (e16 == 0) ? x[j + gap] : F::mul(x[j + gap], twi.w[e16]);
+                x[j] = F::add(a, b);
+                x[j + gap] = F::sub(a, b);
+            }
+        }
+    }
+}
+
+// Inverse of one strided pass, in place: divide by the pass twiddles (the table built from w^-1), then the inverse
+// register radix.  SCALE: this is the last inverse pass, multiply by n^-1 on the way out.
+template <int FID, int R>
+__global__ void __launch_bounds__(256, 2)
+k_intt_strided(uint64_t *data, size_t n, size_t n_rows, int log_sub, const uint64_t *__restrict__ twi,
+               const __grid_constant__ SmallTw<FID> stwi, const __grid_constant__ typename Field<FID>::E ninv, int scale) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    const int log_n2 = log_sub - R;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (n >> R)) return;
+    const size_t hi = g >> log_n2, lo = g & (((size_t)1 << log_n2) - 1);
+    const size_t base = (hi << log_sub) + lo;
+    for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        E x[1 << R];
+        uint64_t *io = data + (row * n + base) * L;
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) x[m] = ld_fe<L>(io + ((size_t)m << log_n2) * L);
+        if (log_n2 > 0) {
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(twi + (((size_t)m << log_n2) + lo) * L));
+        }
+        radix_dit_inv<FID, R>(x, stwi);
+        if (scale) {
+#pragma unroll
+            for (int m = 0; m < (1 << R); m++) x[m] = F::mul(x[m], ninv);
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) st_fe<L>(io + ((size_t)m << log_n2) * L, x[m]);
+    }
+}
+
+template <int FID, int R>
+__device__ __forceinline__ void block_substep_inv(uint64_t *sm, unsigned plane, int LB, int log_sub,
+                                                  const uint64_t *__restrict__ twi, const SmallTw<FID> &stwi) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    const int log_n2 = log_sub - R;
+    const unsigned groups = (1u << LB) >> R;
+    for (unsigned g = threadIdx.x; g < groups; g += blockDim.x) {
+        const unsigned hi = g >> log_n2, lo = g & ((1u << log_n2) - 1);
+        const unsigned base = (hi << log_sub) + lo;
+        E x[1 << R];
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            const unsigned p = sm_phys(base + ((unsigned)m << log_n2));
+#pragma unroll
+            for (int l = 0; l < L; l++) x[m].v[l] = sm[l * plane + p];
+        }
+        if (log_n2 > 0) {
+#pragma unroll
+            for (int m = 1; m < (1 << R); m++) x[m] = F::mul(x[m], ld_fe<L>(twi + (size_t)(((unsigned)m << log_n2) + lo) * L));
+        }
+        radix_dit_inv<FID, R>(x, stwi);
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            const unsigned p = sm_phys(base + ((unsigned)m << log_n2));
+#pragma unroll
+            for (int l = 0; l < L; l++) sm[l * plane + p] = x[m].v[l];
+        }
+    }
+}
+
+// Inverse of the block pass: the sub-steps of k_ntt_block in reverse order on a block held in shared memory.
+template <int FID, int RMAX>
+__global__ void __launch_bounds__(256, 2)
+k_intt_block(uint64_t *data, size_t n, size_t n_rows, int LB, const uint64_t *__restrict__ twi,
+             const __grid_constant__ SmallTw<FID> stwi, const __grid_constant__ typename Field<FID>::E ninv, int scale) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    constexpr int L = F::LIMBS;
+    extern __shared__ uint64_t sm[];
+    const unsigned NB = 1u << LB;
+    const unsigned plane = NB + (NB >> 4) + 1;
+    const size_t col0 = (size_t)blockIdx.x << LB;
+    // forward sub-steps (log_sub, R, table offset), replayed backwards
+    int ls_list[16], r_list[16];
+    size_t off_list[16];
+    int n_steps = 0;
+    {
+        int log_sub = LB;
+        size_t off = 0;
+        while (log_sub > 0) {
+            const int R = log_sub < RMAX ? log_sub : RMAX;
+            ls_list[n_steps] = log_sub;
+            r_list[n_steps] = R;
+            off_list[n_steps] = off;
+            n_steps++;
+            if (log_sub - R > 0) off += (size_t)1 << log_sub;
+            log_sub -= R;
+        }
+    }
+    for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        uint64_t *io = data + (row * n + col0) * L;
+        for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) {
+            const E v = ld_fe<L>(io + (size_t)i * L);
+            const unsigned p = sm_phys(i);
+#pragma unroll
+            for (int l = 0; l < L; l++) sm[l * plane + p] = v.v[l];
+        }
+        __syncthreads();
+        for (int k = n_steps - 1; k >= 0; k--) {
+            const uint64_t *t = twi + off_list[k] * L;
+            switch (r_list[k]) {
+            case 4:
+                if constexpr (RMAX >= 4) block_substep_inv<FID, 4>(sm, plane, LB, ls_list[k], t, stwi);
+                break;
+            case 3: block_substep_inv<FID, 3>(sm, plane, LB, ls_list[k], t, stwi); break;
+            case 2: block_substep_inv<FID, 2>(sm, plane, LB, ls_list[k], t, stwi); break;
+            default: block_substep_inv<FID, 1>(sm, plane, LB, ls_list[k], t, stwi); break;
+            }
+            __syncthreads();
+        }
+        for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) {
+            E v;
+            const unsigned p = sm_phys(i);
+#pragma unroll
+            for (int l = 0; l < L; l++) v.v[l] = sm[l * plane + p];
+            if (scale) v = F::mul(v, ninv);
+            st_fe<L>(io + (size_t)i * L, v);
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ host side
 
 static int block_bits_max(int limbs) { return limbs == 1 ? 12 : (limbs == 2 ? 11 : 10); }
@@ -396,8 +579,8 @@ cudaError_t plan_build_t(NttPlan &plan, int log_n, const uint64_t *root_mont, co
     }
     plan.tw_elems = tw_elems;
     cudaError_t e;
-    uint64_t *d_consts = nullptr;  // [w_n | stw(8)] | optional root_in
-    if ((e = cudaMalloc(&d_consts, (size_t)(1 + 8 + 1) * L * sizeof(uint64_t))) != cudaSuccess) return e;
+    uint64_t *d_consts = nullptr;  // [w_n | stw(8)] | optional root_in | [w_n^-1 | stw_inv(8)] | n^-1
+    if ((e = cudaMalloc(&d_consts, (size_t)(1 + 8 + 1 + 1 + 8 + 1) * L * sizeof(uint64_t))) != cudaSuccess) return e;
     uint64_t *d_root_in = nullptr;
     if (root_mont != nullptr) {
         d_root_in = d_consts + 9 * L;
@@ -409,17 +592,29 @@ cudaError_t plan_build_t(NttPlan &plan, int log_n, const uint64_t *root_mont, co
     lc.begin("k_init_root");
     k_init_root<FID><<<1, 1, 0, lc.s>>>(d_root_in, log_n, d_consts, d_consts + L);
     lc.end();
+    // the inverse transform (ifft_oi) uses the same tables built from w^-1, stored behind the forward ones
+    uint64_t *d_inv = d_consts + 10 * L;  // [w^-1 | stw_inv(8)], then n^-1 at d_consts + 19 L
+    lc.begin("k_init_inverse");
+    k_init_inverse<FID><<<1, 1, 0, lc.s>>>(d_consts, log_n, d_inv, d_consts + 19 * L);
+    lc.end();
+    lc.begin("k_init_root");
+    k_init_root<FID><<<1, 1, 0, lc.s>>>(d_inv, log_n, d_inv, d_inv + L);
+    lc.end();
     if (tw_elems > 0) {
-        if ((e = cudaMalloc(&plan.d_tw, tw_elems * L * sizeof(uint64_t))) != cudaSuccess) {
+        if ((e = cudaMalloc(&plan.d_tw, 2 * tw_elems * L * sizeof(uint64_t))) != cudaSuccess) {
             cudaFree(d_consts);
             return e;
         }
+        plan.d_tw_inv = plan.d_tw + tw_elems * L;
     }
     auto build = [&](size_t off, int ls, int r) {
         size_t total = (size_t)1 << ls;
         unsigned blocks = (unsigned)((total + 255) / 256);
         lc.begin("k_build_twiddles");
         k_build_twiddles<FID><<<blocks, 256, 0, lc.s>>>(plan.d_tw + off * L, d_consts, (uint64_t)1 << (log_n - ls), r, ls - r);
+        lc.end();
+        lc.begin("k_build_twiddles");
+        k_build_twiddles<FID><<<blocks, 256, 0, lc.s>>>(plan.d_tw_inv + off * L, d_inv, (uint64_t)1 << (log_n - ls), r, ls - r);
         lc.end();
     };
     for (const NttPass &p : plan.passes) {
@@ -438,14 +633,19 @@ cudaError_t plan_build_t(NttPlan &plan, int log_n, const uint64_t *root_mont, co
             }
         }
     }
-    uint64_t h_stw[8 * L];
+    uint64_t h_stw[8 * L], h_inv[10 * L];
     e = cudaMemcpyAsync(h_stw, d_consts + L, sizeof h_stw, cudaMemcpyDeviceToHost, lc.s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_inv, d_inv + L, sizeof h_inv - L * sizeof(uint64_t), cudaMemcpyDeviceToHost, lc.s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(lc.s);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFree(d_consts);
     if (e != cudaSuccess) return e;
     for (int i = 0; i < 8; i++)
-        for (int l = 0; l < MAX_LIMBS; l++) plan.stw.w[i][l] = l < L ? h_stw[i * L + l] : 0;
+        for (int l = 0; l < MAX_LIMBS; l++) {
+            plan.stw.w[i][l] = l < L ? h_stw[i * L + l] : 0;
+            plan.stw_inv.w[i][l] = l < L ? h_inv[i * L + l] : 0;
+        }
+    for (int l = 0; l < MAX_LIMBS; l++) plan.ninv[l] = l < L ? h_inv[8 * L + l] : 0;  // n^-1 sits right behind stw_inv
     return cudaSuccess;
 }
 
@@ -550,6 +750,53 @@ cudaError_t encode_t(const NttPlan &plan, const uint64_t *src, size_t src_stride
         }
         lc.end();
         first = false;
+    }
+    return cudaGetLastError();
+}
+
+// n_rows independent inverse transforms in place (rows of stride n): bit-reversed input, in-order output, scaled by
+// 1/n -- fffft's ifft_oi, so decode(encode(x)) == x.  The forward passes are undone last to first.
+template <int FID>
+cudaError_t decode_t(const NttPlan &plan, uint64_t *data, size_t n_rows, const Launch &lc) {
+    using F = Field<FID>;
+    constexpr int L = F::LIMBS;
+    constexpr int RMAX = L <= 2 ? 4 : 3;
+    if (n_rows == 0 || plan.log_n == 0) return cudaSuccess;
+    SmallTw<FID> stwi;
+    typename F::E ninv;
+    for (int i = 0; i < 8; i++)
+        for (int l = 0; l < L; l++) stwi.w[i].v[l] = plan.stw_inv.w[i][l];
+    for (int l = 0; l < L; l++) ninv.v[l] = plan.ninv[l];
+    const size_t n = plan.n;
+    const unsigned gy = (unsigned)(n_rows < 65535 ? n_rows : 65535);
+    for (size_t k = plan.passes.size(); k-- > 0;) {
+        const NttPass &p = plan.passes[k];
+        const uint64_t *twi = plan.d_tw_inv + p.tw_off * L;
+        const int scale = k == 0 ? 1 : 0;
+        if (p.kind == 0) {
+            const size_t groups = n >> p.bits;
+            dim3 grid((unsigned)((groups + 255) / 256), gy);
+            lc.begin("k_intt_strided");
+            switch (p.bits) {
+            case 1: k_intt_strided<FID, 1><<<grid, 256, 0, lc.s>>>(data, n, n_rows, p.log_sub, twi, stwi, ninv, scale); break;
+            case 2: k_intt_strided<FID, 2><<<grid, 256, 0, lc.s>>>(data, n, n_rows, p.log_sub, twi, stwi, ninv, scale); break;
+            case 3: k_intt_strided<FID, 3><<<grid, 256, 0, lc.s>>>(data, n, n_rows, p.log_sub, twi, stwi, ninv, scale); break;
+            default:
+                if constexpr (RMAX >= 4) k_intt_strided<FID, 4><<<grid, 256, 0, lc.s>>>(data, n, n_rows, p.log_sub, twi, stwi, ninv, scale);
+                break;
+            }
+        } else {
+            const int LB = p.bits;
+            const size_t NB = (size_t)1 << LB;
+            const size_t plane = NB + (NB >> 4) + 1;
+            const size_t smem = plane * L * sizeof(uint64_t);
+            size_t thr = NB >> RMAX;
+            thr = thr < 32 ? 32 : (thr > 256 ? 256 : thr);
+            dim3 grid((unsigned)(n >> LB), gy);
+            lc.begin("k_intt_block");
+            k_intt_block<FID, RMAX><<<grid, (unsigned)thr, smem, lc.s>>>(data, n, n_rows, LB, twi, stwi, ninv, scale);
+        }
+        lc.end();
     }
     return cudaGetLastError();
 }

@@ -106,6 +106,15 @@ class Context:
         check(_lib.load().lcpc_ctx_stream(self._h, C.byref(out)))
         return int(out.value or 0)
 
+    def measure_int_pipes(self) -> dict:
+        """Integer-pipe issue rates of this device (lcpc_ctx_measure_int_pipes): SM sub-partition cycles per warp
+        instruction for IMAD.WIDE / IMAD / LOP3 / an IMAD + LOP3 mix, and the SM clock seen during the measurement."""
+        cyc = (C.c_double * 4)()
+        ghz = C.c_double()
+        check(_lib.load().lcpc_ctx_measure_int_pipes(self._h, cyc, C.byref(ghz)))
+        return {"cycles_per_warp_instr": {"imad_wide": cyc[0], "imad": cyc[1], "lop3": cyc[2], "imad_lop3_mix": cyc[3]},
+                "sm_ghz": ghz.value}
+
     def launch_count(self) -> int:
         return int(_lib.load().lcpc_ctx_launch_count(self._h))
 
@@ -208,6 +217,14 @@ class _Encoding:
         rows = inp.size // (self.n_cols * self.limbs)
         assert rows * self.n_cols * self.limbs == inp.size, "row length must be n_cols"
         _prover_call(_lib.load().lcpc_encode_rows(self._plan, _ptr(inp), rows))
+
+    def decode(self, inp: np.ndarray) -> None:
+        """fffft ifft_oi on one row (or a batch of rows) of n_cols encoded elements, in place: decode(encode(x)) == x
+        (proof-of-storage decode_row, lcpc_online.rs:568-573).  Ligero encodings only."""
+        assert inp.dtype == np.uint64 and inp.flags["C_CONTIGUOUS"]
+        rows = inp.size // (self.n_cols * self.limbs)
+        assert rows * self.n_cols * self.limbs == inp.size, "row length must be n_cols"
+        _prover_call(_lib.load().lcpc_decode_rows(self._plan, _ptr(inp), rows))
 
     def close(self) -> None:
         if getattr(self, "_plan", None):

@@ -266,6 +266,13 @@ def client_verify_commitment(commitment_root: bytes, locally_derived_column_leav
     client_online_verify_column_paths(commitment_root, requested_columns, received_columns, ctx, field)
 
 
+def decode_row(row: np.ndarray, enc: LigeroEncoding) -> np.ndarray:
+    """lcpc_online.rs:568-573: the coefficients (zero padded to n_cols) of one encoded row, or of a batch of rows."""
+    out = np.array(row, dtype=np.uint64, copy=True, order="C")
+    enc.decode(out)
+    return out
+
+
 def verifiable_polynomial_evaluation(commitment: LcCommit, left_evaluation_column: np.ndarray) -> np.ndarray:
     """lcpc_online.rs:454-484: result[j] = sum_r left[r] * comm[r][j] over the ENCODED matrix."""
     return commitment.fold(np.ascontiguousarray(left_evaluation_column, dtype=np.uint64).reshape(1, -1, 1), encoded=True)[0]

@@ -151,6 +151,24 @@ class GpuOps:
                                               tensors.data_ptr(), n_tensors, out.data_ptr()))
         return out
 
+    def gather_columns(self, mat: torch.Tensor, n_rows: int, row_stride: int, d_cols: torch.Tensor) -> torch.Tensor:
+        """out[i][r] = mat[r][cols[i]]: [n, n_rows * L] int64 on the device (k_gather_columns)."""
+        n = d_cols.numel()
+        out = torch.empty(n, n_rows * self.L, dtype=torch.int64, device=self.device)
+        if n and n_rows:
+            _lib.check(self.lib.lcpc_dev_gather_columns(self.enc.ctx.handle, self.fid, mat.data_ptr(), n_rows, row_stride,
+                                                        d_cols.data_ptr(), n, out.data_ptr()))
+        return out
+
+    def gather_paths(self, tree: torch.Tensor, n_leaves: int, d_cols: torch.Tensor) -> torch.Tensor:
+        """Sibling digests of every index inside a flat tree over n_leaves: [n, log2(n_leaves), 32] uint8 (k_gather_paths)."""
+        n, depth = d_cols.numel(), log2(n_leaves)
+        out = torch.empty(n, depth, 32, dtype=torch.uint8, device=self.device)
+        if n and depth:
+            _lib.check(self.lib.lcpc_dev_gather_paths(self.enc.ctx.handle, tree.data_ptr(), n_leaves, d_cols.data_ptr(), n,
+                                                      out.data_ptr()))
+        return out
+
     def add_partials(self, parts: torch.Tensor, n_parts: int, n: int) -> torch.Tensor:
         out = torch.empty(n * self.L, dtype=torch.int64, device=self.device)
         _lib.check(self.lib.lcpc_dev_add_partials(self.enc.ctx.handle, self.fid, parts.data_ptr(), n_parts, n,
@@ -498,6 +516,47 @@ class ShardedLigeroCommitter:
         return out.contiguous().view(-1)
 
     # ------------------------------------------------------------------ open
+    def open_columns_dev(self, cols: Sequence[int]):
+        """open_column for each index with everything on the device (row-sharded matrix, GPU back end): every rank
+        gathers its rows of the requested columns (k_gather_columns) and the path levels inside its own subtree
+        (k_gather_paths), ONE all-gather moves both, and rank 0 assembles [n, n_rows, L] column values and
+        [n, depth, 32] paths with the siblings above the subtree roots appended.  Returns the two device tensors on rank
+        0, None elsewhere.  The retrievability proof of proof-of-storage (networking/client.rs:443-456,
+        lcpc_online.rs:226-237) is this call on 309 columns."""
+        L, cb, W = self.L, self.cb, self.world
+        assert self.hashing == "rows" and self.comm_rows is not None
+        n = len(cols)
+        dev = self.comm_rows.device
+        idx = torch.tensor(list(cols), dtype=torch.int64, device=dev)
+        max_rows = max(cnt for _, cnt in self.rows)
+        depth = log2(self.n_cols)
+        depth_sub = min(depth, log2(cb))
+        vw = max_rows * L
+        payload = torch.zeros(n, vw + depth_sub * 4, dtype=torch.int64, device=dev)
+        if self.rows_local:
+            payload[:, :self.rows_local * L] = self.ops.gather_columns(self.comm_rows, self.rows_local, self.n_cols, idx)
+        if depth_sub:
+            # every rank gathers from its own subtree at the column's offset inside a block; rank 0 keeps the owner's
+            local = idx & (cb - 1)
+            payload[:, vw:] = self.ops.gather_paths(self.subtree, cb, local).view(n, depth_sub * 32).view(torch.int64)
+        if W > 1:
+            allp = torch.empty(W, n, vw + depth_sub * 4, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allp.view(-1), payload.view(-1), group=self.group)
+        else:
+            allp = payload.view(1, n, -1)
+        if self.rank != 0:
+            return None
+        vals = torch.cat([allp[q, :, :cnt * L] for q, (_, cnt) in enumerate(self.rows)], dim=1).view(n, self.n_rows, L)
+        owner = idx // cb
+        ar = torch.arange(n, device=dev)
+        parts = []
+        if depth_sub:
+            parts.append(allp[owner, ar, vw:].contiguous().view(torch.uint8).view(n, depth_sub, 32))
+        if depth > depth_sub:
+            parts.append(self.ops.gather_paths(self.top, W, owner))
+        paths = torch.cat(parts, dim=1) if parts else torch.empty(n, 0, 32, dtype=torch.uint8, device=dev)
+        return vals, paths
+
     def open_columns(self, cols: Sequence[int]) -> Optional[List[LcColumn]]:
         """open_column (lcpc-2d/src/lib.rs:818-855) for each index.  The owner of a column block sends
         the column values together with the part of the Merkle path that lies inside its subtree;
@@ -511,6 +570,13 @@ class ShardedLigeroCommitter:
                 from .lcpc2d import ProverError
 
                 raise ProverError("ColumnNumber", "bad column number")
+        if self.hashing == "rows" and hasattr(self.ops, "gather_paths"):
+            res = self.open_columns_dev(cols)
+            if res is None:
+                return None
+            vals = res[0].cpu().numpy().view(np.uint64)   # one device -> host copy each
+            paths = res[1].cpu().numpy()
+            return [LcColumn(vals[k], paths[k]) for k in range(len(cols))]
         by_rows = self.hashing == "rows"  # the encoded matrix is row-sharded: values come from every rank, paths from the owner
         dev = (self.comm_rows if by_rows else self.comm_cols).device
         val_w = 0 if by_rows else self.n_rows * L  # words of column values in an owner's payload

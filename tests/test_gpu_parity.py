@@ -51,6 +51,54 @@ def test_ligero_encode_large_rows(P, oracle, fid, log_n):
     assert np.array_equal(got, O.fft_io(fid, rows))
 
 
+@pytest.mark.parametrize("fid", FIELDS)
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 16])
+def test_ligero_decode_rows_match_ifft_oi(P, oracle, fid, log_n):
+    """decode_row == fffft ifft_oi on whole rows (proof-of-storage/src/lcpc_online.rs:568-573), and it undoes encode."""
+    O = oracle
+    n = 1 << log_n
+    n_rows = 3 if log_n < 14 else 2
+    rows = _rand(O, fid, 2000 + log_n, n_rows * n).reshape(n_rows, n, -1)
+    enc = P.LigeroEncoding(fid, max(1, n // 2), n)
+    got = rows.copy()
+    enc.decode(got)
+    assert np.array_equal(got, O.ifft_oi(fid, rows))
+    enc.encode(got)
+    assert np.array_equal(got, rows)          # encode(decode(y)) == y
+    enc.encode(got)
+    enc.decode(got)
+    assert np.array_equal(got, rows)          # decode(encode(x)) == x
+
+
+@pytest.mark.parametrize("fid,log_n", [(0, 17), (0, 18), (0, 20), (1, 17), (3, 15), (4, 15)])
+def test_ligero_decode_large_rows(P, oracle, fid, log_n):
+    """Rows with strided passes in front of the block pass (2^20: the shape the fused two-pass encode kernel takes)."""
+    O = oracle
+    n = 1 << log_n
+    rows = _rand(O, fid, 78, n).reshape(1, n, -1)
+    enc = P.LigeroEncoding(fid, n // 2, n)
+    got = rows.copy()
+    enc.decode(got)
+    assert np.array_equal(got, O.ifft_oi(fid, rows))
+    enc.encode(got)
+    assert np.array_equal(got, rows)
+
+
+def test_decode_custom_root_and_errors(P, oracle):
+    O = oracle
+    fid, log_n = 0, 10
+    n = 1 << log_n
+    rows = _rand(O, fid, 6, n).reshape(1, n, -1)
+    enc = P.LigeroEncoding(fid, n // 2, n, root_of_unity=O.ntt_root(fid, log_n))
+    got = rows.copy()
+    enc.decode(got)
+    assert np.array_equal(got, O.ifft_oi(fid, rows))
+    senc = P.SdigEncoding.new(0, 3000, seed=0)
+    with pytest.raises(P.ProverError) as ei:
+        senc.decode(np.zeros((1, senc.n_cols, 1), dtype=np.uint64))
+    assert ei.value.variant == "Encode"
+
+
 def test_ligero_custom_root_of_unity(P, oracle):
     """The plan takes the n-th root from the caller (Rust passes F::ROOT_OF_UNITY.pow(2^(S-k)))."""
     O = oracle

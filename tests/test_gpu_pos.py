@@ -71,6 +71,18 @@ def test_upload_then_retrievability_proof(P, pos, oracle, n_bytes, dims):
     assert ei.value.variant == "ColumnEval"
 
 
+def test_encode_then_decode_row(P, pos, oracle):
+    """The reference's own test (lcpc_online.rs:588-601): commit a short vector as a single-row matrix, decode the encoded
+    row, get the coefficients back."""
+    O = oracle
+    row = O.random_field_elements(0, 17, 4)
+    enc = P.LigeroEncoding(0, 1 << 4, 1 << 8)
+    commit = P.LcCommit.commit(row, enc)
+    back = pos.decode_row(commit.comm.reshape(commit.n_rows, 1 << 8, 1), enc)
+    assert np.array_equal(back[0, :16], commit.coeffs.reshape(-1, 1)[:16])
+    assert not back[0, 16:].any()
+
+
 def test_polynomial_evaluation_tall_vs_wide(P, pos, oracle):
     """lcpc_online.rs:629-674 / networking/tests.rs:374-466: the fold of the encoded matrix decodes to
     the fold of the file's elements, and evaluating through a tall or a wide layout agrees."""
@@ -87,6 +99,8 @@ def test_polynomial_evaluation_tall_vs_wide(P, pos, oracle):
         folded = pos.verifiable_polynomial_evaluation(comm, left)
         assert np.array_equal(folded, O.collapse_columns(0, comm.comm, left))
         poly = O.from_mont(0, O.ifft_oi(0, folded.reshape(1, enc, 1))[0])
+        # decode_row on the GPU (lcpc_online.rs:568-573) gives the same coefficients
+        assert O.from_mont(0, pos.decode_row(folded.reshape(1, enc, 1), comm.enc)[0]) == poly
         assert all(v == 0 for v in poly[pre:])
         results.append(sum(c * pow(x, j, p) for j, c in enumerate(poly[:pre])) % p)
     direct = sum(c * pow(x, i, p) for i, c in enumerate(O.from_mont(0, elems))) % p
