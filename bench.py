@@ -749,13 +749,18 @@ def main() -> None:
         h_top = torch.empty((2 * world - 1) * 32, dtype=torch.uint8).pin_memory()
 
         def e2e_sharded_step(full: bool):
-            d = h_coeffs.cuda(non_blocking=True)
-            sc.commit(d)
+            if by_rows:  # PCIe in, encode and PCIe out overlapped over row chunks (ShardedLigeroCommitter.commit_host)
+                sc.commit_host(h_coeffs, h_comm if full else None)
+            else:
+                sc.commit(h_coeffs.cuda(non_blocking=True))
+                if full:
+                    h_comm.copy_(sc.comm_cols, non_blocking=True)
             if full:
-                h_comm.copy_(sc.comm_rows if by_rows else sc.comm_cols, non_blocking=True)
                 h_sub.copy_(sc.subtree, non_blocking=True)
                 if rank == 0:
                     h_top.copy_(sc.top, non_blocking=True)
+                if by_rows:
+                    sc.wait_host_copies()
                 torch.cuda.synchronize()
             elif rank == 0:
                 sc.root()  # device -> host read of the result
@@ -781,11 +786,11 @@ def main() -> None:
         e2e = {"value": n_total * e2e_steps / dt_full, "unit": UNIT, "h2d_bytes_per_step": n_local * 8 * world,
                "d2h_bytes_per_step": d2h_full, "ms_per_step": 1e3 * dt_full / e2e_steps, "steps": e2e_steps,
                "shape": "full LcCommit out (comm + hashes)",
-               "api": "ShardedLigeroCommitter.commit (pinned host row shards in; every rank's encoded rows and Merkle subtree "
-                      "to its pinned host buffers, top of the tree on rank 0)",
+               "api": "ShardedLigeroCommitter.commit_host (pinned host row shards in; every rank's encoded rows and Merkle subtree "
+                      "to its pinned host buffers, top of the tree on rank 0; PCIe in / encode / PCIe out overlapped over row chunks)",
                "root_only": {"value": n_total * e2e_steps / dt_root, "unit": UNIT, "ms_per_step": 1e3 * dt_root / e2e_steps,
                              "h2d_bytes_per_step": n_local * 8 * world, "d2h_bytes_per_step": 32,
-                             "api": "ShardedLigeroCommitter.commit (pinned host row shards in; Merkle root out on rank 0)"}}
+                             "api": "ShardedLigeroCommitter.commit_host (pinned host row shards in; Merkle root out on rank 0)"}}
 
     if rank != 0:
         if dist is not None:

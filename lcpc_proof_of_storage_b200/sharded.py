@@ -91,6 +91,11 @@ class GpuOps:
             _lib.check(self.lib.lcpc_dev_encode(self.enc.plan, coeffs.data_ptr(), n_rows, comm.data_ptr()))
         return comm
 
+    def encode_into(self, coeffs: torch.Tensor, n_rows: int, comm: torch.Tensor) -> None:
+        """Encode n_rows rows of `coeffs` into the preallocated `comm` (both may be slices of larger buffers)."""
+        if n_rows:
+            _lib.check(self.lib.lcpc_dev_encode(self.enc.plan, coeffs.data_ptr(), n_rows, comm.data_ptr()))
+
     def encode_scatter(self, coeffs: torch.Tensor, n_rows: int, row0: int, scratch: torch.Tensor, peer_ptrs) -> None:
         """Fused encode + re-shard: the transform's last pass stores each row block straight into the
         owning rank's column-block matrix (peer HBM over NVLink), see lcpc_dev_encode_scatter."""
@@ -242,6 +247,11 @@ class ShardedLigeroCommitter:
         self._symm = self._hdl = self._peer_ptrs = self._scratch = None
         self._pending: Optional[int] = None  # buffer index of a commit whose exchange is issued but not yet hashed
         want = fused if fused is not None else (isinstance(self.ops, GpuOps) and self.world > 1)
+        # the transform's last pass stores whole shared-memory blocks (2^12 / 2^11 / 2^10 elements for 1 / 2 / 3-4 limbs): a
+        # column block must hold at least one
+        ntt_block = 1 << min(log2(self.n_cols), {1: 12, 2: 11}.get(self.L, 10))
+        if fused is None and self.cb < ntt_block:
+            want = False
         if want and isinstance(self.ops, GpuOps) and self.world > 1 and self.np2 == self.n_cols and self.world <= 16:
             try:
                 import ctypes as C
@@ -339,6 +349,51 @@ class ShardedLigeroCommitter:
             recv = send.view(-1)
         self.comm_cols = recv  # row-major [n_rows_total, cb, L] because row blocks arrive in rank order
         self._finish_tree(dev)
+
+    def commit_host(self, h_coeffs: torch.Tensor, h_comm: Optional[torch.Tensor] = None, n_chunks: int = 8) -> None:
+        """End-to-end form of commit() for row hashing: this rank's coefficient rows come from PINNED host memory and, when
+        `h_comm` is given, its encoded rows go back to pinned host memory, with the three stages overlapped over row
+        chunks the way lcpc_commit_host does it on one GPU: chunk k+1 crosses PCIe while chunk k is encoded and chunk k-1
+        leaves (copy streams on both sides of torch's current stream).  Column hashing needs every row and follows the
+        last chunk.  Bit-identical to commit(): rows are independent."""
+        assert self.hashing == "rows" and isinstance(self.ops, GpuOps), "commit_host: row hashing on the GPU back end"
+        L, npr, nc = self.L, self.n_per_row, self.n_cols
+        dev = self.ops.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_s_in", None) is None:
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._h_coeffs_dev = torch.empty(max(1, self.rows_local) * npr * L, dtype=torch.int64, device=dev)
+            self._h_comm_dev = torch.empty(max(1, self.rows_local) * nc * L, dtype=torch.int64, device=dev)
+        d_coeffs, comm = self._h_coeffs_dev, self._h_comm_dev
+        # the previous call's copies out of `comm` and its kernels reading `d_coeffs` are done before either is rewritten
+        main.wait_stream(self._s_out)
+        self._s_in.wait_stream(main)
+        rows = self.rows_local
+        k = max(1, min(n_chunks, rows))
+        per = (rows + k - 1) // k
+        for r0 in range(0, rows, per):
+            nr = min(per, rows - r0)
+            a, b = r0 * npr * L, (r0 + nr) * npr * L
+            with torch.cuda.stream(self._s_in):
+                d_coeffs[a:b].copy_(h_coeffs[a:b], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._s_in)
+            main.wait_event(ev_in)
+            ca, cb_ = r0 * nc * L, (r0 + nr) * nc * L
+            self.ops.encode_into(d_coeffs[a:b], nr, comm[ca:cb_])
+            if h_comm is not None:
+                ev_enc = torch.cuda.Event()
+                ev_enc.record(main)
+                self._s_out.wait_event(ev_enc)
+                with torch.cuda.stream(self._s_out):
+                    h_comm[ca:cb_].copy_(comm[ca:cb_], non_blocking=True)
+        self.coeffs_local = d_coeffs
+        self._commit_row_hashed(comm, dev)
+
+    def wait_host_copies(self) -> None:
+        """Joins commit_host's device -> host copies onto torch's current stream."""
+        if getattr(self, "_s_out", None) is not None:
+            torch.cuda.current_stream(self.ops.device).wait_stream(self._s_out)
 
     def _commit_row_hashed(self, comm: torch.Tensor, dev) -> None:
         """Chunk chaining values of all columns from my rows, an all-to-all of those (32 bytes per chunk and column),
