@@ -108,6 +108,21 @@ int32_t lcpc_field_constants(int32_t field, uint64_t *modulus, uint64_t *one_mon
 int32_t lcpc_ctx_create(int32_t device, lcpc_ctx **out);
 /* Context that enqueues on a caller-owned cudaStream_t (e.g. torch's current stream). */
 int32_t lcpc_ctx_create_on_stream(int32_t device, void *cuda_stream, lcpc_ctx **out);
+/* Context over several devices of this process (the contract's `lcpc_ctx_create(devices, n)`):
+ * n_devices a power of two <= 16, peer access between every pair is enabled inside the library.  Plans made on such a
+ * context are built on every device, and lcpc_commit_host / lcpc_commit_bytes_host through them shard the commitment:
+ * rows over the devices for encoding (row blocks cut on BLAKE3 chunk boundaries of the column leaves), every device hashes
+ * the chunks of all columns over its own rows and stores the 32-byte chaining values straight into the store of the device
+ * that owns the column block (peer HBM over NVLink), each device builds its Merkle subtree and the first device joins
+ * the subtree roots.  lcpc_commit_root / _download / lcpc_fold_host / lcpc_open_columns_host / lcpc_leaves_host /
+ * lcpc_prove work on the resulting handle unchanged, with bit-identical results.  Commitments too small to give every
+ * device a BLAKE3 chunk of rows (and 24-byte elements, which straddle chunks) run on the first device, as do the
+ * single-row and verifier entry points (lcpc_encode_rows, lcpc_decode_rows, lcpc_verify, lcpc_stream_*).  Row edits
+ * (lcpc_commit_update_rows_host / _append_rows_host) and lcpc_commit_device_ptrs are refused on a sharded handle.
+ * A device may be listed more than once (its shards then share it). */
+int32_t lcpc_ctx_create_multi(const int32_t *devices, int32_t n_devices, lcpc_ctx **out);
+/* Devices of a context: 1 for lcpc_ctx_create / _on_stream, n_devices for lcpc_ctx_create_multi. */
+int32_t lcpc_ctx_device_count(const lcpc_ctx *ctx);
 int32_t lcpc_ctx_synchronize(lcpc_ctx *ctx);
 /* The cudaStream_t every call on this context enqueues on (borrowed).  A caller that mixes the device-pointer entry
  * points with its own work on the same buffers must either enqueue that work on this stream or order the two streams

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "lcpc_field_constants": (C.c_int32, [C.c_int32, u64p, u64p, u64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lcpc_ctx_create": (C.c_int32, [C.c_int32, vpp]),
     "lcpc_ctx_create_on_stream": (C.c_int32, [C.c_int32, C.c_void_p, vpp]),
+    "lcpc_ctx_create_multi": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, vpp]),
+    "lcpc_ctx_device_count": (C.c_int32, [C.c_void_p]),
     "lcpc_ctx_synchronize": (C.c_int32, [C.c_void_p]),
     "lcpc_ctx_stream": (C.c_int32, [C.c_void_p, vpp]),
     "lcpc_ctx_measure_int_pipes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "liblcpc_b200.so")
-SOURCES = ["lcpc_ntt_f0.cu", "lcpc_ntt_f1.cu", "lcpc_ntt_f2.cu", "lcpc_ntt_f3.cu", "lcpc_ntt_f4.cu", "lcpc_ntt.cu", "lcpc_hash.cu", "lcpc_linalg.cu", "lcpc_api.cu", "lcpc_scheme.cu", "lcpc_hostrand.cu", "lcpc_stream.cu", "lcpc_ubench.cu"]
+SOURCES = ["lcpc_ntt_f0.cu", "lcpc_ntt_f1.cu", "lcpc_ntt_f2.cu", "lcpc_ntt_f3.cu", "lcpc_ntt_f4.cu", "lcpc_ntt.cu", "lcpc_hash.cu", "lcpc_linalg.cu", "lcpc_api.cu", "lcpc_scheme.cu", "lcpc_hostrand.cu", "lcpc_stream.cu", "lcpc_ubench.cu", "lcpc_multi.cu"]
 HEADERS = ["lcpc_ntt_impl.cuh", "lcpc_field.cuh", "lcpc_mont32.cuh", "lcpc_blake3.cuh", "lcpc_kernels.h", "lcpc_handles.h", "lcpc_hostrand.h", os.path.join("..", "..", "include", "lcpc_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -130,6 +130,8 @@ namespace {
 // (e.g. a garbage collector) destroys them does not matter.
 void ctx_unref(lcpc_ctx *ctx) {
     if (!ctx || ctx->refs.fetch_sub(1) != 1) return;
+    for (lcpc_ctx *s : ctx->subs) ctx_unref(s);
+    ctx->subs.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -143,6 +145,8 @@ void ctx_unref(lcpc_ctx *ctx) {
 
 void plan_unref(lcpc_plan *plan) {
     if (!plan || plan->refs.fetch_sub(1) != 1) return;
+    for (lcpc_plan *s : plan->subs) plan_unref(s);
+    plan->subs.clear();
     lcpc_ctx *ctx = plan->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -156,6 +160,7 @@ void plan_unref(lcpc_plan *plan) {
 
 void commit_release(lcpc_commit *c) {
     if (!c) return;
+    if (c->plan && !c->shards.empty()) multi::release(c);
     if (c->plan) {
         cudaStream_t s = c->plan->ctx->stream;
         if (c->d_coeffs) cudaFreeAsync(c->d_coeffs, s);
@@ -259,6 +264,25 @@ int32_t commit_shape(lcpc_plan *plan, size_t n_coeffs, lcpc_commit *c) {
     return LCPC_OK;
 }
 
+// commit through a plan made on a multi-device context (lcpc_multi.cu)
+int32_t commit_multi(lcpc_plan *plan, const uint64_t *coeffs, size_t n_coeffs, const uint8_t *file_bytes, size_t n_bytes,
+                     uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out, lcpc_commit **keep) {
+    lcpc_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> g(plan->mu);
+    std::lock_guard<std::mutex> g2(ctx->mu);
+    lcpc_commit *c = new (std::nothrow) lcpc_commit;
+    if (!c) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+    int32_t rc = commit_shape(plan, n_coeffs, c);
+    if (rc == LCPC_OK) rc = multi::commit_host(plan, c, coeffs, n_coeffs, file_bytes, n_bytes, coeffs_out, comm_out, hashes_out);
+    if (rc != LCPC_OK || !keep) {
+        commit_release(c);
+        if (rc == LCPC_OK) lcpc_ctx_synchronize(ctx);
+    } else {
+        *keep = c;
+    }
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -322,14 +346,77 @@ int32_t lcpc_ctx_create_on_stream(int32_t device, void *cuda_stream, lcpc_ctx **
     return ctx_create(device, cuda_stream, false, out);
 }
 
+int32_t lcpc_ctx_create_multi(const int32_t *devices, int32_t n_devices, lcpc_ctx **out) {
+    if (!out || !devices) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > 16 || (n_devices & (n_devices - 1)))
+        return fail(LCPC_ERR_INVALID_ARG, "the number of devices must be a power of two, at most 16");
+    if (n_devices == 1) return ctx_create(devices[0], nullptr, true, out);
+    lcpc_ctx *ctx = nullptr;
+    int32_t rc = ctx_create(devices[0], nullptr, true, &ctx);
+    if (rc != LCPC_OK) return rc;
+    for (int32_t g = 0; g < n_devices; g++) {
+        lcpc_ctx *sub = nullptr;
+        rc = ctx_create(devices[g], nullptr, true, &sub);
+        if (rc != LCPC_OK) {
+            ctx_unref(ctx);
+            return rc;
+        }
+        ctx->subs.push_back(sub);
+    }
+    // every device reads and writes every other device's memory (the chaining-value stores of a sharded commitment, the
+    // partial sums of a fold): peer access for plain allocations and for the stream-ordered pools
+    for (int32_t a = 0; a < n_devices; a++) {
+        for (int32_t b = 0; b < n_devices; b++) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            cudaError_t e = cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            if (e != cudaSuccess || !can) {
+                ctx_unref(ctx);
+                return fail(LCPC_ERR_CUDA, "no peer access between the listed devices (NVLink / PCIe P2P required)");
+            }
+            cudaSetDevice(devices[a]);
+            e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+            } else if (e != cudaSuccess) {
+                ctx_unref(ctx);
+                return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            }
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, devices[b]) == cudaSuccess) {
+                cudaMemAccessDesc d{};
+                d.location.type = cudaMemLocationTypeDevice;
+                d.location.id = devices[a];
+                d.flags = cudaMemAccessFlagsProtReadWrite;
+                e = cudaMemPoolSetAccess(pool, &d, 1);
+                if (e != cudaSuccess) {
+                    ctx_unref(ctx);
+                    return cuda_fail(e, "cudaMemPoolSetAccess");
+                }
+            }
+        }
+    }
+    cudaSetDevice(devices[0]);
+    *out = ctx;
+    return LCPC_OK;
+}
+
+int32_t lcpc_ctx_device_count(const lcpc_ctx *ctx) { return !ctx ? 0 : (ctx->subs.empty() ? 1 : (int32_t)ctx->subs.size()); }
+
 int32_t lcpc_ctx_synchronize(lcpc_ctx *ctx) {
     if (!ctx) return fail(LCPC_ERR_INVALID_ARG, "null context");
+    for (lcpc_ctx *s : ctx->subs) {
+        CU(cudaSetDevice(s->device));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return LCPC_OK;
 }
 
 int32_t lcpc_ctx_stream(const lcpc_ctx *ctx, void **cuda_stream_out) {
+    ctx = primary(const_cast<lcpc_ctx *>(ctx));
     if (!ctx || !cuda_stream_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     *cuda_stream_out = (void *)ctx->stream;
     return LCPC_OK;
@@ -337,9 +424,15 @@ int32_t lcpc_ctx_stream(const lcpc_ctx *ctx, void **cuda_stream_out) {
 
 void lcpc_ctx_destroy(lcpc_ctx *ctx) { ctx_unref(ctx); }
 
-uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t lcpc_ctx_launch_count(const lcpc_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (const lcpc_ctx *s : ctx->subs) n += s->launches;
+    return n;
+}
 
 int32_t lcpc_ctx_kernel_timing(lcpc_ctx *ctx, int32_t enable) {
+    ctx = primary(ctx);
     if (!ctx) return fail(LCPC_ERR_INVALID_ARG, "null context");
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));
@@ -353,6 +446,7 @@ int32_t lcpc_ctx_kernel_timing(lcpc_ctx *ctx, int32_t enable) {
 }
 
 const char *lcpc_ctx_kernel_timing_report(lcpc_ctx *ctx) {
+    ctx = primary(ctx);
     if (!ctx) return "";
     std::lock_guard<std::mutex> g(ctx->mu);
     ctx->timing_report.clear();
@@ -391,6 +485,27 @@ int32_t lcpc_plan_ligero(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size_t 
     int log_n = 0;
     while (((size_t)1 << log_n) < n_cols) log_n++;
     if (log_n > field_consts(field).two_adicity) return fail(LCPC_ERR_TOO_BIG, "n_cols exceeds the field's 2-adicity");
+    if (!ctx->subs.empty()) {  // multi-device context: the same plan on every device
+        lcpc_plan *p = new (std::nothrow) lcpc_plan;
+        if (!p) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+        p->ctx = ctx;
+        ctx->refs.fetch_add(1);
+        p->kind = 0;
+        p->fid = field;
+        p->n_per_row = n_per_row;
+        p->n_cols = n_cols;
+        for (lcpc_ctx *sub : ctx->subs) {
+            lcpc_plan *sp = nullptr;
+            int32_t rc = lcpc_plan_ligero(sub, field, n_per_row, n_cols, root_of_unity_mont, &sp);
+            if (rc != LCPC_OK) {
+                plan_unref(p);
+                return rc;
+            }
+            p->subs.push_back(sp);
+        }
+        *out = p;
+        return LCPC_OK;
+    }
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     lcpc_plan *p = new (std::nothrow) lcpc_plan;
@@ -434,6 +549,27 @@ int32_t lcpc_plan_brakedown(lcpc_ctx *ctx, int32_t field, size_t n_per_row, size
             if (l > 0) in_len = precodes[l - 1].rows + in_len + postcodes[l].rows;
         }
     }
+    if (!ctx->subs.empty()) {  // multi-device context: the matrices are uploaded to every device
+        lcpc_plan *p = new (std::nothrow) lcpc_plan;
+        if (!p) return fail(LCPC_ERR_NOMEM, "host allocation failed");
+        p->ctx = ctx;
+        ctx->refs.fetch_add(1);
+        p->kind = 1;
+        p->fid = field;
+        p->n_per_row = n_per_row;
+        p->n_cols = n_cols;
+        for (lcpc_ctx *sub : ctx->subs) {
+            lcpc_plan *sp = nullptr;
+            int32_t rc = lcpc_plan_brakedown(sub, field, n_per_row, n_cols, n_levels, precodes, postcodes, &sp);
+            if (rc != LCPC_OK) {
+                plan_unref(p);
+                return rc;
+            }
+            p->subs.push_back(sp);
+        }
+        *out = p;
+        return LCPC_OK;
+    }
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     lcpc_plan *p = new (std::nothrow) lcpc_plan;
@@ -474,6 +610,7 @@ void lcpc_plan_destroy(lcpc_plan *plan) { plan_unref(plan); }
 
 
 int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
+    plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || (!rows && n_rows)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_rows == 0) return LCPC_OK;
     lcpc_ctx *ctx = plan->ctx;
@@ -499,6 +636,7 @@ int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
 }
 
 int32_t lcpc_dev_decode(lcpc_plan *plan, uint64_t *d_rows, size_t n_rows) {
+    plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || (!d_rows && n_rows)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (plan->kind != 0) return fail(LCPC_ERR_ENCODE, "only Ligero (Reed-Solomon) rows have an inverse transform");
     if (n_rows == 0) return LCPC_OK;
@@ -511,6 +649,7 @@ int32_t lcpc_dev_decode(lcpc_plan *plan, uint64_t *d_rows, size_t n_rows) {
 }
 
 int32_t lcpc_decode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
+    plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || (!rows && n_rows)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (plan->kind != 0) return fail(LCPC_ERR_ENCODE, "only Ligero (Reed-Solomon) rows have an inverse transform");
     if (n_rows == 0) return LCPC_OK;
@@ -532,6 +671,13 @@ int32_t lcpc_commit_host(lcpc_plan *plan, const uint64_t *coeffs, size_t n_coeff
                          uint64_t *comm_out, uint8_t *hashes_out, lcpc_commit **keep) {
     if (keep) *keep = nullptr;
     if (!plan || !coeffs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!plan->subs.empty()) {
+        // multi-device context: shard over its devices when every device gets whole BLAKE3 chunks of rows, else (small
+        // commitments, 24-byte elements) the first device takes it
+        const size_t rows = n_coeffs ? (n_coeffs + plan->n_per_row - 1) / plan->n_per_row : 0;
+        if (multi::usable(plan, rows)) return commit_multi(plan, coeffs, n_coeffs, nullptr, 0, coeffs_out, comm_out, hashes_out, keep);
+        plan = primary(plan);
+    }
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -567,6 +713,13 @@ int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_
     if (!plan || !file_bytes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (plan->fid != FT63 && plan->fid != FT253_192)
         return fail(LCPC_ERR_INVALID_ARG, "byte packing is defined for the DataField types only (Ft63, Ft253_192)");
+    if (!plan->subs.empty()) {
+        const size_t n_el = (n_bytes + 6) / 7;
+        const size_t rows = n_el ? (n_el + plan->n_per_row - 1) / plan->n_per_row : 0;
+        if (plan->fid == FT63 && multi::usable(plan, rows))
+            return commit_multi(plan, nullptr, n_el, file_bytes, n_bytes, coeffs_out, comm_out, hashes_out, keep);
+        plan = primary(plan);
+    }
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -612,6 +765,7 @@ int32_t lcpc_commit_bytes_host(lcpc_plan *plan, const uint8_t *file_bytes, size_
 }
 
 int32_t lcpc_commit_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_coeffs, lcpc_commit **keep) {
+    plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || !d_coeffs || !keep) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     *keep = nullptr;
     lcpc_ctx *ctx = plan->ctx;
@@ -650,6 +804,11 @@ int32_t lcpc_commit_get_dims(const lcpc_commit *c, size_t *n_rows, size_t *n_per
 
 int32_t lcpc_commit_root(lcpc_commit *c, uint8_t root_out[LCPC_DIGEST_BYTES]) {
     if (!c || !root_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!c->shards.empty()) {
+        std::lock_guard<std::mutex> gm(c->mu);
+        std::lock_guard<std::mutex> gm2(c->plan->ctx->mu);
+        return multi::root(c, root_out);
+    }
     lcpc_ctx *ctx = c->plan->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -661,6 +820,11 @@ int32_t lcpc_commit_root(lcpc_commit *c, uint8_t root_out[LCPC_DIGEST_BYTES]) {
 
 int32_t lcpc_commit_download(lcpc_commit *c, uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out) {
     if (!c) return fail(LCPC_ERR_INVALID_ARG, "null commit");
+    if (!c->shards.empty()) {
+        std::lock_guard<std::mutex> gm(c->mu);
+        std::lock_guard<std::mutex> gm2(c->plan->ctx->mu);
+        return multi::download(c, coeffs_out, comm_out, hashes_out);
+    }
     lcpc_ctx *ctx = c->plan->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -678,6 +842,7 @@ int32_t lcpc_commit_download(lcpc_commit *c, uint64_t *coeffs_out, uint64_t *com
 
 int32_t lcpc_commit_device_ptrs(lcpc_commit *c, uint64_t **d_coeffs, uint64_t **d_comm, uint8_t **d_hashes) {
     if (!c) return fail(LCPC_ERR_INVALID_ARG, "null commit");
+    if (!c->shards.empty()) return fail(LCPC_ERR_INVALID_ARG, "a multi-device commitment has no single set of device buffers");
     if (d_coeffs) *d_coeffs = c->d_coeffs;
     if (d_comm) *d_comm = c->d_comm;
     if (d_hashes) *d_hashes = c->d_hashes;
@@ -686,6 +851,7 @@ int32_t lcpc_commit_device_ptrs(lcpc_commit *c, uint64_t **d_coeffs, uint64_t **
 
 void lcpc_commit_free(lcpc_commit *c) {
     if (!c) return;
+    if (c->plan && !c->shards.empty()) lcpc_ctx_synchronize(c->plan->ctx);
     if (c->plan) cudaSetDevice(c->plan->ctx->device);
     commit_release(c);  // may drop the last reference to the plan / context: hold no lock here
 }
@@ -694,6 +860,11 @@ int32_t lcpc_fold_host(lcpc_commit *c, int32_t which, const uint64_t *tensors, s
     if (!c || !tensors || !out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (which != 0 && which != 1) return fail(LCPC_ERR_INVALID_ARG, "which must be 0 (coeffs) or 1 (comm)");
     if (n_tensors == 0) return LCPC_OK;
+    if (!c->shards.empty()) {
+        std::lock_guard<std::mutex> gm(c->mu);
+        std::lock_guard<std::mutex> gm2(c->plan->ctx->mu);
+        return multi::fold_host(c, which, tensors, n_tensors, out);
+    }
     lcpc_ctx *ctx = c->plan->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -719,6 +890,11 @@ int32_t lcpc_open_columns_host(lcpc_commit *c, const uint64_t *cols, size_t n, u
     for (size_t i = 0; i < n; i++)
         if (cols[i] >= c->n_cols) return fail(LCPC_ERR_COLUMN_NUMBER, "bad column number");
     if (n == 0) return LCPC_OK;
+    if (!c->shards.empty()) {
+        std::lock_guard<std::mutex> gm(c->mu);
+        std::lock_guard<std::mutex> gm2(c->plan->ctx->mu);
+        return multi::open_columns_host(c, cols, n, cols_out, paths_out);
+    }
     lcpc_ctx *ctx = c->plan->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -749,6 +925,11 @@ int32_t lcpc_leaves_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint8_t
     for (size_t i = 0; i < n; i++)
         if (cols[i] >= c->n_cols) return fail(LCPC_ERR_COLUMN_NUMBER, "bad column number");
     if (n == 0) return LCPC_OK;
+    if (!c->shards.empty()) {
+        std::lock_guard<std::mutex> gm(c->mu);
+        std::lock_guard<std::mutex> gm2(c->plan->ctx->mu);
+        return multi::leaves_host(c, cols, n, leaves_out);
+    }
     lcpc_ctx *ctx = c->plan->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -769,6 +950,7 @@ int32_t lcpc_leaves_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint8_t
 // ---- device-pointer building blocks -------------------------------------------------
 
 int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm) {
+    plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || !d_coeffs || !d_comm) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(plan->ctx->mu);
@@ -778,6 +960,7 @@ int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows
 
 int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t row0,
                                 uint64_t *d_scratch, uint64_t *const *peer_blocks, size_t n_peers) {
+    plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || !d_coeffs || !peer_blocks) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (plan->kind != 0) return fail(LCPC_ERR_INVALID_ARG, "the fused encode + re-shard is defined for Ligero plans");
     if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || plan->n_cols % n_peers)
@@ -804,6 +987,7 @@ int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_
 
 int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
                               size_t n_cols, uint8_t *d_leaves) {
+    ctx = primary(ctx);
     if (!ctx || !d_mat || !d_leaves) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -817,6 +1001,7 @@ int32_t lcpc_dev_hash_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_ma
 int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
                                   size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
                                   uint64_t chunk_end, uint8_t *d_cvs) {
+    ctx = primary(ctx);
     if (!ctx || !d_mat || !d_cvs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     const uint64_t w = 8ull * (uint64_t)limbs_of(field);
@@ -839,6 +1024,7 @@ int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *
 int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
                                           size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
                                           uint64_t chunk_end, uint8_t *const *peer_cvs, size_t n_peers) {
+    ctx = primary(ctx);
     if (!ctx || !d_mat || !peer_cvs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || n_cols == 0 || (n_cols & (n_cols - 1)) || n_cols % n_peers)
@@ -865,6 +1051,7 @@ int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const ui
 }
 
 int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_leaves) {
+    ctx = primary(ctx);
     if (!ctx || !d_cvs || !d_leaves) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_chunks < 2) return fail(LCPC_ERR_DIMS, "a single chaining value is the leaf itself");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -875,6 +1062,7 @@ int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, 
 
 int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes,
                                  size_t n_leaves) {
+    ctx = primary(ctx);
     if (!ctx || !d_hashes || (!d_cvs && n_chunks > 1)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1)) || n_cols > n_leaves) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two >= n_cols");
     if (n_chunks == 0) return fail(LCPC_ERR_DIMS, "a leaf has at least one chunk");
@@ -888,6 +1076,7 @@ int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_c
 
 int32_t lcpc_dev_merkleize(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride, size_t n_cols,
                            uint8_t *d_hashes) {
+    ctx = primary(ctx);
     if (!ctx || !d_mat || !d_hashes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     if (n_cols == 0 || n_cols > row_stride) return fail(LCPC_ERR_DIMS, "bad column window");
@@ -899,6 +1088,7 @@ int32_t lcpc_dev_merkleize(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, 
 }
 
 int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves) {
+    ctx = primary(ctx);
     if (!ctx || !d_hashes) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -909,6 +1099,7 @@ int32_t lcpc_dev_merkle_tree(lcpc_ctx *ctx, uint8_t *d_hashes, size_t n_leaves) 
 
 int32_t lcpc_dev_fold(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t width,
                       size_t row_stride, const uint64_t *d_tensors, size_t n_tensors, uint64_t *d_out) {
+    ctx = primary(ctx);
     if (!ctx || !d_mat || !d_tensors || !d_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -921,6 +1112,7 @@ int32_t lcpc_dev_fold(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_
 
 int32_t lcpc_dev_add_partials(lcpc_ctx *ctx, int32_t field, const uint64_t *d_parts, size_t n_parts, size_t n,
                               uint64_t *d_out) {
+    ctx = primary(ctx);
     if (!ctx || !d_parts || !d_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -931,6 +1123,7 @@ int32_t lcpc_dev_add_partials(lcpc_ctx *ctx, int32_t field, const uint64_t *d_pa
 
 int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, size_t n_rows, size_t row_stride,
                                 const uint64_t *d_cols, size_t n, uint64_t *d_out) {
+    ctx = primary(ctx);
     if (!ctx || !d_mat || !d_cols || !d_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -941,6 +1134,7 @@ int32_t lcpc_dev_gather_columns(lcpc_ctx *ctx, int32_t field, const uint64_t *d_
 
 int32_t lcpc_dev_gather_paths(lcpc_ctx *ctx, const uint8_t *d_hashes, size_t n_leaves, const uint64_t *d_cols, size_t n,
                               uint8_t *d_paths) {
+    ctx = primary(ctx);
     if (!ctx || !d_hashes || (n && (!d_cols || !d_paths))) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -950,6 +1144,7 @@ int32_t lcpc_dev_gather_paths(lcpc_ctx *ctx, const uint8_t *d_hashes, size_t n_l
 }
 
 int32_t lcpc_dev_pack_bytes7(lcpc_ctx *ctx, const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_elems) {
+    ctx = primary(ctx);
     if (!ctx || !d_bytes || !d_elems) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));

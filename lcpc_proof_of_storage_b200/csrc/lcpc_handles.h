@@ -52,6 +52,9 @@ struct lcpc_ctx {
     // both PCIe directions and the kernels overlap
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
+    // multi-device context (lcpc_ctx_create_multi): one sub-context per listed device, each with its own stream; this
+    // object then only carries the lock and the device of the first entry.  Empty for an ordinary context.
+    std::vector<lcpc_ctx *> subs;
     // zeroed ticket counters of the one-launch hash + tree kernels (they leave them zeroed); grown on demand
     unsigned *d_tickets = nullptr;
     size_t n_tickets = 0;
@@ -89,6 +92,21 @@ struct lcpc_plan {
     lcpc::SdigPlan sdig;
     std::mutex mu;
     std::atomic<int> refs{1};  // the creator + every live commit
+    // plan on a multi-device context: the same encoding built on every device (twiddles / CSR matrices replicated)
+    std::vector<lcpc_plan *> subs;
+};
+
+// One device's part of a commitment made on a multi-device context: a block of whole rows of the
+// coefficient and encoded matrices, and one block of columns of the Merkle tree's leaves.
+struct lcpc_shard {
+    size_t row0 = 0, rows = 0;      // my rows [row0, row0 + rows), cut on BLAKE3 chunk boundaries of the column leaves
+    uint64_t c0 = 0, c1 = 0;        // the chunks of every leaf those rows make up
+    size_t cols_local = 0;          // real columns inside my block of the padded leaf range
+    uint64_t *d_coeffs = nullptr;   // [rows][n_per_row]
+    uint64_t *d_comm = nullptr;     // [rows][n_cols]
+    uint8_t *d_cvs = nullptr;       // chaining values of MY column block from EVERY device's rows: [n_chunks][cb][32 B]
+    uint8_t *d_subtree = nullptr;   // flat Merkle tree over my cb leaves
+    cudaEvent_t ev = nullptr, ev_tree = nullptr;
 };
 
 struct lcpc_commit {
@@ -101,6 +119,12 @@ struct lcpc_commit {
     // kept so that a row edit re-hashes only the chunks it touches (lcpc_commit_update_rows_host)
     uint8_t *d_cvs = nullptr;
     std::mutex mu;
+    // multi-device commitment: shards[g] lives on plan->ctx->subs[g]; d_top = the log2(n) levels above the subtree
+    // roots, on the first device.  The single-device members above stay null.
+    std::vector<lcpc_shard> shards;
+    uint8_t *d_top = nullptr;
+    size_t cb = 0;            // leaves per column block = np2 / devices
+    uint64_t n_chunks = 0;    // BLAKE3 chunks per leaf
 };
 
 
@@ -158,6 +182,24 @@ struct DevBuf {
 // above them.  d_cvs_keep: where the chunk chaining values go when the caller keeps them (a commit handle)
 int32_t merkleize_dev(lcpc_ctx *ctx, int fid, const uint64_t *d_comm, size_t n_rows, size_t row_stride, size_t n_cols,
                       size_t np2, uint8_t *d_hashes, uint8_t **d_cvs_keep = nullptr);
+
+// multi-device paths (lcpc_multi.cu); all called with the parent plan / context / commit locks held
+namespace multi {
+bool usable(const lcpc_plan *plan, size_t n_rows);  // a chunk-aligned row partition with rows on every device exists
+int32_t commit_host(lcpc_plan *plan, lcpc_commit *c, const uint64_t *coeffs, size_t n_coeffs, const uint8_t *file_bytes,
+                    size_t n_bytes, uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out);
+int32_t root(lcpc_commit *c, uint8_t *root_out);
+int32_t download(lcpc_commit *c, uint64_t *coeffs_out, uint64_t *comm_out, uint8_t *hashes_out);
+int32_t fold_host(lcpc_commit *c, int32_t which, const uint64_t *tensors, size_t n_tensors, uint64_t *out);
+int32_t open_columns_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out, uint8_t *paths_out);
+int32_t leaves_host(lcpc_commit *c, const uint64_t *cols, size_t n, uint8_t *leaves_out);
+void release(lcpc_commit *c);
+}  // namespace multi
+
+// the device-0 plan of a plan made on a multi-device context (the plan itself otherwise): entry points that work on one
+// device (single rows, verification, streaming) run there
+inline lcpc_plan *primary(lcpc_plan *p) { return (p && !p->subs.empty()) ? p->subs[0] : p; }
+inline lcpc_ctx *primary(lcpc_ctx *c) { return (c && !c->subs.empty()) ? c->subs[0] : c; }
 
 // encode rows already on the device (Ligero reads d_coeffs with stride n_per_row; Brakedown widens first)
 int32_t encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);

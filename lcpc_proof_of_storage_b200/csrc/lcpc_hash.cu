@@ -383,17 +383,71 @@ __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, u
 // (-> leaf; with n_chunks == 1 the leaves are already in place), then the whole Merkle tree (merkleize, lib.rs:720-734:
 // leaves n_cols..np2 are all-zero).  grid = np2 / T tiles.
 constexpr int MT_TILE = 256;
+// PAR: the BLAKE3 parent tree over a column's n_chunks chaining values, level by level across the CTA instead of one
+// thread walking it: BLAKE3's tree ("the left subtree takes the largest power of two of chunks below the total") is the
+// tree obtained by pairing adjacent nodes and carrying an odd last node up unchanged, so level k is
+// floor(n_k / 2) independent compressions per column.  C columns at a time sit in shared memory as [chunk][column]
+// (two buffers used alternately); depth ceil(log2 n_chunks) instead of n_chunks - 1 -- at 8 GPUs the leaves of the
+// weak-scaling bench have 33 chunks and a rank owns only 8192 columns, so the serial walk was a 32-deep chain on 32 CTAs.
+// cv_stride: columns per chunk row of `cvs` (n_cols, or the column-block width of a row-sharded store).
+template <bool PAR>
 __global__ void __launch_bounds__(MT_TILE)
-k_merge_tree(const uint32_t *cvs, size_t n_cols, uint64_t n_chunks, uint8_t *hashes, size_t np2, unsigned *ticket) {
+k_merge_tree(const uint32_t *cvs, size_t n_cols, size_t cv_stride, uint64_t n_chunks, uint8_t *hashes, size_t np2,
+             unsigned *ticket, int C) {
     __shared__ uint32_t buf[2][MT_TILE][8];
     __shared__ unsigned s_flag;
-    const size_t j = (size_t)blockIdx.x * MT_TILE + threadIdx.x;
+    extern __shared__ uint32_t sm_cv[];  // PAR: [n_chunks][C][8] | [(n_chunks + 1) / 2][C][8]
+    const unsigned t = threadIdx.x;
+    const size_t j = (size_t)blockIdx.x * MT_TILE + t;
     uint32_t leaf[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) leaf[k] = 0;
-    if (j < n_cols) {
+    if constexpr (PAR) {
+        const unsigned nc = (unsigned)n_chunks;
+        uint32_t *bufA = sm_cv, *bufB = sm_cv + (size_t)nc * C * 8;
+        for (unsigned sub = 0; sub < MT_TILE; sub += C) {
+            const size_t j0 = (size_t)blockIdx.x * MT_TILE + sub;
+            if (j0 < n_cols) {
+                for (unsigned idx = t; idx < nc * C * 2; idx += MT_TILE) {  // 16 bytes per thread per trip, coalesced
+                    const unsigned c = idx / (2 * C), rem = idx % (2 * C), col = rem >> 1, half = rem & 1;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (j0 + col < n_cols) v = __ldcg(reinterpret_cast<const uint4 *>(cvs + ((size_t)c * cv_stride + j0 + col) * 8) + half);
+                    *reinterpret_cast<uint4 *>(bufA + ((size_t)c * C + col) * 8 + half * 4) = v;
+                }
+                __syncthreads();
+                uint32_t *in = bufA, *out = bufB;
+                unsigned n = nc;
+                while (n > 1) {
+                    const unsigned pairs = n >> 1;
+                    const uint32_t flags = n == 2 ? (uint32_t)b3::ROOT : 0u;
+                    for (unsigned idx = t; idx < pairs * C; idx += MT_TILE) {
+                        const unsigned p = idx / C, col = idx % C;
+                        uint32_t o[8];
+                        b3::parent_cv(in + ((size_t)(2 * p) * C + col) * 8, in + ((size_t)(2 * p + 1) * C + col) * 8, flags, o);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) out[((size_t)p * C + col) * 8 + k] = o[k];
+                    }
+                    if (n & 1) {  // the odd last node moves up unchanged
+                        for (unsigned idx = t; idx < (unsigned)C * 8; idx += MT_TILE)
+                            out[(size_t)pairs * C * 8 + idx] = in[(size_t)(n - 1) * C * 8 + idx];
+                    }
+                    __syncthreads();
+                    uint32_t *tmp = in;
+                    in = out;
+                    out = tmp;
+                    n = pairs + (n & 1);
+                }
+                // row 0 of `in` holds the leaves of columns j0 .. j0 + C
+                if (t >= sub && t < sub + C && j < n_cols) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) leaf[k] = in[(size_t)(t - sub) * 8 + k];
+                }
+                __syncthreads();  // before the next sub-tile overwrites the buffers
+            }
+        }
+    } else if (j < n_cols) {
         if (n_chunks > 1) {
-            merge_column(leaf, cvs, n_cols, n_chunks, j);
+            merge_column(leaf, cvs, cv_stride, n_chunks, j);
         } else {
             const uint4 *in = reinterpret_cast<const uint4 *>(hashes + j * 32);
             const uint4 a = __ldcg(in), b = __ldcg(in + 1);
@@ -558,11 +612,29 @@ cudaError_t hash_merge(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, u
 
 // cvs (n_chunks >= 2) or leaves already in d_hashes (n_chunks == 1) -> leaves + the whole tree, one launch
 cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes, size_t np2, unsigned *d_ticket,
-                       const Launch &lc) {
+                       const Launch &lc, size_t cv_stride) {
     if (np2 == 0 || n_cols > np2) return cudaErrorInvalidValue;
+    if (cv_stride == 0) cv_stride = n_cols;
     const unsigned tiles = (unsigned)((np2 + MT_TILE - 1) / MT_TILE);
+    // columns per shared-memory sub-tile of the level-wise merge: the largest power of two <= 32 whose two buffers
+    // (1.5 x n_chunks rows of C digests) fit 30 KiB (beside 16 KiB of static tile buffers, under the 48 KiB default); the serial per-thread walk when that leaves fewer than 4 columns.
+    // With few chunks per leaf and many columns (one GPU: 5 chunks, 65536 columns) the walk is short and every SM is
+    // busy anyway, and the level-wise form's extra shared-memory traffic only costs: serial below 8 chunks.
+    int C = 0;
+    if (n_chunks >= 8) {
+        for (C = 32; C >= 4; C >>= 1)
+            if ((n_chunks + (n_chunks + 1) / 2) * (uint64_t)C * 32 <= 30 * 1024) break;
+        if (C < 4) C = 0;
+    }
     lc.begin("k_merge_tree");
-    k_merge_tree<<<tiles, MT_TILE, 0, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, n_chunks, d_hashes, np2, d_ticket);
+    if (C > 0) {
+        const size_t smem = (size_t)(n_chunks + (n_chunks + 1) / 2) * C * 32;
+        k_merge_tree<true><<<tiles, MT_TILE, smem, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, cv_stride, n_chunks,
+                                                          d_hashes, np2, d_ticket, C);
+    } else {
+        k_merge_tree<false><<<tiles, MT_TILE, 0, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, cv_stride, n_chunks,
+                                                         d_hashes, np2, d_ticket, 0);
+    }
     lc.end();
     return cudaGetLastError();
 }

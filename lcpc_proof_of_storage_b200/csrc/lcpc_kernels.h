@@ -119,8 +119,9 @@ cudaError_t merkle_tree(uint8_t *d_hashes, size_t n_leaves, const Launch &lc);
 // d_hashes) -> leaves and the whole tree over the padded leaf range (padding leaves written as zero).  d_ticket: one
 // zeroed counter, left zeroed.  hash_tree: the whole of merkleize (leaf hashing + merge + tree) for columns [0, n_cols)
 // of a matrix; d_cvs needs hash_scratch_bytes(), d_tickets hash_tree_tickets(np2) zeroed counters (left zeroed).
+// cv_stride: columns per chunk row of d_cvs (0 = n_cols; the column-block width for a row-sharded store)
 cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes, size_t np2, unsigned *d_ticket,
-                       const Launch &lc);
+                       const Launch &lc, size_t cv_stride = 0);
 size_t hash_tree_tickets(size_t np2);
 bool hash_tree_supported(int fid, size_t n_rows, size_t np2);
 bool hash_tree_preferred(int fid, size_t n_rows, size_t np2);

@@ -138,6 +138,7 @@ int32_t lcpc_pos_choose_columns(uint64_t seed, size_t amount, size_t max_index, 
 int32_t lcpc_verify_columns_host(lcpc_ctx *ctx, int32_t field, const uint64_t *columns, size_t n_rows, const uint8_t *paths,
                                  size_t path_len, const uint64_t *col_idx, size_t n, const uint8_t root[LCPC_DIGEST_BYTES],
                                  uint8_t *leaves_out, uint32_t *ok_out) {
+    ctx = primary(ctx);
     if (!ctx || (!columns && n && n_rows) || (!col_idx && n && paths)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
     if (paths && (!root || !ok_out)) return fail(LCPC_ERR_INVALID_ARG, "paths given without root / ok_out");
@@ -216,6 +217,43 @@ int32_t lcpc_prove(lcpc_commit *c, const uint64_t *outer_tensor, size_t outer_le
         ((!columns_out || !paths_out) && n_col_opens))
         return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (outer_len != c->n_rows) return fail(LCPC_ERR_OUTER_TENSOR, "bad outer tensor size");  // lib.rs:1046-1048
+    if (!c->shards.empty()) {
+        // multi-device commitment: the same sequence with the sharded fold / open (lcpc_multi.cu); the canonical bytes for
+        // the transcript are produced on the first device
+        lcpc_ctx *mctx = c->plan->ctx, *p0 = primary(mctx);
+        std::lock_guard<std::mutex> g(c->mu);
+        std::lock_guard<std::mutex> g2(mctx->mu);
+        std::lock_guard<std::mutex> g3(tr->mu);
+        const int fid = c->plan->fid, L = limbs_of(fid);
+        const size_t wbytes = (size_t)L * 8, n_rows = c->n_rows, npr = c->n_per_row;
+        std::vector<uint64_t> tensor(n_rows * L), canon(npr * L);
+        auto fold_one = [&](const uint64_t *t_host, const uint8_t *label, uint64_t *dst) -> int32_t {
+            int32_t rc = multi::fold_host(c, 0, t_host, 1, dst);
+            if (rc != LCPC_OK) return rc;
+            CU(cudaSetDevice(p0->device));
+            DevBuf d_p, d_pc;
+            CU(d_p.alloc(npr * wbytes, p0->stream));
+            CU(d_pc.alloc(npr * wbytes, p0->stream));
+            CU(cudaMemcpyAsync(d_p.p, dst, npr * wbytes, cudaMemcpyHostToDevice, p0->stream));
+            CU(to_canon(fid, d_p.as<uint64_t>(), npr, d_pc.as<uint64_t>(), p0->lc()));
+            CU(cudaMemcpyAsync(canon.data(), d_pc.p, npr * wbytes, cudaMemcpyDeviceToHost, p0->stream));
+            CU(cudaStreamSynchronize(p0->stream));
+            transcript_update(tr->t, label, canon.data(), npr, L);
+            return LCPC_OK;
+        };
+        for (size_t i = 0; i < n_degree_tests; i++) {
+            expand_tensor(tr->t, fid, n_rows, tensor.data());
+            int32_t rc = fold_one(tensor.data(), LABEL_PR, p_random_out + i * npr * L);
+            if (rc != LCPC_OK) return rc;
+        }
+        int32_t rc = fold_one(outer_tensor, LABEL_PE, p_eval_out);
+        if (rc != LCPC_OK) return rc;
+        std::vector<uint64_t> cols(n_col_opens);
+        expand_columns(tr->t, c->n_cols, n_col_opens, cols.data());
+        if (col_idx_out) std::memcpy(col_idx_out, cols.data(), n_col_opens * sizeof(uint64_t));
+        if (n_col_opens) return multi::open_columns_host(c, cols.data(), n_col_opens, columns_out, paths_out);
+        return LCPC_OK;
+    }
     lcpc_ctx *ctx = c->plan->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     std::lock_guard<std::mutex> g2(ctx->mu);
@@ -277,6 +315,7 @@ int32_t lcpc_verify(lcpc_plan *plan, const uint8_t root[LCPC_DIGEST_BYTES], cons
                     size_t n_per_row, const uint64_t *p_random, size_t n_p_random, const uint64_t *columns, size_t n_rows,
                     const uint8_t *paths, size_t path_len, size_t n_columns, size_t n_col_opens, size_t n_degree_tests,
                     lcpc_transcript *tr, uint64_t *result_out) {
+    plan = primary(plan);  // verification is replicas-only work: the first device of a multi-device context
     if (!plan || !root || !outer_tensor || !inner_tensor || !p_eval || !tr || !result_out)
         return fail(LCPC_ERR_INVALID_ARG, "null argument");
     // lib.rs:874-891 argument checks, in the reference's order

@@ -204,6 +204,7 @@ extern "C" {
 
 int32_t lcpc_stream_begin(lcpc_plan *plan, size_t max_rows, size_t block_rows, uint8_t *sink, size_t sink_row_capacity,
                           lcpc_stream **out) {
+    plan = primary(plan);  // streaming runs on the first device of a multi-device context
     if (!plan || !out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     if (max_rows == 0) return fail(LCPC_ERR_DIMS, "stream: max_rows must be positive");
@@ -305,6 +306,7 @@ void lcpc_stream_free(lcpc_stream *s) { stream_release(s); }
 static int32_t commit_write_rows(lcpc_commit *c, size_t row0, size_t n_rows, const uint64_t *coeff_rows, bool allow_grow,
                                  uint64_t *comm_rows_out, uint8_t *hashes_out) {
     if (!c || !coeff_rows) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    if (!c->shards.empty()) return fail(LCPC_ERR_INVALID_ARG, "row edits are not supported on a multi-device commitment");
     lcpc_plan *plan = c->plan;
     lcpc_ctx *ctx = plan->ctx;
     std::lock_guard<std::mutex> g0(c->mu);

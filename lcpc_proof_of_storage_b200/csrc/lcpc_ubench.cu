@@ -91,6 +91,7 @@ cudaError_t run_stream(lcpc_ctx *ctx, int n_sm, uint32_t *d_out, long long *d_tm
 
 extern "C" int32_t lcpc_ctx_measure_int_pipes(lcpc_ctx *ctx, double cycles_out[4], double *sm_ghz_out) {
     if (!ctx || !cycles_out) return fail(LCPC_ERR_INVALID_ARG, "null argument");
+    ctx = primary(ctx);
     std::lock_guard<std::mutex> g(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     int n_sm = 0;

@@ -92,6 +92,23 @@ class Context:
         self._h = h
         self.device = device
 
+    @classmethod
+    def multi(cls, devices: Sequence[int]) -> "Context":
+        """lcpc_ctx_create_multi: one context over several devices of this process; commitments made through it are
+        sharded inside the library (rows for encoding, column blocks of the leaf range for the Merkle subtrees)."""
+        lib = _lib.load()
+        h = C.c_void_p()
+        arr = (C.c_int32 * len(devices))(*devices)
+        check(lib.lcpc_ctx_create_multi(arr, len(devices), C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        self.device = devices[0]
+        return self
+
+    @property
+    def n_devices(self) -> int:
+        return int(_lib.load().lcpc_ctx_device_count(self._h))
+
     @property
     def handle(self):
         return self._h

@@ -234,6 +234,35 @@ def test_hash_chunk_range_and_merge_one_gpu(oracle, fid, n_rows, n_per_row, n_co
         ops.hash_chunk_range(hi, row_split, n_rows, n_cols, split_chunk - 1, n_chunks)
 
 
+@pytest.mark.parametrize("n_chunks,n_cols,n_leaves", [
+    (1, 300, 512), (2, 37, 64), (5, 1000, 1024), (8, 256, 256), (9, 700, 1024), (33, 520, 1024), (147, 100, 128),
+    (200, 40, 64), (700, 9, 16),   # 8..159 chunks take the level-wise merge, the others the per-thread walk
+])
+def test_hash_merge_tree_one_launch(oracle, n_chunks, n_cols, n_leaves):
+    """lcpc_dev_hash_merge_tree (leaf merge + the whole Merkle tree, one launch, last-CTA ticket for the top levels)
+    against the BLAKE3 parent tree and merkle_tree of the oracle on random chaining values, padding leaves included."""
+    import torch
+
+    import lcpc_proof_of_storage_b200 as P
+    from lcpc_proof_of_storage_b200 import _lib
+
+    O = oracle
+    rng = np.random.default_rng(n_chunks * 1000 + n_cols)
+    cvs = rng.integers(0, 256, size=(n_chunks, n_cols, 32), dtype=np.uint8)
+    leaves = np.zeros((n_leaves, 32), dtype=np.uint8)
+    leaves[:n_cols] = O.hash_merge(cvs) if n_chunks > 1 else cvs[0]
+    exp = O.merkle_tree(leaves)
+    ctx = P.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    lib = _lib.load()
+    d_cvs = torch.from_numpy(cvs.reshape(-1)).cuda()
+    for rep in range(2):   # twice: the ticket counter must be left at zero
+        tree = torch.full(((2 * n_leaves - 1) * 32,), 0xAB, dtype=torch.uint8, device="cuda")
+        if n_chunks == 1:
+            tree[:n_cols * 32] = d_cvs
+        _lib.check(lib.lcpc_dev_hash_merge_tree(ctx.handle, d_cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(), n_leaves))
+        assert np.array_equal(tree.cpu().numpy().reshape(-1, 32), exp)
+
+
 def _worker_rows(rank, world, port, q, cv_fused=False):
     sys.path.insert(0, ROOT)
     import torch
