@@ -370,6 +370,10 @@ cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_ele
 
 // ------------------------------------------------------------------ Brakedown
 
+#ifndef LCPC_SPMV_UNROLL
+#define LCPC_SPMV_UNROLL 2
+#endif
+
 // The expander levels run on a TRANSPOSED working copy xT[codeword index][matrix row] (leading
 // dimension bp = matrix rows rounded up to the lane-group size): every gathered operand
 // x[col_k][b .. b+GS) is then one contiguous run, the non-zero a[i,k] is loaded once per lane group
@@ -395,7 +399,24 @@ k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colid
     for (size_t b = (size_t)blockIdx.y * gs + bl; b < bp; b += (size_t)gridDim.y * gs) {
         typename F::Dot acc;  // `data` is pre-scaled by 2^32 for the multi-limb fields (scale_csr_data)
         F::dot_init(acc);
-        for (uint32_t k = kfirst; k < k1; k += kstep) {
+        // U non-zeros per trip with every load issued before the arithmetic: a non-zero costs two dependent trips to L2
+        // (column index, then the gathered operand), and one chain per thread leaves the kernel waiting on them
+        // (long-scoreboard was the top stall with the integer pipes half idle, profiles/r02_spmv.md)
+        constexpr int U = LCPC_SPMV_UNROLL;
+        uint32_t k = kfirst;
+        for (; k + (U - 1) * kstep < k1; k += U * kstep) {
+            uint32_t ci[U];
+            E a[U], x[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) ci[u] = colidx[k + u * kstep];
+#pragma unroll
+            for (int u = 0; u < U; u++) a[u] = ld_fe<L>(data + (size_t)(k + u * kstep) * L);
+#pragma unroll
+            for (int u = 0; u < U; u++) x[u] = ld_fe<L>(xT + ((size_t)ci[u] * bp + b) * L);
+#pragma unroll
+            for (int u = 0; u < U; u++) F::dot_mac(acc, a[u], x[u]);
+        }
+        for (; k < k1; k += kstep) {
             const E a = ld_fe<L>(data + (size_t)k * L);
             const E x = ld_fe<L>(xT + ((size_t)colidx[k] * bp + b) * L);
             F::dot_mac(acc, a, x);
