@@ -149,3 +149,20 @@ def test_cpp_host_mirror_builds_and_runs(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, (res.stdout, res.stderr)
     assert "host mirror ok" in res.stdout
+
+
+def test_rust_sys_bindings_cover_the_header():
+    """rust/lcpc-b200-sys/src/lib.rs is generated from include/lcpc_b200.h (tools/gen_rust_sys.py): every declared function
+    is bound, and the committed file is what the generator produces (no Rust toolchain here: source only)."""
+    import os
+    import re
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_rust_sys
+
+    text = open(gen_rust_sys.OUT).read()
+    assert text == gen_rust_sys.render(), "stale bindings: run python tools/gen_rust_sys.py"
+    bound = set(re.findall(r"pub fn (lcpc_\w+)", text))
+    assert bound == set(_lib.declared_symbols())
