@@ -96,6 +96,9 @@ class Context {
 public:
     explicit Context(int32_t device = 0) { check(lcpc_ctx_create(device, &h_)); }
     Context(int32_t device, void *cuda_stream) { check(lcpc_ctx_create_on_stream(device, cuda_stream, &h_)); }
+    // several devices of this process: commitments made through encodings on this context are sharded inside the library
+    explicit Context(const std::vector<int32_t> &devices) { check(lcpc_ctx_create_multi(devices.data(), (int32_t)devices.size(), &h_)); }
+    int32_t n_devices() const { return lcpc_ctx_device_count(h_); }
     ~Context() { if (h_) lcpc_ctx_destroy(h_); }
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
@@ -139,6 +142,12 @@ public:
         const size_t per = n_cols * (size_t)field.limbs;
         if (per == 0 || rows.size() % per) throw Error(LCPC_ERR_ENCODE, "row length must be n_cols");
         check(lcpc_encode_rows(plan_, rows.data(), rows.size() / per));
+    }
+    // fffft ifft_oi on whole encoded rows in place (proof-of-storage decode_row, lcpc_online.rs:568-573); Ligero only
+    void decode(std::vector<uint64_t> &rows) const {
+        const size_t per = n_cols * (size_t)field.limbs;
+        if (per == 0 || rows.size() % per) throw Error(LCPC_ERR_ENCODE, "row length must be n_cols");
+        check(lcpc_decode_rows(plan_, rows.data(), rows.size() / per));
     }
     // (n_rows, n_per_row, n_cols)
     std::array<size_t, 3> get_dims(size_t len) const {

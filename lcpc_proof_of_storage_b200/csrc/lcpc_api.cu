@@ -1,6 +1,9 @@
 // C ABI of lcpc_b200 (see include/lcpc_b200.h for the contract and the reference
 // items each entry point replaces).  Handles own device memory; host buffers belong to
 // the caller.  No CPU fallback: without a CUDA device every call fails loudly.
+#include <algorithm>
+#include <cstdlib>
+
 #include "lcpc_handles.h"
 
 using namespace lcpc;
@@ -213,13 +216,25 @@ int32_t commit_host_pipelined(lcpc_plan *plan, lcpc_commit *c, const uint64_t *h
     CU(cudaEventRecord(ready, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->s_in, ready, 0));
     CU(cudaStreamWaitEvent(ctx->s_out, ready, 0));
-    // 8 chunks: measured best at 2^24 (5.55 ms; 32 chunks of 8 MiB: 6.78 ms -- many small copies in both directions
-    // leave bubbles between the copy engines' event waits)
-    size_t n_chunks = n_rows < 8 ? n_rows : 8;
-    const size_t rows_per = (n_rows + n_chunks - 1) / n_chunks;
-    n_chunks = (n_rows + rows_per - 1) / rows_per;
+    // Row chunks: 8 equal ones measured best at 2^24 in round 1 (32 chunks of 8 MiB: many small copies in both directions
+    // leave bubbles between the copy engines' event waits); the first chunk is split in two so that the device-to-host
+    // stream, which bounds the call, starts after half as much input.  LCPC_COMMIT_CHUNKS / LCPC_COMMIT_RAMP override
+    // for experiments (tools/e2e_sharded_probe.py).
+    size_t want_chunks = 8;
+    bool ramp = true;
+    if (const char *e = getenv("LCPC_COMMIT_CHUNKS")) want_chunks = (size_t)std::max(1, atoi(e));
+    if (const char *e = getenv("LCPC_COMMIT_RAMP")) ramp = atoi(e) != 0;
+    std::vector<size_t> bounds{0};
+    {
+        size_t k = n_rows < want_chunks ? n_rows : want_chunks;
+        const size_t per = (n_rows + k - 1) / k;
+        if (ramp && per >= 2) bounds.push_back(per / 2);
+        for (size_t r = per; r < n_rows; r += per) bounds.push_back(r);
+        bounds.push_back(n_rows);
+    }
+    const size_t n_chunks = bounds.size() - 1;
     for (size_t k = 0; k < n_chunks; k++) {
-        const size_t r0 = k * rows_per, nr = r0 + rows_per <= n_rows ? rows_per : n_rows - r0;
+        const size_t r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
         const size_t e0 = r0 * npr, e1 = (r0 + nr) * npr;  // element range of this chunk's coefficient rows
         const size_t have = n_coeffs > e0 ? (n_coeffs < e1 ? n_coeffs - e0 : e1 - e0) : 0;
         if (have)

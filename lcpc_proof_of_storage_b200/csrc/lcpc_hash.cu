@@ -319,17 +319,19 @@ __device__ __forceinline__ size_t level_offset(size_t np2, int l) { return l == 
 // The Merkle levels above one tile of T = blockDim.x adjacent leaves (thread t holds leaf tile*T + t in `leaf`): the
 // leaf level and the log2(T) levels inside the tile are written to the flat tree; then the LAST tile of the launch to
 // get here (ticket counter, left at zero again) computes the levels above the tile roots.  One launch builds the tree.
+// tw: leaves per tile (a power of two <= T; T when 0); the CTA may have more threads than that.
 template <int T>
 __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, uint8_t *hashes, size_t np2, unsigned *ticket,
-                                          unsigned n_tiles, uint32_t (*buf)[T][8], unsigned *s_flag) {
+                                          unsigned n_tiles, uint32_t (*buf)[T][8], unsigned *s_flag, unsigned tw = 0) {
     const unsigned t = threadIdx.x;
-    const size_t tile_n = np2 < (size_t)T ? np2 : (size_t)T;
+    if (tw == 0) tw = T;
+    const size_t tile_n = np2 < (size_t)tw ? np2 : (size_t)tw;
     int lt = 0;
     while (((size_t)1 << lt) < tile_n) lt++;
     if (t < tile_n) {
 #pragma unroll
         for (int k = 0; k < 8; k++) buf[0][t][k] = leaf[k];
-        uint4 *g = reinterpret_cast<uint4 *>(hashes + (tile * T + t) * 32);
+        uint4 *g = reinterpret_cast<uint4 *>(hashes + (tile * tw + t) * 32);
         g[0] = make_uint4(leaf[0], leaf[1], leaf[2], leaf[3]);
         g[1] = make_uint4(leaf[4], leaf[5], leaf[6], leaf[7]);
     }
@@ -366,7 +368,7 @@ __device__ __forceinline__ void tile_tree(const uint32_t leaf[8], size_t tile, u
         const size_t n_out = np2 >> l;
         const uint4 *in = reinterpret_cast<const uint4 *>(hashes + level_offset(np2, l - 1) * 32);
         uint4 *out = reinterpret_cast<uint4 *>(hashes + level_offset(np2, l) * 32);
-        for (size_t i = t; i < n_out; i += T) {
+        for (size_t i = t; i < n_out; i += blockDim.x) {
             const uint4 a0 = __ldcg(in + 4 * i), a1 = __ldcg(in + 4 * i + 1), b0 = __ldcg(in + 4 * i + 2), b1 = __ldcg(in + 4 * i + 3);
             const uint32_t lft[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const uint32_t rgt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -386,9 +388,11 @@ constexpr int MT_TILE = 256;
 // PAR: the BLAKE3 parent tree over a column's n_chunks chaining values, level by level across the CTA instead of one
 // thread walking it: BLAKE3's tree ("the left subtree takes the largest power of two of chunks below the total") is the
 // tree obtained by pairing adjacent nodes and carrying an odd last node up unchanged, so level k is
-// floor(n_k / 2) independent compressions per column.  C columns at a time sit in shared memory as [chunk][column]
-// (two buffers used alternately); depth ceil(log2 n_chunks) instead of n_chunks - 1 -- at 8 GPUs the leaves of the
-// weak-scaling bench have 33 chunks and a rank owns only 8192 columns, so the serial walk was a 32-deep chain on 32 CTAs.
+// floor(n_k / 2) independent compressions per column.  A CTA owns only C columns (their chaining values sit in shared
+// memory as [chunk][column], two buffers used alternately) and the grid is np2 / C tiles: depth ceil(log2 n_chunks)
+// instead of n_chunks - 1, and enough CTAs to fill the machine when few columns meet many chunks -- at 8 GPUs the leaves
+// of the weak-scaling bench have 33 chunks and a rank owns 8192 columns: the per-thread walk was a 32-deep chain on 32
+// CTAs (0.063 ms); 512 CTAs of 16 columns walk 6 levels.
 // cv_stride: columns per chunk row of `cvs` (n_cols, or the column-block width of a row-sharded store).
 template <bool PAR>
 __global__ void __launch_bounds__(MT_TILE)
@@ -398,64 +402,64 @@ k_merge_tree(const uint32_t *cvs, size_t n_cols, size_t cv_stride, uint64_t n_ch
     __shared__ unsigned s_flag;
     extern __shared__ uint32_t sm_cv[];  // PAR: [n_chunks][C][8] | [(n_chunks + 1) / 2][C][8]
     const unsigned t = threadIdx.x;
-    const size_t j = (size_t)blockIdx.x * MT_TILE + t;
     uint32_t leaf[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) leaf[k] = 0;
     if constexpr (PAR) {
         const unsigned nc = (unsigned)n_chunks;
-        uint32_t *bufA = sm_cv, *bufB = sm_cv + (size_t)nc * C * 8;
-        for (unsigned sub = 0; sub < MT_TILE; sub += C) {
-            const size_t j0 = (size_t)blockIdx.x * MT_TILE + sub;
-            if (j0 < n_cols) {
-                for (unsigned idx = t; idx < nc * C * 2; idx += MT_TILE) {  // 16 bytes per thread per trip, coalesced
-                    const unsigned c = idx / (2 * C), rem = idx % (2 * C), col = rem >> 1, half = rem & 1;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (j0 + col < n_cols) v = __ldcg(reinterpret_cast<const uint4 *>(cvs + ((size_t)c * cv_stride + j0 + col) * 8) + half);
-                    *reinterpret_cast<uint4 *>(bufA + ((size_t)c * C + col) * 8 + half * 4) = v;
+        uint32_t *in = sm_cv, *out = sm_cv + (size_t)nc * C * 8;
+        const size_t j0 = (size_t)blockIdx.x * C;
+        if (j0 < n_cols) {
+            for (unsigned idx = t; idx < nc * C * 2; idx += MT_TILE) {  // 16 bytes per thread per trip, coalesced
+                const unsigned c = idx / (2 * C), rem = idx % (2 * C), col = rem >> 1, half = rem & 1;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (j0 + col < n_cols) v = __ldcg(reinterpret_cast<const uint4 *>(cvs + ((size_t)c * cv_stride + j0 + col) * 8) + half);
+                *reinterpret_cast<uint4 *>(in + ((size_t)c * C + col) * 8 + half * 4) = v;
+            }
+            __syncthreads();
+            unsigned n = nc;
+            while (n > 1) {
+                const unsigned pairs = n >> 1;
+                const uint32_t flags = n == 2 ? (uint32_t)b3::ROOT : 0u;
+                for (unsigned idx = t; idx < pairs * C; idx += MT_TILE) {
+                    const unsigned p = idx / C, col = idx % C;
+                    uint32_t o[8];
+                    b3::parent_cv(in + ((size_t)(2 * p) * C + col) * 8, in + ((size_t)(2 * p + 1) * C + col) * 8, flags, o);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) out[((size_t)p * C + col) * 8 + k] = o[k];
+                }
+                if (n & 1) {  // the odd last node moves up unchanged
+                    for (unsigned idx = t; idx < (unsigned)C * 8; idx += MT_TILE)
+                        out[(size_t)pairs * C * 8 + idx] = in[(size_t)(n - 1) * C * 8 + idx];
                 }
                 __syncthreads();
-                uint32_t *in = bufA, *out = bufB;
-                unsigned n = nc;
-                while (n > 1) {
-                    const unsigned pairs = n >> 1;
-                    const uint32_t flags = n == 2 ? (uint32_t)b3::ROOT : 0u;
-                    for (unsigned idx = t; idx < pairs * C; idx += MT_TILE) {
-                        const unsigned p = idx / C, col = idx % C;
-                        uint32_t o[8];
-                        b3::parent_cv(in + ((size_t)(2 * p) * C + col) * 8, in + ((size_t)(2 * p + 1) * C + col) * 8, flags, o);
+                uint32_t *tmp = in;
+                in = out;
+                out = tmp;
+                n = pairs + (n & 1);
+            }
+            // row 0 of `in` holds the leaves of columns j0 .. j0 + C
+            if (t < (unsigned)C && j0 + t < n_cols) {
 #pragma unroll
-                        for (int k = 0; k < 8; k++) out[((size_t)p * C + col) * 8 + k] = o[k];
-                    }
-                    if (n & 1) {  // the odd last node moves up unchanged
-                        for (unsigned idx = t; idx < (unsigned)C * 8; idx += MT_TILE)
-                            out[(size_t)pairs * C * 8 + idx] = in[(size_t)(n - 1) * C * 8 + idx];
-                    }
-                    __syncthreads();
-                    uint32_t *tmp = in;
-                    in = out;
-                    out = tmp;
-                    n = pairs + (n & 1);
-                }
-                // row 0 of `in` holds the leaves of columns j0 .. j0 + C
-                if (t >= sub && t < sub + C && j < n_cols) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) leaf[k] = in[(size_t)(t - sub) * 8 + k];
-                }
-                __syncthreads();  // before the next sub-tile overwrites the buffers
+                for (int k = 0; k < 8; k++) leaf[k] = in[(size_t)t * 8 + k];
             }
         }
-    } else if (j < n_cols) {
-        if (n_chunks > 1) {
-            merge_column(leaf, cvs, cv_stride, n_chunks, j);
-        } else {
-            const uint4 *in = reinterpret_cast<const uint4 *>(hashes + j * 32);
-            const uint4 a = __ldcg(in), b = __ldcg(in + 1);
-            leaf[0] = a.x; leaf[1] = a.y; leaf[2] = a.z; leaf[3] = a.w;
-            leaf[4] = b.x; leaf[5] = b.y; leaf[6] = b.z; leaf[7] = b.w;
+        tile_tree<MT_TILE>(leaf, blockIdx.x, hashes, np2, ticket, gridDim.x, buf, &s_flag, (unsigned)C);
+        return;
+    } else {
+        const size_t j = (size_t)blockIdx.x * MT_TILE + t;
+        if (j < n_cols) {
+            if (n_chunks > 1) {
+                merge_column(leaf, cvs, cv_stride, n_chunks, j);
+            } else {
+                const uint4 *in = reinterpret_cast<const uint4 *>(hashes + j * 32);
+                const uint4 a = __ldcg(in), b = __ldcg(in + 1);
+                leaf[0] = a.x; leaf[1] = a.y; leaf[2] = a.z; leaf[3] = a.w;
+                leaf[4] = b.x; leaf[5] = b.y; leaf[6] = b.z; leaf[7] = b.w;
+            }
         }
+        tile_tree<MT_TILE>(leaf, blockIdx.x, hashes, np2, ticket, gridDim.x, buf, &s_flag);
     }
-    tile_tree<MT_TILE>(leaf, blockIdx.x, hashes, np2, ticket, gridDim.x, buf, &s_flag);
 }
 
 // The whole of merkleize (lib.rs:720-734) in ONE launch: grid = (chunks, tiles of 128 columns over the PADDED leaf range).
@@ -616,20 +620,29 @@ cudaError_t merge_tree(const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, u
     if (np2 == 0 || n_cols > np2) return cudaErrorInvalidValue;
     if (cv_stride == 0) cv_stride = n_cols;
     const unsigned tiles = (unsigned)((np2 + MT_TILE - 1) / MT_TILE);
-    // columns per shared-memory sub-tile of the level-wise merge: the largest power of two <= 32 whose two buffers
-    // (1.5 x n_chunks rows of C digests) fit 30 KiB (beside 16 KiB of static tile buffers, under the 48 KiB default); the serial per-thread walk when that leaves fewer than 4 columns.
-    // With few chunks per leaf and many columns (one GPU: 5 chunks, 65536 columns) the walk is short and every SM is
-    // busy anyway, and the level-wise form's extra shared-memory traffic only costs: serial below 8 chunks.
+    // Level-wise merge (PAR) or the per-thread walk?  Both do the same n_chunks - 1 compressions per column; the walk keeps
+    // every thread busy but is a chain of n_chunks - 1 dependent compressions on n_cols / 256 CTAs, the level-wise form is
+    // ceil(log2 n_chunks) deep on n_cols / C CTAs with a third of its threads busy on average.  Measured
+    // (tools/bench_merge_tree.py, profiles/r02_hash_tail.md): 33 chunks x 8192 columns 54 -> 33 us, 147 x 8192 191 -> 95 us,
+    // 17 x 16384 a tie, and from 32768 columns up the walk wins by 1.5 - 2 x.  So: level-wise when a leaf has at least 8
+    // chunks and there are at most 16384 columns (a rank's column block of a sharded commitment, the proof-of-storage
+    // shapes); C = the largest power of two <= 32 whose two buffers (1.5 x n_chunks rows of C digests) fit 30 KiB beside
+    // the 16 KiB of static tile buffers.
     int C = 0;
-    if (n_chunks >= 8) {
+    if (n_chunks >= 8 && n_cols <= 16384) {
         for (C = 32; C >= 4; C >>= 1)
-            if ((n_chunks + (n_chunks + 1) / 2) * (uint64_t)C * 32 <= 30 * 1024) break;
+            if ((n_chunks + (n_chunks + 1) / 2) * (uint64_t)C * 32 <= 30 * 1024 && (size_t)C <= np2) break;
         if (C < 4) C = 0;
+    }
+    if (const char *e = getenv("LCPC_MERGE_PAR")) {  // experiments: 0 forces the per-thread walk, n >= 4 that many columns per CTA
+        const int v = atoi(e);
+        if (v == 0) C = 0;
+        else if (n_chunks >= 2 && (n_chunks + (n_chunks + 1) / 2) * (uint64_t)v * 32 <= 30 * 1024 && (size_t)v <= np2) C = v;
     }
     lc.begin("k_merge_tree");
     if (C > 0) {
         const size_t smem = (size_t)(n_chunks + (n_chunks + 1) / 2) * C * 32;
-        k_merge_tree<true><<<tiles, MT_TILE, smem, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, cv_stride, n_chunks,
+        k_merge_tree<true><<<(unsigned)(np2 / C), MT_TILE, smem, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, cv_stride, n_chunks,
                                                           d_hashes, np2, d_ticket, C);
     } else {
         k_merge_tree<false><<<tiles, MT_TILE, 0, lc.s>>>(reinterpret_cast<const uint32_t *>(d_cvs), n_cols, cv_stride, n_chunks,
