@@ -68,8 +68,7 @@ def commit_case(name, enc, n, steps=10):
 
     def step():
         _lib.check(lib.lcpc_dev_encode(enc.plan, coeffs.data_ptr(), n_rows, comm.data_ptr()))
-        _lib.check(lib.lcpc_dev_hash_columns(ctx.handle, fid, comm.data_ptr(), n_rows, n_cols, n_cols, hashes.data_ptr()))
-        _lib.check(lib.lcpc_dev_merkle_tree(ctx.handle, hashes.data_ptr(), np2))
+        _lib.check(lib.lcpc_dev_merkleize(ctx.handle, fid, comm.data_ptr(), n_rows, n_cols, n_cols, hashes.data_ptr()))
 
     ms, kt = timed(step, steps)
     alg = n * 8 * L + n_rows * n_cols * 8 * L + (2 * np2 - 1) * 32
@@ -160,8 +159,7 @@ def main():
             def step():
                 _lib.check(lib.lcpc_dev_pack_bytes7(ctx.handle, data.data_ptr(), n_bytes, elems.data_ptr()))
                 _lib.check(lib.lcpc_dev_encode(enc.plan, elems.data_ptr(), n_rows, comm.data_ptr()))
-                _lib.check(lib.lcpc_dev_hash_columns(ctx.handle, 0, comm.data_ptr(), n_rows, 65536, 65536, hashes.data_ptr()))
-                _lib.check(lib.lcpc_dev_merkle_tree(ctx.handle, hashes.data_ptr(), 65536))
+                _lib.check(lib.lcpc_dev_merkleize(ctx.handle, 0, comm.data_ptr(), n_rows, 65536, 65536, hashes.data_ptr()))
 
             ms, kt = timed(step, 5)
             print(json.dumps({"case": "pos_1GiB_file", "n_rows": n_rows, "ms": round(ms, 3), "file_GBps": n_bytes / ms / 1e6,
