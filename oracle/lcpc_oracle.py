@@ -11,8 +11,12 @@ Montgomery residue, least-significant limb first -- bit-identical to a Rust
 ``&[F]`` (SURVEY.md section 8 a').  Paths cited are relative to /root/reference.
 
 Parity status: blake3 / ChaCha20 / Keccak / merlin / field arithmetic are pinned
-against independent implementations (tests/test_oracle_*.py).  The Ligero NTT
-convention (fffft, not in the tree) is PARITY UNPINNED.
+against independent implementations (tests/test_oracle_*.py).  PARITY UNPINNED (two
+items, no reference-attested vector exists and the Rust reference cannot be built
+here): the Ligero NTT convention (fffft, not in the tree) and the consumers of the
+ChaCha streams as rand 0.8 / rand_chacha 0.3 / ff 0.13 define them (seed_from_u64,
+set_stream, Uniform, choose_multiple, F::random), both restated as recalled;
+rust/lcpc-b200/tests/parity.rs pins them where cargo exists.
 """
 from __future__ import annotations
 
