@@ -71,6 +71,12 @@ def workload_name(n_gpus: int) -> str:
             f"({rows * N_PER_ROW} coefficients)")
 
 
+def workload_config(n_gpus: int) -> dict:
+    """`config` of the result line: the workload and nothing else, identical in both arms (ours and --impl reference)."""
+    return {"workload": workload_name(n_gpus), "field": "Ft63", "n_rows": ROWS_PER_GPU * n_gpus, "n_per_row": N_PER_ROW,
+            "n_cols": N_COLS, "digest": "BLAKE3", "l2": "inputs larger than L2 (128 MiB in, 256 MiB out per GPU)"}
+
+
 def algorithmic_bytes(n_coeffs: int, n_rows: int) -> int:
     """read coeffs once + write encoded matrix once + write the tree."""
     return n_coeffs * 8 + n_rows * N_COLS * 8 + (2 * N_COLS - 1) * 32
@@ -379,6 +385,97 @@ def run_configs(torch, P, lib, _lib, ctx, stream, peak_gbs: float, d_coeffs_24) 
     return out
 
 
+def run_pos_config(torch, dist, P, ctx, stream, rank: int, world: int, peak_gbs: float):
+    """BASELINE configs[3] at N > 1: proof-of-storage commit of a 4 GiB synthetic file sharded over the ranks (7-byte packing
+    on the device, default aspect of networking/server.rs:1139-1182: 18725 rows x 32768 -> 65536), then the retrievability
+    proof -- the 309 columns of get_column_indicies_from_random_seed(1337, ..) opened with their Merkle paths -- and its
+    verification on rank 0.  Root, column indices, opened values, paths and leaves are checked against the CPU oracle's
+    (tests/golden/pos_4gib.json).  Returns the `configs` entry on rank 0, None elsewhere."""
+    import hashlib
+
+    from lcpc_proof_of_storage_b200 import pos
+    from lcpc_proof_of_storage_b200 import synth as S
+    from lcpc_proof_of_storage_b200.sharded import ShardedLigeroCommitter
+
+    n_bytes = 1 << 32
+    pre, enc_cols, soundness = pos.get_aspect_ratio_default_from_file_len(n_bytes)
+    n_elems = (n_bytes + 6) // 7
+    n_rows = (n_elems + pre - 1) // pre
+    dev = torch.device("cuda", ctx.device)
+    enc = P.LigeroEncoding(P.FT63, pre, enc_cols, ctx=ctx)
+    sc = ShardedLigeroCommitter(enc, n_rows, dist.group.WORLD, hashing="auto")
+    lo, hi = sc.byte_range(n_bytes)
+    lo8 = lo - lo % 8
+    data = S.bytes_torch(4, hi - lo8, dev, lo8)[lo - lo8:].clone()
+    for _ in range(2):
+        sc.commit_bytes(data)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        sc.commit_bytes(data)
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_commit = float(t.item())
+    cols = pos.get_column_indicies_from_random_seed(1337, soundness, enc_cols)
+    sc.open_columns(cols)  # first use: staging buffers, NCCL channels
+    ms_open_dev = None
+    if sc.hashing == "rows":
+        dist.barrier()
+        torch.cuda.synchronize()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for _ in range(5):
+            sc.open_columns_dev(cols)
+        e3.record(stream)
+        torch.cuda.synchronize()
+        ms_open_dev = e2.elapsed_time(e3) / 5
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    opened = sc.open_columns(cols)
+    torch.cuda.synchronize()
+    ms_open_host = (time.perf_counter() - t0) * 1e3
+    if rank != 0:
+        return None
+    root = sc.root()
+    t0 = time.perf_counter()
+    try:
+        pos.client_online_verify_column_paths(root, cols, opened, ctx)
+        verified = True
+    except Exception:
+        verified = False
+    ms_verify = (time.perf_counter() - t0) * 1e3
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "pos_4gib.json")) as f:
+            want = json.load(f)
+    except OSError:
+        want = None
+    known = None
+    if want:
+        vals = np.stack([o.col for o in opened])
+        paths = np.stack([o.path for o in opened])
+        leaves, _ = pos._verify_columns(ctx, opened, None, None)
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        known = {"root": root.hex() == want["root"], "columns": cols == want["columns"],
+                 "column_values": sha(vals) == want["column_values_sha256"], "paths": sha(paths) == want["paths_sha256"],
+                 "leaves": sha(leaves) == want["leaves_sha256"]}
+    alg = n_bytes + n_rows * enc_cols * 8 + (2 * enc_cols - 1) * 32   # SURVEY 8(d): PoS commit from bytes
+    gbs = alg / (ms_commit * 1e-3) / 1e9
+    return {"workload": f"proof-of-storage commit, 4 GiB file, WriteableFt63, {n_rows} rows x {pre} -> {enc_cols}, sharded over "
+                        f"{world} GPUs; retrievability proof of {len(cols)} columns (seed 1337)",
+            "ms": ms_commit, "elements_per_s": n_elems / (ms_commit * 1e-3), "file_GBps": n_bytes / (ms_commit * 1e-3) / 1e9,
+            "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / (peak_gbs * world), "hashing": sc.hashing, "cv_fused": sc.cv_fused,
+            "open_columns": len(cols), "open_on_device_ms": ms_open_dev, "open_to_host_ms": ms_open_host,
+            "open_bytes": len(cols) * (n_rows * 8 + int(opened[0].path.size)), "verify_paths_ms": ms_verify,
+            "verified": verified, "root": root.hex(), "matches_known_answer": None if known is None else all(known.values()),
+            "known_answers": known}
+
+
 def sharded_parity_checks(torch, dist, P, ctx, rank: int, world: int) -> dict:
     """Small sharded cases against committed known answers (tests/golden/bench_roots.json `parity`), run on every rank
     before the timed region: both hashing modes and the fused exchange on a Ligero commit, the coefficient fold, the fold
@@ -487,7 +584,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (63-bit prime field, Montgomery)", "data": "synthetic",
-        "config": {"workload": workload_name(max(1, args.gpus)), "sample": f"{sample_rows} of {n_rows} rows per step"},
+        "config": workload_config(max(1, args.gpus)), "sample": f"{sample_rows} of {n_rows} rows per step",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample_rows} rows x {N_PER_ROW} -> {N_COLS} (full width), C restatement "
                                    f"of the reference algorithm, OpenMP over rows / 32-column blocks"},
@@ -532,7 +629,8 @@ def main() -> None:
                          "where the rows are and the hash kernel stores the 32-byte chaining values into the owners' stores "
                          "over NVLink; 'rows': the same values through an NCCL all-to-all; 'columns': the encoded matrix is "
                          "re-sharded to column blocks (the NTT's last pass stores into peer HBM)")
-    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the `configs` block (the other BASELINE.json cases)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the `configs` block (N = 1: Ligero 2^28, Brakedown Ft255 2^24, folds; N > 1: the 4 GiB proof-of-storage file)")
     ap.add_argument("--no-parity-checks", action="store_true", help="N > 1: skip the sharded known-answer checks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -792,6 +890,18 @@ def main() -> None:
                              "h2d_bytes_per_step": n_local * 8 * world, "d2h_bytes_per_step": 32,
                              "api": "ShardedLigeroCommitter.commit_host (pinned host row shards in; Merkle root out on rank 0)"}}
 
+    # ---- BASELINE configs[3] on the N GPUs (N > 1): 4 GiB proof-of-storage file, commit + retrievability proof + verify
+    pos_cfg = None
+    if world > 1 and not args.no_configs:
+        del h_comm
+        sc_fused, sc_cv_fused, sc_hashing = sc.fused, sc.cv_fused, sc.hashing
+        sc = None  # release the headline workload's buffers (symmetric memory stays mapped until exit)
+        torch.cuda.empty_cache()
+        pos_cfg = run_pos_config(torch, dist, P, ctx, stream, rank, world, measured_peak_gbs()[0])
+
+    elif world > 1:
+        sc_fused, sc_cv_fused, sc_hashing = sc.fused, sc.cv_fused, sc.hashing
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -834,7 +944,9 @@ def main() -> None:
     step_gbs = algorithmic_bytes(n_total, n_rows_total) / (ms_per_step * 1e-3) / 1e9
 
     # ---- the other BASELINE.json configurations (N = 1) ----------------------------------------------
-    configs = None
+    configs = {"pos_4gib": pos_cfg} if pos_cfg is not None else None
+    if pos_cfg is not None:
+        assert pos_cfg["matches_known_answer"] is not False and pos_cfg["verified"], f"configs[3] differs from its known answer: {pos_cfg}"
     if world == 1 and not args.no_configs:
         del d_comm, d_hashes, h_comm, h_hashes
         torch.cuda.empty_cache()
@@ -879,16 +991,15 @@ def main() -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 (63-bit prime field, Montgomery)", "data": "synthetic",
-        "config": {"workload": workload_name(world), "field": "Ft63", "n_rows": n_rows_total, "n_per_row": N_PER_ROW,
-                   "n_cols": N_COLS, "digest": "BLAKE3", "l2": "inputs larger than L2 (128 MiB in, 256 MiB out per GPU)",
-                   "parallelism": "single GPU" if world == 1 else (
+        "config": workload_config(world),
+        "parallelism": "single GPU" if world == 1 else (
                        f"row shards x{world}; " + ("encode kernel stores into peer column blocks over NVLink (symmetric memory); commit k hashed "
                                                     "after commit k+1's encode is issued, all K finished inside the timed region"
-                                                   if sc.fused else ("BLAKE3 chunk chaining values hashed where the rows are, "
+                                                   if sc_fused else ("BLAKE3 chunk chaining values hashed where the rows are, "
                                                                      + ("stored by the hash kernel into the owners' stores over NVLink"
-                                                                        if sc.cv_fused else "NCCL all-to-all of 32 B per chunk and column")
-                                                                     if sc.hashing == "rows" else "NCCL all-to-all"))
-                       + "; per-rank Merkle subtrees, roots all-gathered")},
+                                                                        if sc_cv_fused else "NCCL all-to-all of 32 B per chunk and column")
+                                                                     if sc_hashing == "rows" else "NCCL all-to-all"))
+                       + "; per-rank Merkle subtrees, roots all-gathered"),
         "algorithmic_GBps": step_gbs, "frac_of_hbm_peak_whole_commit": step_gbs / peak,
         "single_commit_latency_ms": latency_ms,
         "host_binding": numa,

@@ -298,9 +298,19 @@ def _worker_rows(rank, world, port, q, cv_fused=False):
             folded_enc = sc.fold_encoded(t_dev)
             cols = [0, n_cols - 1, n_cols // 2, n_cols // 2 - 1]
             opened = sc.open_columns(cols)
+            dev_open = sc.open_columns_dev(cols)   # the same openings left on the device (rank 0)
+            # the end-to-end form: pinned host rows in, encoded rows out, PCIe / encode overlapped over row chunks
+            h_in = local.cpu().pin_memory()
+            h_out = torch.empty(cnt * n_cols * L, dtype=torch.int64).pin_memory()
+            sc.commit_host(h_in, h_out, n_chunks=3)
+            sc.wait_host_copies()
+            torch.cuda.synchronize()
+            exp = O.commit(coeffs[:n], O.LigeroEncoding(fid, n_per_row, n_cols))
+            ok &= np.array_equal(h_out.numpy().view(np.uint64).reshape(cnt, n_cols, L), exp.comm[r0:r0 + cnt])
             if rank == 0:
-                exp = O.commit(coeffs[:n], O.LigeroEncoding(fid, n_per_row, n_cols))
                 ok &= sc.root() == exp.get_root()
+                ok &= np.array_equal(dev_open[0].cpu().numpy().view(np.uint64), np.stack([O.open_column(exp, c).col for c in cols]))
+                ok &= np.array_equal(dev_open[1].cpu().numpy(), np.stack([O.open_column(exp, c).path for c in cols]))
                 ok &= np.array_equal(hashes.cpu().numpy().reshape(-1, 32), exp.hashes)
                 f = folded.cpu().numpy().view(np.uint64).reshape(2, n_per_row, L)
                 fe = folded_enc.cpu().numpy().view(np.uint64).reshape(2, n_cols, L)
@@ -314,6 +324,24 @@ def _worker_rows(rank, world, port, q, cv_fused=False):
             q.put(bool(ok))
     finally:
         dist.destroy_process_group()
+
+
+def test_row_hashed_commit_one_gpu():
+    """The row-hashed committer on a one-rank NCCL group (what the driver's one-GPU test box can run): commit, commit_host,
+    folds, openings on the host and on the device against the oracle."""
+    import torch.multiprocessing as mp
+
+    sk = socket.socket()
+    sk.bind(("127.0.0.1", 0))
+    port = sk.getsockname()[1]
+    sk.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_worker_rows, args=(0, 1, port, q, False))
+    p.start()
+    p.join(300)
+    assert p.exitcode == 0
+    assert q.get(timeout=5) is True
 
 
 @pytest.mark.parametrize("cv_fused", [False, True])
