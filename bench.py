@@ -537,7 +537,7 @@ def sharded_parity_checks(torch, dist, P, ctx, rank: int, world: int) -> dict:
     k = PARITY_CASES["brakedown"]
     enc_s = P.SdigEncoding.new_from_dims(FID, k["n_per_row"], k["n_cols"], seed=k["code_seed"], ctx=ctx)
     n_total = k["n_rows"] * k["n_per_row"] - 5
-    for mode in ("columns", "rows"):
+    for mode in ("columns", "rows", "auto"):   # auto = row hashing with the chaining values stored into the owners' stores
         sc = ShardedCommitter(enc_s, k["n_rows"], dist.group.WORLD, hashing=mode)
         e0, e1 = sc.row0 * k["n_per_row"], (sc.row0 + sc.rows_local) * k["n_per_row"]
         coeffs = torch.zeros(sc.rows_local * k["n_per_row"], dtype=torch.int64, device=dev)
@@ -545,7 +545,16 @@ def sharded_parity_checks(torch, dist, P, ctx, rank: int, world: int) -> dict:
         if have:
             coeffs[:have] = S.ft63_torch(k["seed"], have, dev, start=e0)
         sc.commit(coeffs)
-        put(f"brakedown_{mode}_root", rank != 0 or sc.root().hex() == want.get("brakedown_root"))
+        put(f"brakedown_{'rows_fused' if mode == 'auto' else mode}_root", rank != 0 or sc.root().hex() == want.get("brakedown_root"))
+        if mode == "auto":
+            put("brakedown_auto_picks_fused_row_hashing", sc.hashing == "rows" and sc.cv_fused)
+            opened = sc.open_columns([0, k["n_cols"] - 1, 3000, 4095])
+            if rank == 0:
+                try:
+                    pos.client_online_verify_column_paths(sc.root(), [0, k["n_cols"] - 1, 3000, 4095], opened, ctx)
+                    put("brakedown_rows_fused_open_verify", True)
+                except Exception:
+                    put("brakedown_rows_fused_open_verify", False)
         del sc
     return res
 

@@ -331,8 +331,9 @@ int32_t lcpc_dev_hash_chunk_range(lcpc_ctx *ctx, int32_t field, const uint64_t *
                                   uint64_t chunk_end, uint8_t *d_cvs);
 /* lcpc_dev_hash_chunk_range with the exchange fused into the kernel: the chaining value of (chunk, column) is stored
  * directly into the chaining-value store of the rank that owns the column.  peer_cvs[g] is rank g's store,
- * [n_chunks_total][n_cols / n_peers][32 B] (this rank's own buffer or a peer-mapped pointer reached over NVLink);
- * n_cols and n_peers are powers of two, n_peers <= 16.  The caller synchronises the ranks before anyone runs
+ * [n_chunks_total][cb][32 B], cb = next_power_of_two(n_cols) / n_peers (this rank's own buffer or a peer-mapped pointer
+ * reached over NVLink): the PADDED leaf range is what is split, so with a non power-of-two n_cols (Brakedown) the last
+ * blocks hold fewer real columns or none; n_peers a power of two <= 16.  The caller synchronises the ranks before anyone runs
  * lcpc_dev_hash_merge on its store. */
 int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const uint64_t *d_mat, uint64_t row_base,
                                           size_t n_rows_total, size_t row_stride, size_t n_cols, uint64_t chunk0,
@@ -343,9 +344,10 @@ int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, 
 /* lcpc_dev_hash_merge and lcpc_dev_merkle_tree in ONE launch: d_hashes is the flat tree [n_leaves | n_leaves/2 | ... | 1]
  * (n_leaves a power of two >= n_cols); leaves [0, n_cols) come from the chaining values (n_chunks >= 2) or are already in
  * d_hashes (n_chunks == 1, d_cvs may be NULL), leaves [n_cols, n_leaves) are written as zero (lib.rs:685-695), then
- * every level above.  The last CTA to finish its tile builds the top levels, so no second launch exists. */
+ * every level above.  cv_stride: columns per chunk row of d_cvs (0 = n_cols; the column-block width when d_cvs is a store
+ * filled by lcpc_dev_hash_chunk_range_scatter and the block holds fewer real columns than it is wide).  The last CTA to finish its tile builds the top levels, so no second launch exists. */
 int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes,
-                                 size_t n_leaves);
+                                 size_t n_leaves, size_t cv_stride);
 /* merkleize (lib.rs:720-734) of a device matrix in one launch: leaf hashing of columns [0, n_cols) (row stride
  * `row_stride` elements), the BLAKE3 parent tree per leaf and the Merkle tree over next_power_of_two(n_cols) leaves
  * into d_hashes ((2*np2-1)*32 bytes). */

@@ -108,7 +108,7 @@ _SIGNATURES = {
                                             C.POINTER(C.c_void_p), C.c_size_t]),
     "lcpc_dev_hash_columns": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_merkle_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
-    "lcpc_dev_hash_merge_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "lcpc_dev_hash_merge_tree": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
     "lcpc_dev_merkleize": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "lcpc_dev_fold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),

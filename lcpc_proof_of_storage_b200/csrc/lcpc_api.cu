@@ -1042,8 +1042,8 @@ int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const ui
     ctx = primary(ctx);
     if (!ctx || !d_mat || !peer_cvs) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (!valid_field(field)) return fail(LCPC_ERR_INVALID_ARG, "unknown field id");
-    if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || n_cols == 0 || (n_cols & (n_cols - 1)) || n_cols % n_peers)
-        return fail(LCPC_ERR_DIMS, "n_cols and n_peers must be powers of two, n_peers <= 16");
+    if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || n_cols == 0 || next_pow2(n_cols) < n_peers)
+        return fail(LCPC_ERR_DIMS, "n_peers must be a power of two <= 16 and <= the padded column count");
     const uint64_t w = 8ull * (uint64_t)limbs_of(field);
     const uint64_t total = 32 + (uint64_t)n_rows_total * w, n_chunks = (total + 1023) / 1024;
     if (1024 % w != 0) return fail(LCPC_ERR_DIMS, "elements straddle BLAKE3 chunk boundaries for this field");
@@ -1053,7 +1053,7 @@ int32_t lcpc_dev_hash_chunk_range_scatter(lcpc_ctx *ctx, int32_t field, const ui
     if (chunk0 < chunk_end && first_row < row_base) return fail(LCPC_ERR_INVALID_ARG, "chunk range starts before row_base");
     CvScatter sc{};
     sc.log_cb = 0;
-    while (((size_t)1 << sc.log_cb) < n_cols / n_peers) sc.log_cb++;
+    while (((size_t)1 << sc.log_cb) < next_pow2(n_cols) / n_peers) sc.log_cb++;  // blocks of the PADDED leaf range
     for (size_t i = 0; i < n_peers; i++) {
         if (!peer_cvs[i]) return fail(LCPC_ERR_INVALID_ARG, "null peer pointer");
         sc.base[i] = reinterpret_cast<uint32_t *>(peer_cvs[i]);
@@ -1076,7 +1076,7 @@ int32_t lcpc_dev_hash_merge(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, 
 }
 
 int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_cols, uint64_t n_chunks, uint8_t *d_hashes,
-                                 size_t n_leaves) {
+                                 size_t n_leaves, size_t cv_stride) {
     ctx = primary(ctx);
     if (!ctx || !d_hashes || (!d_cvs && n_chunks > 1)) return fail(LCPC_ERR_INVALID_ARG, "null argument");
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1)) || n_cols > n_leaves) return fail(LCPC_ERR_DIMS, "n_leaves must be a power of two >= n_cols");
@@ -1085,7 +1085,8 @@ int32_t lcpc_dev_hash_merge_tree(lcpc_ctx *ctx, const uint8_t *d_cvs, size_t n_c
     CU(cudaSetDevice(ctx->device));
     unsigned *tk = nullptr;
     CU(ctx->tickets(1, &tk));
-    CU(merge_tree(d_cvs, n_cols, n_chunks, d_hashes, n_leaves, tk, ctx->lc()));
+    if (cv_stride != 0 && cv_stride < n_cols) return fail(LCPC_ERR_DIMS, "cv_stride below n_cols");
+    CU(merge_tree(d_cvs, n_cols, n_chunks, d_hashes, n_leaves, tk, ctx->lc(), cv_stride));
     return LCPC_OK;
 }
 

@@ -138,10 +138,12 @@ class GpuOps:
     def hash_merge(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, out: torch.Tensor) -> None:
         _lib.check(self.lib.lcpc_dev_hash_merge(self.enc.ctx.handle, cvs.data_ptr(), n_cols, n_chunks, out.data_ptr()))
 
-    def hash_merge_tree(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, tree: torch.Tensor, n_leaves: int) -> None:
-        """hash_merge + merkle_tree in one launch (padding leaves written as zero by the kernel)."""
+    def hash_merge_tree(self, cvs: torch.Tensor, n_cols: int, n_chunks: int, tree: torch.Tensor, n_leaves: int,
+                        cv_stride: int = 0) -> None:
+        """hash_merge + merkle_tree in one launch (padding leaves written as zero by the kernel); cv_stride = columns per
+        chunk row of `cvs` when that is wider than n_cols (a scatter store of a block with padding columns)."""
         _lib.check(self.lib.lcpc_dev_hash_merge_tree(self.enc.ctx.handle, cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(),
-                                                     n_leaves))
+                                                     n_leaves, cv_stride))
 
     def merkleize(self, mat: torch.Tensor, n_rows: int, row_stride: int, n_cols: int, tree: torch.Tensor) -> None:
         """hash_columns + merkle_tree over next_pow2(n_cols) leaves in one launch."""
@@ -214,9 +216,10 @@ class ShardedLigeroCommitter:
         self.rows = row_partition(n_rows_total, self.world)
         self.hashing, self.chunks = "columns", None
         if hashing == "auto":
-            ok = (chunk_row_partition(self.L, n_rows_total, self.world) is not None and isinstance(self.ops, GpuOps)
-                  and 1 < self.world <= 16 and self.np2 == self.n_cols)
-            hashing, fused = ("rows", True) if ok else ("columns", None)
+            if chunk_row_partition(self.L, n_rows_total, self.world) is None:
+                hashing, fused = "columns", None
+            else:  # stores over NVLink where peers can be mapped, the NCCL all-to-all of the chaining values otherwise
+                hashing, fused = "rows", isinstance(self.ops, GpuOps) and 1 < self.world <= 16
         if hashing == "rows":
             part = chunk_row_partition(self.L, n_rows_total, self.world)
             if part is None:
@@ -278,8 +281,8 @@ class ShardedLigeroCommitter:
                 self._symm = self._hdl = self._peer_ptrs = self._scratch = None
 
         if self.hashing == "rows" and self._cv_fused:
-            if not (isinstance(self.ops, GpuOps) and self.world > 1 and self.np2 == self.n_cols and self.world <= 16):
-                raise ValueError("fused chaining-value exchange needs the GPU back end, 2..16 ranks and power-of-two n_cols")
+            if not (isinstance(self.ops, GpuOps) and 1 < self.world <= 16):
+                raise ValueError("fused chaining-value exchange needs the GPU back end and 2..16 ranks")
             import ctypes as C
 
             import torch.distributed._symmetric_memory as symm_mem
@@ -415,8 +418,9 @@ class ShardedLigeroCommitter:
             self._roots = torch.empty(W * 32, dtype=torch.uint8, device=dev)
             self.top = torch.zeros((2 * W - 1) * 32, dtype=torch.uint8, device=dev)
         if self.cols_local and hasattr(self.ops, "hash_merge_tree"):
-            # leaves of my column block from the chaining values + my whole subtree: one launch
-            self.ops.hash_merge_tree(recv, self.cols_local, self.n_chunks, self.subtree, cb)
+            # leaves of my column block from the chaining values + my whole subtree: one launch (a scatter store is cb wide
+            # also when the block holds fewer real columns, the NCCL form is compact)
+            self.ops.hash_merge_tree(recv, self.cols_local, self.n_chunks, self.subtree, cb, cb if self.cv_fused else 0)
             self._join_subtrees(tree_done=True)
             return
         if self.cols_local:  # padding leaves are never written: they stay zero

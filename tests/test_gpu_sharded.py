@@ -259,7 +259,7 @@ def test_hash_merge_tree_one_launch(oracle, n_chunks, n_cols, n_leaves):
         tree = torch.full(((2 * n_leaves - 1) * 32,), 0xAB, dtype=torch.uint8, device="cuda")
         if n_chunks == 1:
             tree[:n_cols * 32] = d_cvs
-        _lib.check(lib.lcpc_dev_hash_merge_tree(ctx.handle, d_cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(), n_leaves))
+        _lib.check(lib.lcpc_dev_hash_merge_tree(ctx.handle, d_cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(), n_leaves, 0))
         assert np.array_equal(tree.cpu().numpy().reshape(-1, 32), exp)
 
 

@@ -21,7 +21,7 @@ for n_chunks, n_cols in [(5, 65536), (33, 8192), (17, 16384), (9, 32768), (147, 
         tree = torch.zeros((2 * n_cols - 1) * 32, dtype=torch.uint8, device="cuda")
 
         def fn():
-            _lib.check(lib.lcpc_dev_hash_merge_tree(ctx.handle, cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(), n_cols))
+            _lib.check(lib.lcpc_dev_hash_merge_tree(ctx.handle, cvs.data_ptr(), n_cols, n_chunks, tree.data_ptr(), n_cols, 0))
 
         for _ in range(3):
             fn()

@@ -41,7 +41,7 @@ def main():
     ap.add_argument("--log-n", dest="logs", type=int, nargs="*", default=[20, 22, 24, 26, 28])
     ap.add_argument("--schemes", nargs="*", default=["ligero63", "brakedown63", "brakedown255"])
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--hashing", default="columns", choices=["columns", "rows"],
+    ap.add_argument("--hashing", default="auto", choices=["auto", "columns", "rows"],
                     help="rows: hash BLAKE3 chunks where the rows are and re-shard chaining values (sharded.py)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -105,7 +105,7 @@ def main():
                 w = 8 * L
                 alg = n * w + n_rows * n_cols * w + (2 * P.next_pow2(n_cols) - 1) * 32
                 print(json.dumps({"case": f"{scheme}_2^{log_n}", "n_gpus": world, "shape": [n_rows, npr, n_cols],
-                                  "fused_nvlink": sc.fused, "ms_commit": round(ms_commit, 4), "coeffs_per_s": n / ms_commit * 1e3,
+                                  "hashing": sc.hashing, "cv_fused": sc.cv_fused, "fused_nvlink": sc.fused, "ms_commit": round(ms_commit, 4), "coeffs_per_s": n / ms_commit * 1e3,
                                   "commit_algorithmic_GBps": alg / ms_commit / 1e6, "n_folds": n_dt + 1,
                                   "ms_folds": round(ms_fold, 4), "fold_GBps": (n_dt + 1) * n * w / ms_fold / 1e6,
                                   "root": sc.root().hex()}), flush=True)
