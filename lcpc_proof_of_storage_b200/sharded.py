@@ -216,7 +216,12 @@ class ShardedLigeroCommitter:
         self.rows = row_partition(n_rows_total, self.world)
         self.hashing, self.chunks = "columns", None
         if hashing == "auto":
-            if chunk_row_partition(self.L, n_rows_total, self.world) is None:
+            part = chunk_row_partition(self.L, n_rows_total, self.world)
+            # row hashing cuts the rows on chunk boundaries: a leaf of few chunks (a short matrix: Brakedown's 13 - 404
+            # rows) leaves some ranks with far more rows than others, or none -- 202 rows of 8 bytes are two chunks, i.e.
+            # two busy ranks at any world size (profiles/r02_sweep.md).  Take it when the largest block is within 30 % of
+            # the even split, the even row split with column blocks otherwise.
+            if part is None or max(cnt for _, cnt in part[0]) > 1.3 * n_rows_total / self.world:
                 hashing, fused = "columns", None
             else:  # stores over NVLink where peers can be mapped, the NCCL all-to-all of the chaining values otherwise
                 hashing, fused = "rows", isinstance(self.ops, GpuOps) and 1 < self.world <= 16
