@@ -46,6 +46,7 @@ void free_csr(DevCsr &m) {
     if (m.d_rowptr) cudaFree(m.d_rowptr);
     if (m.d_colidx) cudaFree(m.d_colidx);
     if (m.d_data) cudaFree(m.d_data);
+    if (m.d_order) cudaFree(m.d_order);
     m = DevCsr{};
 }
 
@@ -69,9 +70,19 @@ int32_t upload_csr(const lcpc_csc &a, int fid, int L, DevCsr &out) {
             colidx[dst] = (uint32_t)j;
             std::memcpy(&data[(size_t)dst * L], &a.data[k * L], L * sizeof(uint64_t));
         }
+    // Rows by decreasing length: a warp of k_spmv_t serves 32/gs rows at once and runs as long as the longest of them
+    // (the generated codes have 7 - 76 non-zeros per row: 15 % of the lane cycles idle in matrix order), and the longest
+    // rows start first.
+    std::vector<uint32_t> order(a.rows);
+    for (size_t i = 0; i < a.rows; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
+    });
     out.rows = a.rows;
     out.cols = a.cols;
     out.nnz = nnz;
+    CU(cudaMalloc(&out.d_order, (a.rows ? a.rows : 1) * sizeof(uint32_t)));
+    if (a.rows) CU(cudaMemcpy(out.d_order, order.data(), a.rows * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&out.d_rowptr, (a.rows + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&out.d_colidx, (nnz ? nnz : 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&out.d_data, (nnz ? nnz : 1) * L * sizeof(uint64_t)));

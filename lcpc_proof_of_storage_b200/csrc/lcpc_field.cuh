@@ -10,9 +10,14 @@
 // "big"): Field::to_repr() below returns the element whose memory image is those bytes.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "lcpc_mont32.cuh"
+
+#ifndef LCPC_KARATSUBA
+#define LCPC_KARATSUBA 1
+#endif
 
 namespace lcpc {
 
@@ -390,6 +395,57 @@ struct Field {
     __device__ __forceinline__ static E dot_finish(const Dot &d) {
         if constexpr (LIMBS == 1) return dot_finish_prescaled(d);
         else return mul(dot_finish_prescaled(d), dot_scale());
+    }
+
+    // The same dot product on running accumulators that cost fewer instructions per term and more registers -- for
+    // kernels that keep ONE accumulator per thread (the Brakedown levels).  Four-limb fields: one Karatsuba level on
+    // three split accumulators (m32::kara_mac, 48 IMAD.WIDE per term instead of 64); two and three limbs: split
+    // accumulators (m32::split_mac); one limb: the eager form above.
+    static constexpr bool DOTW_KARA = LIMBS == 4 && LCPC_KARATSUBA;
+    struct DotWSplit {
+        uint32_t x[LIMBS == 1 ? 2 : 4 * LIMBS + 2], y[LIMBS == 1 ? 1 : 4 * LIMBS + 2], z[LIMBS == 1 ? 1 : 2 * LIMBS + 2];
+    };
+    struct DotWKara {
+        m32::KaraAcc<LIMBS> k;
+    };
+    using DotW = typename std::conditional<DOTW_KARA, DotWKara, DotWSplit>::type;
+    __device__ __forceinline__ static void dotw_init(DotW &d) {
+        if constexpr (DOTW_KARA) {
+            m32::kara_init<LIMBS>(d.k);
+        } else {
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(d.x) / 4); i++) d.x[i] = 0;
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(d.y) / 4); i++) d.y[i] = 0;
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(d.z) / 4); i++) d.z[i] = 0;
+        }
+    }
+    __device__ __forceinline__ static void dotw_mac(DotW &d, const E &a, const E &b) {
+        if constexpr (LIMBS == 1) {
+            const uint64_t r = ft63::add(ft63::pack(d.x[0], d.x[1]), ft63::mul(a.v[0], b.v[0]));
+            d.x[0] = ft63::lo32(r);
+            d.x[1] = ft63::hi32(r);
+        } else {
+            uint32_t x[2 * LIMBS], y[2 * LIMBS];
+            split(x, a);
+            split(y, b);
+            if constexpr (DOTW_KARA) m32::kara_mac<2 * LIMBS, PWord>(d.k, x, y);
+            else m32::split_mac<2 * LIMBS, PWord>(d.x, d.y, d.z, x, y);
+        }
+    }
+    __device__ __forceinline__ static E dotw_finish_prescaled(const DotW &d) {
+        E r;
+        if constexpr (LIMBS == 1) {
+            r.v[0] = ft63::pack(d.x[0], d.x[1]);
+        } else {
+            uint32_t s[4 * LIMBS + 2], z[2 * LIMBS];
+            if constexpr (DOTW_KARA) m32::kara_sum<2 * LIMBS>(s, d.k);
+            else m32::split_sum<2 * LIMBS>(s, d.x, d.y, d.z);
+            m32::wide_redc<2 * LIMBS>(z, s, PWord{});
+            r = join(z);
+        }
+        return r;
     }
 
     __device__ static E pow(E base, uint64_t e) {

@@ -370,8 +370,8 @@ cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_ele
 
 // ------------------------------------------------------------------ Brakedown
 
-#ifndef LCPC_SPMV_UNROLL
-#define LCPC_SPMV_UNROLL 2
+#ifndef LCPC_SPMV_DEPTH
+#define LCPC_SPMV_DEPTH 0  // 0: three slots for the one-limb field, two otherwise (measured: profiles/r02_spmv.md)
 #endif
 
 // The expander levels run on a TRANSPOSED working copy xT[codeword index][matrix row] (leading
@@ -385,43 +385,55 @@ cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_ele
 template <int FID, bool KSPLIT>
 __global__ void __launch_bounds__(128)
 k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint64_t *__restrict__ data,
-         size_t m_rows, const uint64_t *xT, uint64_t *yT, size_t bp, int log_gs) {
+         const uint32_t *__restrict__ order, size_t m_rows, const uint64_t *xT, uint64_t *yT, size_t bp, int log_gs) {
     using F = Field<FID>;
     using E = typename F::E;
     constexpr int L = F::LIMBS;
     const int gs = 1 << log_gs, slices = 32 >> log_gs;
     const int lane = threadIdx.x & 31, sub = lane >> log_gs, bl = lane & (gs - 1);
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t i = KSPLIT ? warp : warp * slices + sub;
-    if (i >= m_rows) return;
+    const size_t slot = KSPLIT ? warp : warp * slices + sub;
+    if (slot >= m_rows) return;
+    const size_t i = order[slot];  // rows by decreasing length: the lane groups of a warp finish together
     const uint32_t k0 = rowptr[i], k1 = rowptr[i + 1];
     const uint32_t kfirst = KSPLIT ? k0 + (uint32_t)sub : k0, kstep = KSPLIT ? (uint32_t)slices : 1u;
     for (size_t b = (size_t)blockIdx.y * gs + bl; b < bp; b += (size_t)gridDim.y * gs) {
-        typename F::Dot acc;  // `data` is pre-scaled by 2^32 for the multi-limb fields (scale_csr_data)
-        F::dot_init(acc);
-        // U non-zeros per trip with every load issued before the arithmetic: a non-zero costs two dependent trips to L2
-        // (column index, then the gathered operand), and one chain per thread leaves the kernel waiting on them
-        // (long-scoreboard was the top stall with the integer pipes half idle, profiles/r02_spmv.md)
-        constexpr int U = LCPC_SPMV_UNROLL;
+        typename F::DotW acc;  // `data` is pre-scaled by 2^32 for the multi-limb fields (scale_csr_data)
+        F::dotw_init(acc);
+        // A non-zero costs two dependent trips to L2 (column index, then the gathered operand).  Software pipeline with a
+        // ring of D slots: while a term is multiplied, the operands of the next D - 1 terms and the column indices of the D
+        // terms after those are in flight (without it the kernel waits on the gathers with the integer pipes half idle:
+        // long-scoreboard was the top stall, profiles/r02_spmv.md).  Slots beyond the end of the row hold zeros.
+        constexpr int D = LCPC_SPMV_DEPTH ? LCPC_SPMV_DEPTH : (L == 1 ? 3 : 2);
+        E a[D], x[D];
+        uint32_t cin[D];
         uint32_t k = kfirst;
-        for (; k + (U - 1) * kstep < k1; k += U * kstep) {
-            uint32_t ci[U];
-            E a[U], x[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) ci[u] = colidx[k + u * kstep];
-#pragma unroll
-            for (int u = 0; u < U; u++) a[u] = ld_fe<L>(data + (size_t)(k + u * kstep) * L);
-#pragma unroll
-            for (int u = 0; u < U; u++) x[u] = ld_fe<L>(xT + ((size_t)ci[u] * bp + b) * L);
-#pragma unroll
-            for (int u = 0; u < U; u++) F::dot_mac(acc, a[u], x[u]);
+        for (int d = 0; d < D; d++) {
+            const uint32_t kk = k + d * kstep;
+            cin[d] = kk < k1 ? colidx[kk] : 0u;
         }
-        for (; k < k1; k += kstep) {
-            const E a = ld_fe<L>(data + (size_t)k * L);
-            const E x = ld_fe<L>(xT + ((size_t)colidx[k] * bp + b) * L);
-            F::dot_mac(acc, a, x);
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const uint32_t kk = k + d * kstep, kk2 = kk + D * kstep;
+            const bool v = kk < k1;
+            a[d] = v ? ld_fe<L>(data + (size_t)kk * L) : F::zero();
+            x[d] = v ? ld_fe<L>(xT + ((size_t)cin[d] * bp + b) * L) : F::zero();
+            cin[d] = kk2 < k1 ? colidx[kk2] : 0u;
         }
-        E r = F::dot_finish_prescaled(acc);
+        while (k < k1) {
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                if (d == 0 || k + d * kstep < k1) F::dotw_mac(acc, a[d], x[d]);
+                const uint32_t kk = k + (D + d) * kstep, kk2 = kk + D * kstep;
+                const bool v = kk < k1;
+                a[d] = v ? ld_fe<L>(data + (size_t)kk * L) : F::zero();
+                x[d] = v ? ld_fe<L>(xT + ((size_t)cin[d] * bp + b) * L) : F::zero();
+                cin[d] = kk2 < k1 ? colidx[kk2] : 0u;
+            }
+            k += D * kstep;
+        }
+        E r = F::dotw_finish_prescaled(acc);
         if constexpr (KSPLIT) {
             for (int off = gs; off < 32; off <<= 1) {
                 E o;
@@ -587,8 +599,8 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t 
         const size_t rows_per_cta = ksplit ? 4 : 4 * slices;
         dim3 grid((unsigned)((m.rows + rows_per_cta - 1) / rows_per_cta), (unsigned)(groups < 65535 ? groups : 65535));
         lc.begin("k_spmv_t");
-        if (ksplit) k_spmv_t<FID, true><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, xT + x_off * bp * L, y, bp, log_gs);
-        else k_spmv_t<FID, false><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.rows, xT + x_off * bp * L, y, bp, log_gs);
+        if (ksplit) k_spmv_t<FID, true><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.d_order, m.rows, xT + x_off * bp * L, y, bp, log_gs);
+        else k_spmv_t<FID, false><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.d_order, m.rows, xT + x_off * bp * L, y, bp, log_gs);
         lc.end();
     };
     // encode.rs:46-58 precodes all the way down

@@ -141,6 +141,14 @@ struct MontRows {
             MontRows<N, I + 1, PW>::product(X, Y, a, b);
         }
     }
+    // the same rows on accumulators that already hold data (split_mac): every chain-end carry goes to the sink
+    __device__ __forceinline__ static void product_sink(uint32_t (&X)[2 * N + 2], uint32_t (&Y)[2 * N + 2], uint32_t (&Z)[N + 2],
+                                                        const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+        if constexpr (I < N) {
+            row_mad_impl<N, I, true>(X, Y, Z, b[I], [&](int j) { return a[j]; });
+            MontRows<N, I + 1, PW>::product_sink(X, Y, Z, a, b);
+        }
+    }
     // Montgomery digits: word I of T = X + Y (+ carry c of the words already cleared) is cancelled by
     // adding m*p*2^(32*I) with m = -word (p = 1 mod 2^32); the cleared word is then exactly 0 or 2^32.
     __device__ __forceinline__ static void reduce(uint32_t (&X)[2 * N + 2], uint32_t (&Y)[2 * N + 2], uint32_t (&Z)[N + 2],
@@ -225,6 +233,146 @@ __device__ __forceinline__ void wide_mac(uint32_t (&S)[2 * N + 2], const uint32_
     add_cc(S[1], Y[1]);  // Y[0] is never written (odd-aligned pairs)
 #pragma unroll
     for (int i = 2; i < 2 * N + 1; i++) addc_cc(S[i], Y[i]);
+    addc(S[2 * N + 1], 0);
+}
+
+// The same sum kept as THREE running accumulators (even-aligned pairs, odd-aligned pairs, chain-end carries) so that a
+// term costs its N^2 IMAD.WIDE.X and 2N carry catches and nothing else: wide_mac above builds every product from zero
+// and then adds 2(2N+1) words into S, which is 40 % of its instructions at N = 8.  The sink words only count carries
+// (at most two per term and word), so any K < 2^31 is safe.  Costs 5N+6 registers instead of 2N+2: used where one
+// accumulator per thread is live (the Brakedown levels), not by the four-tensor fold.
+template <int N, class PW>
+__device__ __forceinline__ void split_mac(uint32_t (&X)[2 * N + 2], uint32_t (&Y)[2 * N + 2], uint32_t (&Z)[N + 2],
+                                          const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    MontRows<N, 0, PW>::product_sink(X, Y, Z, a, b);
+}
+// S = X + Y + Z * 2^(32N)
+template <int N>
+__device__ __forceinline__ void split_sum(uint32_t (&S)[2 * N + 2], const uint32_t (&X)[2 * N + 2],
+                                          const uint32_t (&Y)[2 * N + 2], const uint32_t (&Z)[N + 2]) {
+#pragma unroll
+    for (int i = 0; i < 2 * N + 2; i++) S[i] = X[i];
+    add_cc(S[1], Y[1]);  // Y[0] is never written
+#pragma unroll
+    for (int i = 2; i < 2 * N + 1; i++) addc_cc(S[i], Y[i]);
+    addc(S[2 * N + 1], Y[2 * N + 1]);
+    add_cc(S[N], Z[0]);
+#pragma unroll
+    for (int i = 1; i < N + 1; i++) addc_cc(S[N + i], Z[i]);
+    addc(S[2 * N + 1], Z[N + 1]);
+}
+
+// ---- Karatsuba dot products (N = 2H words) ------------------------------------------------------
+// The N^2 IMAD.WIDE of a term are what bounds the Brakedown levels over the 255-bit field (FMA pipe; the ALU pipe is half
+// idle, profiles/r02_spmv.md), so one Karatsuba level trades a quarter of them for ALU-pipe work: with a = aL + aH*W,
+// b = bL + bH*W (W = 2^(32H)),  aL*bH + aH*bL = (aL + aH)(bL + bH) - aL*bL - aH*bH.  The three half-size products of
+// every term go to three split accumulators (as split_mac) and the subtraction is paid ONCE per dot product.  aL + aH and
+// bL + bH can be one bit longer than H words; with sa = sa' + ca*W, sb = sb' + cb*W
+//     sa*sb = sa'*sb' + W*(ca*sb' + cb*sa') + W^2*ca*cb,
+// and the three correction sums are plain (predicated) additions into Ca, Cb and a counter.
+template <int H>
+struct KaraAcc {
+    uint32_t X0[2 * H + 2], Y0[2 * H + 2], Z0[H + 2];  // sum aL*bL
+    uint32_t X2[2 * H + 2], Y2[2 * H + 2], Z2[H + 2];  // sum aH*bH
+    uint32_t Xm[2 * H + 2], Ym[2 * H + 2], Zm[H + 2];  // sum sa'*sb'
+    uint32_t Ca[H + 1], Cb[H + 1];                     // sum of sb' over the terms with ca, of sa' over those with cb
+    uint32_t Cc;                                       // number of terms with ca and cb
+};
+
+template <int H>
+__device__ __forceinline__ void kara_init(KaraAcc<H> &k) {
+#pragma unroll
+    for (int i = 0; i < 2 * H + 2; i++) k.X0[i] = k.Y0[i] = k.X2[i] = k.Y2[i] = k.Xm[i] = k.Ym[i] = 0;
+#pragma unroll
+    for (int i = 0; i < H + 2; i++) k.Z0[i] = k.Z2[i] = k.Zm[i] = 0;
+#pragma unroll
+    for (int i = 0; i < H + 1; i++) k.Ca[i] = k.Cb[i] = 0;
+    k.Cc = 0;
+}
+
+// C += flag ? v : 0   (H words into H + 1; flag is 0 or 1)
+template <int H>
+__device__ __forceinline__ void cond_add(uint32_t (&C)[H + 1], const uint32_t (&v)[H], uint32_t flag) {
+    if constexpr (H == 4) {
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0;\n\t"
+                     "@q add.cc.u32 %0, %0, %6;\n\t@q addc.cc.u32 %1, %1, %7;\n\t@q addc.cc.u32 %2, %2, %8;\n\t"
+                     "@q addc.cc.u32 %3, %3, %9;\n\t@q addc.u32 %4, %4, 0; }"
+                     : "+r"(C[0]), "+r"(C[1]), "+r"(C[2]), "+r"(C[3]), "+r"(C[4])
+                     : "r"(flag), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]));
+    } else {
+        const uint32_t m = 0u - flag;
+        add_cc(C[0], v[0] & m);
+#pragma unroll
+        for (int i = 1; i < H; i++) addc_cc(C[i], v[i] & m);
+        addc(C[H], 0);
+    }
+}
+
+// acc += a*b
+template <int N, class PW>
+__device__ __forceinline__ void kara_mac(KaraAcc<N / 2> &k, const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    constexpr int H = N / 2;
+    static_assert(N % 2 == 0, "even word count");
+    uint32_t aL[H], aH[H], bL[H], bH[H], sa[H], sb[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) { aL[i] = a[i]; aH[i] = a[H + i]; bL[i] = b[i]; bH[i] = b[H + i]; sa[i] = a[i]; sb[i] = b[i]; }
+    uint32_t ca = 0, cb = 0;
+    add_cc(sa[0], aH[0]);
+#pragma unroll
+    for (int i = 1; i < H; i++) addc_cc(sa[i], aH[i]);
+    addc(ca, 0);
+    add_cc(sb[0], bH[0]);
+#pragma unroll
+    for (int i = 1; i < H; i++) addc_cc(sb[i], bH[i]);
+    addc(cb, 0);
+    MontRows<H, 0, PW>::product_sink(k.X0, k.Y0, k.Z0, aL, bL);
+    MontRows<H, 0, PW>::product_sink(k.X2, k.Y2, k.Z2, aH, bH);
+    MontRows<H, 0, PW>::product_sink(k.Xm, k.Ym, k.Zm, sa, sb);
+    cond_add<H>(k.Ca, sb, ca);
+    cond_add<H>(k.Cb, sa, cb);
+    k.Cc += ca & cb;
+}
+
+// S = the accumulated sum, 2N + 2 words
+template <int N>
+__device__ __forceinline__ void kara_sum(uint32_t (&S)[2 * N + 2], const KaraAcc<N / 2> &k) {
+    constexpr int H = N / 2, W2 = 2 * H + 2;
+    uint32_t S0[W2], S2[W2], Sm[W2];
+    split_sum<H>(S0, k.X0, k.Y0, k.Z0);
+    split_sum<H>(S2, k.X2, k.Y2, k.Z2);
+    split_sum<H>(Sm, k.Xm, k.Ym, k.Zm);
+    // Sm += (Ca + Cb) * W + Cc * W^2
+    add_cc(Sm[H], k.Ca[0]);
+#pragma unroll
+    for (int i = 1; i < H + 1; i++) addc_cc(Sm[H + i], k.Ca[i]);
+    addc(Sm[2 * H + 1], 0);
+    add_cc(Sm[H], k.Cb[0]);
+#pragma unroll
+    for (int i = 1; i < H + 1; i++) addc_cc(Sm[H + i], k.Cb[i]);
+    addc(Sm[2 * H + 1], 0);
+    add_cc(Sm[2 * H], k.Cc);
+    addc(Sm[2 * H + 1], 0);
+    // Sm -= S0 + S2  (what is left is sum aL*bH + aH*bL >= 0)
+    sub_cc(Sm[0], S0[0]);
+#pragma unroll
+    for (int i = 1; i < W2 - 1; i++) subc_cc(Sm[i], S0[i]);
+    subc(Sm[W2 - 1], S0[W2 - 1]);
+    sub_cc(Sm[0], S2[0]);
+#pragma unroll
+    for (int i = 1; i < W2 - 1; i++) subc_cc(Sm[i], S2[i]);
+    subc(Sm[W2 - 1], S2[W2 - 1]);
+    // S = S0 + S2 * W^2 + Sm * W
+#pragma unroll
+    for (int i = 0; i < 2 * N + 2; i++) S[i] = i < W2 ? S0[i] : 0;
+    add_cc(S[2 * H], S2[0]);
+#pragma unroll
+    for (int i = 1; i < W2 - 1; i++) addc_cc(S[2 * H + i], S2[i]);
+    addc(S[2 * H + W2 - 1], S2[W2 - 1]);
+    add_cc(S[H], Sm[0]);
+#pragma unroll
+    for (int i = 1; i < W2; i++) addc_cc(S[H + i], Sm[i]);
+#pragma unroll
+    for (int i = H + W2; i < 2 * N + 1; i++) addc_cc(S[i], 0);
     addc(S[2 * N + 1], 0);
 }
 
