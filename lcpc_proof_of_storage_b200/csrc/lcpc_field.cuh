@@ -398,12 +398,14 @@ struct Field {
     }
 
     // The same dot product on running accumulators that cost fewer instructions per term and more registers -- for
-    // kernels that keep ONE accumulator per thread (the Brakedown levels).  Four-limb fields: one Karatsuba level on
-    // three split accumulators (m32::kara_mac, 48 IMAD.WIDE per term instead of 64); two and three limbs: split
-    // accumulators (m32::split_mac); one limb: the eager form above.
+    // the Brakedown levels, whose constant operand class (the matrix) is pre-scaled by 2^32 at plan time for EVERY field
+    // (DOTW prescale; dotw_scale()).  Four-limb fields: one Karatsuba level on three split accumulators (m32::kara_mac,
+    // 48 IMAD.WIDE per term instead of 64); one to three limbs: split accumulators (m32::split_mac) -- for the one-limb
+    // field that is 4 IMAD.WIDE.X + 4 carry catches per term against 6 IMAD.WIDE + ~20 other instructions for the eager
+    // Montgomery multiply-add.
     static constexpr bool DOTW_KARA = LIMBS == 4 && LCPC_KARATSUBA;
     struct DotWSplit {
-        uint32_t x[LIMBS == 1 ? 2 : 4 * LIMBS + 2], y[LIMBS == 1 ? 1 : 4 * LIMBS + 2], z[LIMBS == 1 ? 1 : 2 * LIMBS + 2];
+        m32::SplitAcc<2 * LIMBS> s;
     };
     struct DotWKara {
         m32::KaraAcc<LIMBS> k;
@@ -413,38 +415,29 @@ struct Field {
         if constexpr (DOTW_KARA) {
             m32::kara_init<LIMBS>(d.k);
         } else {
-#pragma unroll
-            for (int i = 0; i < (int)(sizeof(d.x) / 4); i++) d.x[i] = 0;
-#pragma unroll
-            for (int i = 0; i < (int)(sizeof(d.y) / 4); i++) d.y[i] = 0;
-#pragma unroll
-            for (int i = 0; i < (int)(sizeof(d.z) / 4); i++) d.z[i] = 0;
+            m32::split_init<2 * LIMBS>(d.s);
         }
     }
     __device__ __forceinline__ static void dotw_mac(DotW &d, const E &a, const E &b) {
-        if constexpr (LIMBS == 1) {
-            const uint64_t r = ft63::add(ft63::pack(d.x[0], d.x[1]), ft63::mul(a.v[0], b.v[0]));
-            d.x[0] = ft63::lo32(r);
-            d.x[1] = ft63::hi32(r);
-        } else {
-            uint32_t x[2 * LIMBS], y[2 * LIMBS];
-            split(x, a);
-            split(y, b);
-            if constexpr (DOTW_KARA) m32::kara_mac<2 * LIMBS, PWord>(d.k, x, y);
-            else m32::split_mac<2 * LIMBS, PWord>(d.x, d.y, d.z, x, y);
-        }
+        uint32_t x[2 * LIMBS], y[2 * LIMBS];
+        split(x, a);
+        split(y, b);
+        if constexpr (DOTW_KARA) m32::kara_mac<2 * LIMBS>(d.k, x, y);
+        else m32::split_mac<2 * LIMBS>(d.s, x, y);
     }
+    // sum * 2^-32 (one operand class pre-scaled by dotw_scale())
     __device__ __forceinline__ static E dotw_finish_prescaled(const DotW &d) {
+        uint32_t s[4 * LIMBS + 2], z[2 * LIMBS];
+        if constexpr (DOTW_KARA) m32::kara_sum<2 * LIMBS>(s, d.k);
+        else m32::split_sum<2 * LIMBS>(s, d.s);
+        m32::wide_redc<2 * LIMBS>(z, s, PWord{});
+        return join(z);
+    }
+    // 2^32 in Montgomery form, every field
+    __device__ __forceinline__ static E dotw_scale() {
         E r;
-        if constexpr (LIMBS == 1) {
-            r.v[0] = ft63::pack(d.x[0], d.x[1]);
-        } else {
-            uint32_t s[4 * LIMBS + 2], z[2 * LIMBS];
-            if constexpr (DOTW_KARA) m32::kara_sum<2 * LIMBS>(s, d.k);
-            else m32::split_sum<2 * LIMBS>(s, d.x, d.y, d.z);
-            m32::wide_redc<2 * LIMBS>(z, s, PWord{});
-            r = join(z);
-        }
+#pragma unroll
+        for (int i = 0; i < LIMBS; i++) r.v[i] = field_two32_mont(FID).v[i];
         return r;
     }
 

@@ -161,7 +161,7 @@ struct DevCsr {
     uint64_t *d_data = nullptr;    // nnz * LIMBS
     uint32_t *d_order = nullptr;   // rows: row indices by decreasing length (the lane groups of a warp get equally long rows)
 };
-// one-time preparation of a matrix's non-zeros for the spmv kernel (multiplies by 2^32 for the multi-limb fields)
+// one-time preparation of a matrix's non-zeros for the spmv kernel (multiplies by 2^32: the lazy dot products reduce by one extra word)
 cudaError_t scale_csr_data(int fid, uint64_t *d_data, size_t nnz, cudaStream_t s);
 struct SdigPlan {
     int fid = 0;

@@ -370,6 +370,9 @@ cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_ele
 
 // ------------------------------------------------------------------ Brakedown
 
+#ifndef LCPC_SPMV_TG_MAX
+#define LCPC_SPMV_TG_MAX 8  // most lane groups of matrix rows one thread of k_spmv_tg serves (2 ... 8)
+#endif
 #ifndef LCPC_SPMV_DEPTH
 #define LCPC_SPMV_DEPTH 0  // 0: three slots for the one-limb field, two otherwise (measured: profiles/r02_spmv.md)
 #endif
@@ -398,7 +401,7 @@ k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colid
     const uint32_t k0 = rowptr[i], k1 = rowptr[i + 1];
     const uint32_t kfirst = KSPLIT ? k0 + (uint32_t)sub : k0, kstep = KSPLIT ? (uint32_t)slices : 1u;
     for (size_t b = (size_t)blockIdx.y * gs + bl; b < bp; b += (size_t)gridDim.y * gs) {
-        typename F::DotW acc;  // `data` is pre-scaled by 2^32 for the multi-limb fields (scale_csr_data)
+        typename F::DotW acc;  // `data` is pre-scaled by 2^32 (scale_csr_data)
         F::dotw_init(acc);
         // A non-zero costs two dependent trips to L2 (column index, then the gathered operand).  Software pipeline with a
         // ring of D slots: while a term is multiplied, the operands of the next D - 1 terms and the column indices of the D
@@ -408,30 +411,30 @@ k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colid
         E a[D], x[D];
         uint32_t cin[D];
         uint32_t k = kfirst;
+        if (k < k1) {
+            // loads past the end of the row are clamped to its last non-zero (loaded, never multiplied): no predicates,
+            // no zero fill
+            const uint32_t klast = k1 - 1;
 #pragma unroll
-        for (int d = 0; d < D; d++) {
-            const uint32_t kk = k + d * kstep;
-            cin[d] = kk < k1 ? colidx[kk] : 0u;
-        }
-#pragma unroll
-        for (int d = 0; d < D; d++) {
-            const uint32_t kk = k + d * kstep, kk2 = kk + D * kstep;
-            const bool v = kk < k1;
-            a[d] = v ? ld_fe<L>(data + (size_t)kk * L) : F::zero();
-            x[d] = v ? ld_fe<L>(xT + ((size_t)cin[d] * bp + b) * L) : F::zero();
-            cin[d] = kk2 < k1 ? colidx[kk2] : 0u;
-        }
-        while (k < k1) {
+            for (int d = 0; d < D; d++) cin[d] = colidx[min(k + d * kstep, klast)];
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                if (d == 0 || k + d * kstep < k1) F::dotw_mac(acc, a[d], x[d]);
-                const uint32_t kk = k + (D + d) * kstep, kk2 = kk + D * kstep;
-                const bool v = kk < k1;
-                a[d] = v ? ld_fe<L>(data + (size_t)kk * L) : F::zero();
-                x[d] = v ? ld_fe<L>(xT + ((size_t)cin[d] * bp + b) * L) : F::zero();
-                cin[d] = kk2 < k1 ? colidx[kk2] : 0u;
+                const uint32_t kk = min(k + d * kstep, klast);
+                a[d] = ld_fe<L>(data + (size_t)kk * L);
+                x[d] = ld_fe<L>(xT + ((size_t)cin[d] * bp + b) * L);
+                cin[d] = colidx[min(k + (D + d) * kstep, klast)];
             }
-            k += D * kstep;
+            do {
+#pragma unroll
+                for (int d = 0; d < D; d++) {
+                    if (d == 0 || k + d * kstep < k1) F::dotw_mac(acc, a[d], x[d]);
+                    const uint32_t kk = min(k + (D + d) * kstep, klast);
+                    a[d] = ld_fe<L>(data + (size_t)kk * L);
+                    x[d] = ld_fe<L>(xT + ((size_t)cin[d] * bp + b) * L);
+                    cin[d] = colidx[min(k + (2 * D + d) * kstep, klast)];
+                }
+                k += D * kstep;
+            } while (k < k1);
         }
         E r = F::dotw_finish_prescaled(acc);
         if constexpr (KSPLIT) {
@@ -448,19 +451,81 @@ k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colid
     }
 }
 
-// data[k] *= 2^32 for the multi-limb fields: the lazy dot product of k_spmv_t reduces by one extra word
+// One-limb field, wide levels: a thread serves NG lane groups of matrix rows (b = (g0 + j) * GS + bl) for its output
+// index, so the column index and the non-zero are loaded once per NG products instead of once per product and the NG
+// gathers of a term are issued back to back from one address (GS is a template parameter: the offsets are immediates).
+// Lane groups past the last one read the start of the next xT row (the working copy is padded by NG * GS elements) and
+// are not stored.
+template <int FID, int NG, int LOG_GS>
+__global__ void __launch_bounds__(128)
+k_spmv_tg(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint64_t *__restrict__ data,
+          const uint32_t *__restrict__ order, size_t m_rows, const uint64_t *xT, uint64_t *yT, size_t bp) {
+    using F = Field<FID>;
+    using E = typename F::E;
+    static_assert(F::LIMBS == 1, "one-limb fields");
+    constexpr int GS = 1 << LOG_GS, SLICES = 32 >> LOG_GS;
+    const int lane = threadIdx.x & 31, sub = lane >> LOG_GS, bl = lane & (GS - 1);
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t slot = warp * SLICES + sub;
+    if (slot >= m_rows) return;
+    const size_t i = order[slot];
+    const uint32_t k0 = rowptr[i], k1 = rowptr[i + 1];
+    const size_t b0 = (size_t)blockIdx.y * NG * GS + bl;
+    typename F::DotW acc[NG];  // `data` is pre-scaled by 2^32 (scale_csr_data)
+#pragma unroll
+    for (int j = 0; j < NG; j++) F::dotw_init(acc[j]);
+    if (k0 < k1) {
+        // two slots: the gathers of the next term are in flight while this one is multiplied; indices one term further.
+        // Loads past the end of the row are clamped to its last non-zero.
+        const uint32_t klast = k1 - 1;
+        const uint64_t *xb = xT + b0;
+        E a[2], x[2][NG];
+        uint32_t cin[2];
+#pragma unroll
+        for (int d = 0; d < 2; d++) cin[d] = colidx[min(k0 + d, klast)];
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            a[d] = ld_fe<1>(data + min(k0 + d, klast));
+            const uint64_t *xp = xb + (size_t)cin[d] * bp;
+#pragma unroll
+            for (int j = 0; j < NG; j++) x[d][j] = ld_fe<1>(xp + j * GS);
+            cin[d] = colidx[min(k0 + 2 + d, klast)];
+        }
+        uint32_t k = k0;
+        do {
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                if (d == 0 || k + d < k1) {
+#pragma unroll
+                    for (int j = 0; j < NG; j++) F::dotw_mac(acc[j], a[d], x[d][j]);
+                }
+                a[d] = ld_fe<1>(data + min(k + 2 + d, klast));
+                const uint64_t *xp = xb + (size_t)cin[d] * bp;
+#pragma unroll
+                for (int j = 0; j < NG; j++) x[d][j] = ld_fe<1>(xp + j * GS);
+                cin[d] = colidx[min(k + 4 + d, klast)];
+            }
+            k += 2;
+        } while (k < k1);
+    }
+#pragma unroll
+    for (int j = 0; j < NG; j++)
+        if (b0 + (size_t)j * GS < bp) st_fe<1>(yT + i * bp + b0 + (size_t)j * GS, F::dotw_finish_prescaled(acc[j]));
+}
+
+// data[k] *= 2^32 (every field): the lazy dot product of k_spmv_t reduces by one extra word
 template <int FID>
 __global__ void k_scale_data(uint64_t *data, size_t n) {
     using F = Field<FID>;
     constexpr int L = F::LIMBS;
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    st_fe<L>(data + k * L, F::mul(ld_fe<L>(data + k * L), F::dot_scale()));
+    st_fe<L>(data + k * L, F::mul(ld_fe<L>(data + k * L), F::dotw_scale()));
 }
 
 template <int FID>
 static cudaError_t scale_csr_data_t(uint64_t *d_data, size_t nnz, cudaStream_t s) {
-    if (!Field<FID>::DOT_PRESCALE || nnz == 0) return cudaSuccess;
+    if (nnz == 0) return cudaSuccess;
     k_scale_data<FID><<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(d_data, nnz);
     return cudaGetLastError();
 }
@@ -575,7 +640,8 @@ static size_t sdig_bp(size_t n_rows) {
 
 // transposed working copy: n_cols codeword rows + the (unstored) output of the last precode
 size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows) {
-    return plan.pre.empty() ? 0 : (plan.n_cols + plan.pre.back().rows) * sdig_bp(n_rows);
+    // + 8 lane groups of 32: k_spmv_tg reads (and discards) up to NG * GS elements past the row it gathers from
+    return plan.pre.empty() ? 0 : (plan.n_cols + plan.pre.back().rows) * sdig_bp(n_rows) + 8 * 32;
 }
 
 template <int FID>
@@ -598,6 +664,32 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t 
         const bool ksplit = slices > 1 && (m.rows / slices + 1) * groups < (size_t)148 * 16;
         const size_t rows_per_cta = ksplit ? 4 : 4 * slices;
         dim3 grid((unsigned)((m.rows + rows_per_cta - 1) / rows_per_cta), (unsigned)(groups < 65535 ? groups : 65535));
+        if constexpr (L == 1) {
+            // wide levels of the one-limb field: NG lane groups per thread (the NG that wastes the fewest group slots)
+            if (!ksplit && groups > 1) {
+                // the largest NG that leaves at most 15 % of the group slots empty, else the one with the fewest empty slots
+                int ng = 0, best_ng = 2;
+                double best_eff = 0.0;
+                for (int c = LCPC_SPMV_TG_MAX; c >= 2 && !ng; c--) {
+                    const double eff = (double)groups / (double)((groups + c - 1) / c * c);
+                    if (eff >= 0.85) ng = c;
+                    if (eff > best_eff) { best_eff = eff; best_ng = c; }
+                }
+                if (!ng) ng = best_ng;
+                const size_t ychunks = (groups + ng - 1) / ng;
+                if ((m.rows / slices + 1) * ychunks >= (size_t)148 * 16) {
+                    dim3 gridg((unsigned)((m.rows + 4 * slices - 1) / (4 * slices)), (unsigned)ychunks);
+                    lc.begin("k_spmv_t");
+#define LCPC_TG2(NGV, LG) k_spmv_tg<FID, NGV, LG><<<gridg, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.d_order, m.rows, xT + x_off * bp * L, y, bp)
+#define LCPC_TG(NGV) case NGV: if (log_gs == 3) LCPC_TG2(NGV, 3); else if (log_gs == 4) LCPC_TG2(NGV, 4); else LCPC_TG2(NGV, 5); break;
+                    switch (ng) { LCPC_TG(2) LCPC_TG(3) LCPC_TG(4) LCPC_TG(5) LCPC_TG(6) LCPC_TG(7) LCPC_TG(8) }
+#undef LCPC_TG2
+#undef LCPC_TG
+                    lc.end();
+                    return;
+                }
+            }
+        }
         lc.begin("k_spmv_t");
         if (ksplit) k_spmv_t<FID, true><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.d_order, m.rows, xT + x_off * bp * L, y, bp, log_gs);
         else k_spmv_t<FID, false><<<grid, 128, 0, lc.s>>>(m.d_rowptr, m.d_colidx, m.d_data, m.d_order, m.rows, xT + x_off * bp * L, y, bp, log_gs);

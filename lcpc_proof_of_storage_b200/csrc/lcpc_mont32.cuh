@@ -141,14 +141,6 @@ struct MontRows {
             MontRows<N, I + 1, PW>::product(X, Y, a, b);
         }
     }
-    // the same rows on accumulators that already hold data (split_mac): every chain-end carry goes to the sink
-    __device__ __forceinline__ static void product_sink(uint32_t (&X)[2 * N + 2], uint32_t (&Y)[2 * N + 2], uint32_t (&Z)[N + 2],
-                                                        const uint32_t (&a)[N], const uint32_t (&b)[N]) {
-        if constexpr (I < N) {
-            row_mad_impl<N, I, true>(X, Y, Z, b[I], [&](int j) { return a[j]; });
-            MontRows<N, I + 1, PW>::product_sink(X, Y, Z, a, b);
-        }
-    }
     // Montgomery digits: word I of T = X + Y (+ carry c of the words already cleared) is cancelled by
     // adding m*p*2^(32*I) with m = -word (p = 1 mod 2^32); the cleared word is then exactly 0 or 2^32.
     __device__ __forceinline__ static void reduce(uint32_t (&X)[2 * N + 2], uint32_t (&Y)[2 * N + 2], uint32_t (&Z)[N + 2],
@@ -236,55 +228,140 @@ __device__ __forceinline__ void wide_mac(uint32_t (&S)[2 * N + 2], const uint32_
     addc(S[2 * N + 1], 0);
 }
 
+// ---- running accumulators held as 64-bit register PAIRS -------------------------------------------------------
 // The same sum kept as THREE running accumulators (even-aligned pairs, odd-aligned pairs, chain-end carries) so that a
-// term costs its N^2 IMAD.WIDE.X and 2N carry catches and nothing else: wide_mac above builds every product from zero
+// term costs its N^2 IMAD.WIDE and 2N carry catches and nothing else: wide_mac above builds every product from zero
 // and then adds 2(2N+1) words into S, which is 40 % of its instructions at N = 8.  The sink words only count carries
-// (at most two per term and word), so any K < 2^31 is safe.  Costs 5N+6 registers instead of 2N+2: used where one
-// accumulator per thread is live (the Brakedown levels), not by the four-tensor fold.
-template <int N, class PW>
-__device__ __forceinline__ void split_mac(uint32_t (&X)[2 * N + 2], uint32_t (&Y)[2 * N + 2], uint32_t (&Z)[N + 2],
-                                          const uint32_t (&a)[N], const uint32_t (&b)[N]) {
-    MontRows<N, 0, PW>::product_sink(X, Y, Z, a, b);
-}
-// S = X + Y + Z * 2^(32N)
+// (at most two per term and word), so any K < 2^31 is safe.
+// The accumulators are uint64_t (word pair 2i, 2i+1 of X; word pair 2i+1, 2i+2 of Y) and every carry chain is ONE asm
+// statement that unpacks its pairs, runs mad.lo.cc / madc.hi.cc over them and packs them again: ptxas then keeps each
+// pair in an aligned register pair for the whole loop.  With one 32-bit variable per word (row_mad above) it moved
+// 2.5 registers per product between the loop-carried words and the pairs IMAD.WIDE needs (IMAD.MOV: 13 % of the FMA-pipe
+// cycles of the four-limb Brakedown level, a third of all instructions of the one-limb one).
+template <int NP>
+struct MadChain;
+template <>
+struct MadChain<1> {
+    __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
+        asm("{ .reg .u32 l0, h0;\n\tmov.b64 {l0, h0}, %0;\n\t"
+            "mad.lo.cc.u32 l0, %2, %3, l0;\n\tmadc.hi.cc.u32 h0, %2, %3, h0;\n\t"
+            "addc.u32 %1, %1, 0;\n\tmov.b64 %0, {l0, h0}; }"
+            : "+l"(P[0]), "+r"(sink) : "r"(x), "r"(y[0]));
+    }
+};
+template <>
+struct MadChain<2> {
+    __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
+        asm("{ .reg .u32 l0, h0, l1, h1;\n\tmov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\t"
+            "mad.lo.cc.u32 l0, %3, %4, l0;\n\tmadc.hi.cc.u32 h0, %3, %4, h0;\n\t"
+            "madc.lo.cc.u32 l1, %3, %5, l1;\n\tmadc.hi.cc.u32 h1, %3, %5, h1;\n\t"
+            "addc.u32 %2, %2, 0;\n\tmov.b64 %0, {l0, h0};\n\tmov.b64 %1, {l1, h1}; }"
+            : "+l"(P[0]), "+l"(P[1]), "+r"(sink) : "r"(x), "r"(y[0]), "r"(y[2]));
+    }
+};
+template <>
+struct MadChain<3> {
+    __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
+        asm("{ .reg .u32 l0, h0, l1, h1, l2, h2;\n\tmov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\tmov.b64 {l2, h2}, %2;\n\t"
+            "mad.lo.cc.u32 l0, %4, %5, l0;\n\tmadc.hi.cc.u32 h0, %4, %5, h0;\n\t"
+            "madc.lo.cc.u32 l1, %4, %6, l1;\n\tmadc.hi.cc.u32 h1, %4, %6, h1;\n\t"
+            "madc.lo.cc.u32 l2, %4, %7, l2;\n\tmadc.hi.cc.u32 h2, %4, %7, h2;\n\t"
+            "addc.u32 %3, %3, 0;\n\tmov.b64 %0, {l0, h0};\n\tmov.b64 %1, {l1, h1};\n\tmov.b64 %2, {l2, h2}; }"
+            : "+l"(P[0]), "+l"(P[1]), "+l"(P[2]), "+r"(sink) : "r"(x), "r"(y[0]), "r"(y[2]), "r"(y[4]));
+    }
+};
+template <>
+struct MadChain<4> {
+    __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
+        asm("{ .reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+            "mov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\tmov.b64 {l2, h2}, %2;\n\tmov.b64 {l3, h3}, %3;\n\t"
+            "mad.lo.cc.u32 l0, %5, %6, l0;\n\tmadc.hi.cc.u32 h0, %5, %6, h0;\n\t"
+            "madc.lo.cc.u32 l1, %5, %7, l1;\n\tmadc.hi.cc.u32 h1, %5, %7, h1;\n\t"
+            "madc.lo.cc.u32 l2, %5, %8, l2;\n\tmadc.hi.cc.u32 h2, %5, %8, h2;\n\t"
+            "madc.lo.cc.u32 l3, %5, %9, l3;\n\tmadc.hi.cc.u32 h3, %5, %9, h3;\n\t"
+            "addc.u32 %4, %4, 0;\n\t"
+            "mov.b64 %0, {l0, h0};\n\tmov.b64 %1, {l1, h1};\n\tmov.b64 %2, {l2, h2};\n\tmov.b64 %3, {l3, h3}; }"
+            : "+l"(P[0]), "+l"(P[1]), "+l"(P[2]), "+l"(P[3]), "+r"(sink)
+            : "r"(x), "r"(y[0]), "r"(y[2]), "r"(y[4]), "r"(y[6]));
+    }
+};
+
+// X[i] = words 2i, 2i+1;  Y[i] = words 2i+1, 2i+2;  Z[k] = carries of weight 2^(32(N+k))
 template <int N>
-__device__ __forceinline__ void split_sum(uint32_t (&S)[2 * N + 2], const uint32_t (&X)[2 * N + 2],
-                                          const uint32_t (&Y)[2 * N + 2], const uint32_t (&Z)[N + 2]) {
+struct SplitAcc {
+    uint64_t X[N], Y[N];
+    uint32_t Z[N + 2];
+};
+template <int N>
+__device__ __forceinline__ void split_init(SplitAcc<N> &s) {
 #pragma unroll
-    for (int i = 0; i < 2 * N + 2; i++) S[i] = X[i];
-    add_cc(S[1], Y[1]);  // Y[0] is never written
+    for (int i = 0; i < N; i++) s.X[i] = s.Y[i] = 0;
 #pragma unroll
-    for (int i = 2; i < 2 * N + 1; i++) addc_cc(S[i], Y[i]);
-    addc(S[2 * N + 1], Y[2 * N + 1]);
-    add_cc(S[N], Z[0]);
+    for (int i = 0; i < N + 2; i++) s.Z[i] = 0;
+}
+template <int N, int I>
+__device__ __forceinline__ void split_rows(SplitAcc<N> &s, const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    if constexpr (I < N) {
+        {
+            constexpr int j0 = I & 1, np = (N - j0 + 1) / 2, end = I + j0 + 2 * np;  // I + j even
+            MadChain<np>::run(&s.X[(I + j0) / 2], b[I], &a[j0], s.Z[end - N]);
+        }
+        {
+            constexpr int j0 = 1 - (I & 1), np = (N - j0 + 1) / 2, end = I + j0 + 2 * np;  // I + j odd
+            MadChain<np>::run(&s.Y[(I + j0 - 1) / 2], b[I], &a[j0], s.Z[end - N]);
+        }
+        split_rows<N, I + 1>(s, a, b);
+    }
+}
+// acc += a*b
+template <int N>
+__device__ __forceinline__ void split_mac(SplitAcc<N> &s, const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    split_rows<N, 0>(s, a, b);
+}
+// S = X + Y + Z * 2^(32N), 2N + 2 words
+template <int N>
+__device__ __forceinline__ void split_sum(uint32_t (&S)[2 * N + 2], const SplitAcc<N> &s) {
+    uint32_t Yw[2 * N + 2];
+    Yw[0] = 0;
+    Yw[2 * N + 1] = 0;
 #pragma unroll
-    for (int i = 1; i < N + 1; i++) addc_cc(S[N + i], Z[i]);
-    addc(S[2 * N + 1], Z[N + 1]);
+    for (int i = 0; i < N; i++) {
+        S[2 * i] = (uint32_t)s.X[i];
+        S[2 * i + 1] = (uint32_t)(s.X[i] >> 32);
+        Yw[2 * i + 1] = (uint32_t)s.Y[i];
+        Yw[2 * i + 2] = (uint32_t)(s.Y[i] >> 32);
+    }
+    S[2 * N] = S[2 * N + 1] = 0;
+    add_cc(S[1], Yw[1]);
+#pragma unroll
+    for (int i = 2; i < 2 * N + 1; i++) addc_cc(S[i], Yw[i]);
+    addc(S[2 * N + 1], 0);
+    add_cc(S[N], s.Z[0]);
+#pragma unroll
+    for (int i = 1; i < N + 1; i++) addc_cc(S[N + i], s.Z[i]);
+    addc(S[2 * N + 1], s.Z[N + 1]);
 }
 
 // ---- Karatsuba dot products (N = 2H words) ------------------------------------------------------
 // The N^2 IMAD.WIDE of a term are what bounds the Brakedown levels over the 255-bit field (FMA pipe; the ALU pipe is half
 // idle, profiles/r02_spmv.md), so one Karatsuba level trades a quarter of them for ALU-pipe work: with a = aL + aH*W,
 // b = bL + bH*W (W = 2^(32H)),  aL*bH + aH*bL = (aL + aH)(bL + bH) - aL*bL - aH*bH.  The three half-size products of
-// every term go to three split accumulators (as split_mac) and the subtraction is paid ONCE per dot product.  aL + aH and
+// every term go to three split accumulators and the subtraction is paid ONCE per dot product.  aL + aH and
 // bL + bH can be one bit longer than H words; with sa = sa' + ca*W, sb = sb' + cb*W
 //     sa*sb = sa'*sb' + W*(ca*sb' + cb*sa') + W^2*ca*cb,
 // and the three correction sums are plain (predicated) additions into Ca, Cb and a counter.
 template <int H>
 struct KaraAcc {
-    uint32_t X0[2 * H + 2], Y0[2 * H + 2], Z0[H + 2];  // sum aL*bL
-    uint32_t X2[2 * H + 2], Y2[2 * H + 2], Z2[H + 2];  // sum aH*bH
-    uint32_t Xm[2 * H + 2], Ym[2 * H + 2], Zm[H + 2];  // sum sa'*sb'
-    uint32_t Ca[H + 1], Cb[H + 1];                     // sum of sb' over the terms with ca, of sa' over those with cb
-    uint32_t Cc;                                       // number of terms with ca and cb
+    SplitAcc<H> p0, p2, pm;         // sum aL*bL, sum aH*bH, sum sa'*sb'
+    uint32_t Ca[H + 1], Cb[H + 1];  // sum of sb' over the terms with ca, of sa' over those with cb
+    uint32_t Cc;                    // number of terms with ca and cb
 };
 
 template <int H>
 __device__ __forceinline__ void kara_init(KaraAcc<H> &k) {
-#pragma unroll
-    for (int i = 0; i < 2 * H + 2; i++) k.X0[i] = k.Y0[i] = k.X2[i] = k.Y2[i] = k.Xm[i] = k.Ym[i] = 0;
-#pragma unroll
-    for (int i = 0; i < H + 2; i++) k.Z0[i] = k.Z2[i] = k.Zm[i] = 0;
+    split_init<H>(k.p0);
+    split_init<H>(k.p2);
+    split_init<H>(k.pm);
 #pragma unroll
     for (int i = 0; i < H + 1; i++) k.Ca[i] = k.Cb[i] = 0;
     k.Cc = 0;
@@ -294,11 +371,11 @@ __device__ __forceinline__ void kara_init(KaraAcc<H> &k) {
 template <int H>
 __device__ __forceinline__ void cond_add(uint32_t (&C)[H + 1], const uint32_t (&v)[H], uint32_t flag) {
     if constexpr (H == 4) {
-        asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0;\n\t"
-                     "@q add.cc.u32 %0, %0, %6;\n\t@q addc.cc.u32 %1, %1, %7;\n\t@q addc.cc.u32 %2, %2, %8;\n\t"
-                     "@q addc.cc.u32 %3, %3, %9;\n\t@q addc.u32 %4, %4, 0; }"
-                     : "+r"(C[0]), "+r"(C[1]), "+r"(C[2]), "+r"(C[3]), "+r"(C[4])
-                     : "r"(flag), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]));
+        asm("{ .reg .pred q; setp.ne.u32 q, %5, 0;\n\t"
+            "@q add.cc.u32 %0, %0, %6;\n\t@q addc.cc.u32 %1, %1, %7;\n\t@q addc.cc.u32 %2, %2, %8;\n\t"
+            "@q addc.cc.u32 %3, %3, %9;\n\t@q addc.u32 %4, %4, 0; }"
+            : "+r"(C[0]), "+r"(C[1]), "+r"(C[2]), "+r"(C[3]), "+r"(C[4])
+            : "r"(flag), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]));
     } else {
         const uint32_t m = 0u - flag;
         add_cc(C[0], v[0] & m);
@@ -309,7 +386,7 @@ __device__ __forceinline__ void cond_add(uint32_t (&C)[H + 1], const uint32_t (&
 }
 
 // acc += a*b
-template <int N, class PW>
+template <int N>
 __device__ __forceinline__ void kara_mac(KaraAcc<N / 2> &k, const uint32_t (&a)[N], const uint32_t (&b)[N]) {
     constexpr int H = N / 2;
     static_assert(N % 2 == 0, "even word count");
@@ -325,9 +402,9 @@ __device__ __forceinline__ void kara_mac(KaraAcc<N / 2> &k, const uint32_t (&a)[
 #pragma unroll
     for (int i = 1; i < H; i++) addc_cc(sb[i], bH[i]);
     addc(cb, 0);
-    MontRows<H, 0, PW>::product_sink(k.X0, k.Y0, k.Z0, aL, bL);
-    MontRows<H, 0, PW>::product_sink(k.X2, k.Y2, k.Z2, aH, bH);
-    MontRows<H, 0, PW>::product_sink(k.Xm, k.Ym, k.Zm, sa, sb);
+    split_mac<H>(k.p0, aL, bL);
+    split_mac<H>(k.p2, aH, bH);
+    split_mac<H>(k.pm, sa, sb);
     cond_add<H>(k.Ca, sb, ca);
     cond_add<H>(k.Cb, sa, cb);
     k.Cc += ca & cb;
@@ -338,9 +415,9 @@ template <int N>
 __device__ __forceinline__ void kara_sum(uint32_t (&S)[2 * N + 2], const KaraAcc<N / 2> &k) {
     constexpr int H = N / 2, W2 = 2 * H + 2;
     uint32_t S0[W2], S2[W2], Sm[W2];
-    split_sum<H>(S0, k.X0, k.Y0, k.Z0);
-    split_sum<H>(S2, k.X2, k.Y2, k.Z2);
-    split_sum<H>(Sm, k.Xm, k.Ym, k.Zm);
+    split_sum<H>(S0, k.p0);
+    split_sum<H>(S2, k.p2);
+    split_sum<H>(Sm, k.pm);
     // Sm += (Ca + Cb) * W + Cc * W^2
     add_cc(Sm[H], k.Ca[0]);
 #pragma unroll

@@ -81,9 +81,13 @@ def test_sass_has_no_short_cs2r_consumer():
     import sass_hazard_scan as scan
 
     _lib.load()  # builds the library when it is stale
-    found = scan.scan(scan.DEFAULT_LIB)
+    found = scan.scan(scan.DEFAULT_LIB, with_pattern=True)
     assert len(found) > 100  # the parser still recognises the listing
-    bad = [f for f in found if f[0] < 8]
+    # the failing shape (a predicated writer of the zeroed pair before its first reader) keeps one cycle of margin over the
+    # closest distance observed to work; a plain CS2R -> reader pair is an ordinary fixed-latency dependency that ptxas
+    # times itself (it schedules the reader 7 cycles behind the CS2R when nothing else is there to issue) and must
+    # not come closer than that
+    bad = [f for f in found if f[0] < (8 if f[4] else 7)]
     assert not bad, bad
 
 
