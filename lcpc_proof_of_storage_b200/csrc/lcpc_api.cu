@@ -26,16 +26,15 @@ std::string &last_error() {
 }  // namespace abi
 }  // namespace lcpc
 
-// encode rows already resident: ligero reads d_coeffs (stride n_per_row), brakedown widens first
+// encode rows already resident: both codes read d_coeffs (stride n_per_row) and write every entry of d_comm
 int32_t lcpc::abi::encode_dev(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm) {
     lcpc_ctx *ctx = plan->ctx;
     if (plan->kind == 0) {
         CU(ntt_encode(plan->ntt, d_coeffs, plan->n_per_row, plan->n_per_row, d_comm, n_rows, ctx->lc()));
     } else {
-        CU(widen_rows(plan->fid, d_coeffs, plan->n_per_row, d_comm, plan->n_cols, n_rows, ctx->lc()));
         DevBuf tmp;
         CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * limbs_of(plan->fid) * sizeof(uint64_t), ctx->stream));
-        CU(sdig_encode(plan->sdig, d_comm, n_rows, tmp.as<uint64_t>(), ctx->lc()));
+        CU(sdig_encode(plan->sdig, d_coeffs, plan->n_per_row, d_comm, n_rows, tmp.as<uint64_t>(), ctx->lc()));
     }
     return LCPC_OK;
 }
@@ -654,7 +653,7 @@ int32_t lcpc_encode_rows(lcpc_plan *plan, uint64_t *rows, size_t n_rows) {
     } else {
         DevBuf tmp;
         CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * L * sizeof(uint64_t), ctx->stream));
-        CU(sdig_encode(plan->sdig, buf.as<uint64_t>(), n_rows, tmp.as<uint64_t>(), ctx->lc()));
+        CU(sdig_encode(plan->sdig, buf.as<uint64_t>(), plan->n_cols, buf.as<uint64_t>(), n_rows, tmp.as<uint64_t>(), ctx->lc()));
     }
     CU(cudaMemcpyAsync(rows, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

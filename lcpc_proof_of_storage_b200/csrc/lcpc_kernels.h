@@ -168,11 +168,12 @@ struct SdigPlan {
     size_t n_per_row = 0, n_cols = 0;
     std::vector<DevCsr> pre, post;
 };
-// rows of d_comm (stride n_cols) already hold the message in their first n_per_row entries.
-cudaError_t sdig_encode(const SdigPlan &plan, uint64_t *d_comm, size_t n_rows, uint64_t *d_tmp, const Launch &lc);
+// Message rows at d_msg (stride msg_ld) -> codeword rows at d_comm (stride n_cols), every entry written.  In place
+// (d_msg == d_comm, msg_ld == n_cols: the rows already hold the message in their first n_per_row entries) or from the
+// coefficient matrix (msg_ld = n_per_row), in which case the pass that builds the transposed working copy also copies
+// the message into d_comm.
+cudaError_t sdig_encode(const SdigPlan &plan, const uint64_t *d_msg, size_t msg_ld, uint64_t *d_comm, size_t n_rows,
+                        uint64_t *d_tmp, const Launch &lc);
 size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows);
-// copy coeff rows (stride n_per_row) into the head of comm rows (stride n_cols), zero the rest
-cudaError_t widen_rows(int fid, const uint64_t *d_coeffs, size_t n_per_row, uint64_t *d_comm, size_t n_cols,
-                       size_t n_rows, const Launch &lc);
 
 }  // namespace lcpc

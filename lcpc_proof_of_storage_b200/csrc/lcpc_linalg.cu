@@ -558,7 +558,7 @@ __global__ void k_reed_solomon_t(const uint64_t *__restrict__ xiT, size_t n_in, 
 template <int L>
 __global__ void __launch_bounds__(256)
 k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src_ld, uint64_t *__restrict__ dst,
-            size_t dst_ld, int zero_pad) {
+            size_t dst_ld, int zero_pad, uint64_t *__restrict__ copy, size_t copy_ld) {
     __shared__ uint64_t tile[L][32][33];
     const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -567,7 +567,10 @@ k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src
         Fe<L> v;
 #pragma unroll
         for (int l = 0; l < L; l++) v.v[l] = 0;
-        if (r < n_r && c < n_c) v = ld_fe<L>(src + (r * src_ld + c) * L);
+        if (r < n_r && c < n_c) {
+            v = ld_fe<L>(src + (r * src_ld + c) * L);
+            if (copy) st_fe<L>(copy + (r * copy_ld + c) * L, v);  // the same element, row-major, into a wider matrix
+        }
 #pragma unroll
         for (int l = 0; l < L; l++) tile[l][rr][tx] = v.v[l];
     }
@@ -585,42 +588,13 @@ k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src
 
 template <int L>
 static void transpose_launch(const uint64_t *src, size_t n_r, size_t n_c, size_t src_ld, uint64_t *dst, size_t dst_ld,
-                             int zero_pad, const Launch &lc) {
+                             int zero_pad, const Launch &lc, uint64_t *copy = nullptr, size_t copy_ld = 0) {
     if (n_r == 0 || n_c == 0) return;
     const size_t rows_cov = zero_pad ? dst_ld : n_r;
     dim3 grid((unsigned)((n_c + 31) / 32), (unsigned)((rows_cov + 31) / 32));
     lc.begin("k_transpose");
-    k_transpose<L><<<grid, 256, 0, lc.s>>>(src, n_r, n_c, src_ld, dst, dst_ld, zero_pad);
+    k_transpose<L><<<grid, 256, 0, lc.s>>>(src, n_r, n_c, src_ld, dst, dst_ld, zero_pad, copy, copy_ld);
     lc.end();
-}
-
-template <int L>
-__global__ void k_widen_rows(const uint64_t *__restrict__ coeffs, size_t n_per_row, uint64_t *__restrict__ comm,
-                             size_t n_cols, size_t n_rows) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cols) return;
-    for (size_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
-        Fe<L> v;
-#pragma unroll
-        for (int l = 0; l < L; l++) v.v[l] = 0;
-        if (j < n_per_row) v = ld_fe<L>(coeffs + (r * n_per_row + j) * L);
-        st_fe<L>(comm + (r * n_cols + j) * L, v);
-    }
-}
-
-cudaError_t widen_rows(int fid, const uint64_t *d_coeffs, size_t n_per_row, uint64_t *d_comm, size_t n_cols,
-                       size_t n_rows, const Launch &lc) {
-    if (n_rows == 0 || n_cols == 0) return cudaSuccess;
-    dim3 grid((unsigned)((n_cols + 255) / 256), (unsigned)(n_rows < 65535 ? n_rows : 65535));
-    lc.begin("k_widen_rows");
-    switch (field_consts(fid).limbs) {
-    case 1: k_widen_rows<1><<<grid, 256, 0, lc.s>>>(d_coeffs, n_per_row, d_comm, n_cols, n_rows); break;
-    case 2: k_widen_rows<2><<<grid, 256, 0, lc.s>>>(d_coeffs, n_per_row, d_comm, n_cols, n_rows); break;
-    case 3: k_widen_rows<3><<<grid, 256, 0, lc.s>>>(d_coeffs, n_per_row, d_comm, n_cols, n_rows); break;
-    default: k_widen_rows<4><<<grid, 256, 0, lc.s>>>(d_coeffs, n_per_row, d_comm, n_cols, n_rows); break;
-    }
-    lc.end();
-    return cudaGetLastError();
 }
 
 // lane-group size (log2) that wastes the fewest padded lanes for this many matrix rows
@@ -645,8 +619,8 @@ size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows) {
 }
 
 template <int FID>
-static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t n_rows, uint64_t *d_tmp,
-                                 const Launch &lc) {
+static cudaError_t sdig_encode_t(const SdigPlan &plan, const uint64_t *d_msg, size_t msg_ld, uint64_t *d_comm, size_t n_rows,
+                                 uint64_t *d_tmp, const Launch &lc) {
     constexpr int L = Field<FID>::LIMBS;
     const size_t nl = plan.pre.size();
     if (nl == 0 || n_rows == 0) return cudaSuccess;
@@ -655,8 +629,11 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t 
     const size_t bp = sdig_bp(n_rows), gs = (size_t)1 << log_gs;
     uint64_t *xT = d_tmp;                        // [n_cols][bp]
     uint64_t *tT = d_tmp + n_cols * bp * L;      // [rows of the last precode][bp]
-    // message columns -> transposed copy (padded lanes zero, so every derived lane stays zero)
-    transpose_launch<L>(d_comm, n_rows, npr, n_cols, xT, bp, 1, lc);
+    // message columns -> transposed copy (padded lanes zero, so every derived lane stays zero); when the message is not
+    // in place yet (commit: the coefficient matrix), the same pass writes it into the first n_per_row columns of comm --
+    // the computed columns are all written by the last transpose, so comm needs no zero fill and no separate widening pass
+    if (d_msg == d_comm) transpose_launch<L>(d_comm, n_rows, npr, n_cols, xT, bp, 1, lc);
+    else transpose_launch<L>(d_msg, n_rows, npr, msg_ld, xT, bp, 1, lc, d_comm, n_cols);
     auto spmv = [&](const DevCsr &m, size_t x_off, uint64_t *y) {
         if (m.rows == 0) return;
         const size_t slices = (size_t)32 >> log_gs, groups = bp / gs;
@@ -726,8 +703,9 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, uint64_t *d_comm, size_t 
     return cudaGetLastError();
 }
 
-cudaError_t sdig_encode(const SdigPlan &plan, uint64_t *d_comm, size_t n_rows, uint64_t *d_tmp, const Launch &lc) {
-#define CALL(F) sdig_encode_t<F>(plan, d_comm, n_rows, d_tmp, lc)
+cudaError_t sdig_encode(const SdigPlan &plan, const uint64_t *d_msg, size_t msg_ld, uint64_t *d_comm, size_t n_rows,
+                        uint64_t *d_tmp, const Launch &lc) {
+#define CALL(F) sdig_encode_t<F>(plan, d_msg, msg_ld, d_comm, n_rows, d_tmp, lc)
     LCPC_FIELD_SWITCH(plan.fid, CALL)
 #undef CALL
 }
