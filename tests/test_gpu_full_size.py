@@ -171,3 +171,38 @@ def test_ligero_ft255_2_24_invariants(P, oracle):
     root = _check_invariants(P, O, enc, c, coeffs)
     streamed = _stream_root(P, enc, coeffs, c.n_rows, 50)
     assert streamed[-1].tobytes() == root
+
+
+@pytest.mark.parametrize("fid,n_rows", [(0, 5), (0, 17), (0, 40), (0, 48), (0, 64), (0, 130), (1, 17), (2, 48), (3, 9), (3, 40), (4, 17)])
+def test_brakedown_wide_levels_every_lane_group_shape(P, oracle, fid, n_rows):
+    """The wide expander levels at a size where they take the many-warp kernels (k_spmv_tg for the one-limb field with
+    NG = 2 ... 7 lane groups per thread and lane groups of 8 / 16 / 32 matrix rows; the pipelined k_spmv_t with split /
+    Karatsuba accumulators for the others), for matrix heights that give every lane-group size and ragged last groups:
+    EVERY encoded row against the oracle's encode (encode.rs:36-94), through both entry points -- the commit (message
+    taken from the coefficient matrix, copied into comm by the transposing pass) and lcpc_encode_rows (in place)."""
+    O = oracle
+    L = P.FIELD_LIMBS[fid]
+    n_per_row = 60000 + fid  # level 0: 60000 -> ~10700 outputs: thousands of warps
+    enc = P.SdigEncoding.new_from_dims(fid, n_per_row, None, seed=3)
+    oenc = O.SdigEncoding(fid, n_per_row, 3)
+    assert oenc.n_cols == enc.n_cols
+    if fid == 4:
+        coeffs = _fast_rand(3, n_rows * n_per_row - 11, 31 + n_rows, L)
+        coeffs[:, L - 1] &= np.uint64((1 << 56) - 1)  # below the 253-bit modulus
+    else:
+        coeffs = _fast_rand(fid, n_rows * n_per_row - 11, 31 + n_rows, L)
+    c = P.LcCommit.commit(coeffs, enc, download=True)
+    assert c.n_rows == n_rows
+    flat = np.zeros((n_rows * n_per_row, L), dtype=np.uint64)
+    flat[:coeffs.shape[0]] = coeffs
+    msg = np.zeros((n_rows, enc.n_cols, L), dtype=np.uint64)
+    msg[:, :n_per_row] = flat.reshape(n_rows, n_per_row, L)
+    exp = oenc.encode_rows(msg.copy())
+    assert np.array_equal(c.comm.reshape(n_rows, enc.n_cols, L), exp), "commit: encoded matrix differs from the oracle's"
+    rows = msg.copy()
+    enc.encode(rows)
+    assert np.array_equal(rows, exp), "encode_rows: differs from the oracle's"
+    cols = [0, n_per_row - 1, n_per_row, enc.n_cols - 1]
+    leaves = c.leaves(cols)
+    for k, j in enumerate(cols):
+        assert O.hash_column(fid, np.ascontiguousarray(exp[:, j])) == leaves[k].tobytes()
