@@ -373,6 +373,9 @@ cudaError_t pack_bytes31(const uint8_t *d_bytes, size_t n_bytes, uint64_t *d_ele
 #ifndef LCPC_SPMV_TG_MAX
 #define LCPC_SPMV_TG_MAX 8  // most lane groups of matrix rows one thread of k_spmv_tg serves (2 ... 8)
 #endif
+#ifndef LCPC_SPMV_TG_DEPTH
+#define LCPC_SPMV_TG_DEPTH 3  // operand slots of k_spmv_tg (2 / 3 / 4: 0.448 / 0.423 / 0.452 ms at Ft63 2^24)
+#endif
 #ifndef LCPC_SPMV_DEPTH
 #define LCPC_SPMV_DEPTH 0  // 0: three slots for the one-limb field, two otherwise (measured: profiles/r02_spmv.md)
 #endif
@@ -406,7 +409,7 @@ k_spmv_t(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colid
         // A non-zero costs two dependent trips to L2 (column index, then the gathered operand).  Software pipeline with a
         // ring of D slots: while a term is multiplied, the operands of the next D - 1 terms and the column indices of the D
         // terms after those are in flight (without it the kernel waits on the gathers with the integer pipes half idle:
-        // long-scoreboard was the top stall, profiles/r02_spmv.md).  Slots beyond the end of the row hold zeros.
+        // long-scoreboard was the top stall, profiles/r02_spmv.md).
         constexpr int D = LCPC_SPMV_DEPTH ? LCPC_SPMV_DEPTH : (L == 1 ? 3 : 2);
         E a[D], x[D];
         uint32_t cin[D];
@@ -475,37 +478,38 @@ k_spmv_tg(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ coli
 #pragma unroll
     for (int j = 0; j < NG; j++) F::dotw_init(acc[j]);
     if (k0 < k1) {
-        // two slots: the gathers of the next term are in flight while this one is multiplied; indices one term further.
-        // Loads past the end of the row are clamped to its last non-zero.
+        // DG slots: the gathers of the next DG - 1 terms are in flight while this one is multiplied; indices DG terms
+        // further.  Loads past the end of the row are clamped to its last non-zero.
+        constexpr int DG = LCPC_SPMV_TG_DEPTH;
         const uint32_t klast = k1 - 1;
         const uint64_t *xb = xT + b0;
-        E a[2], x[2][NG];
-        uint32_t cin[2];
+        E a[DG], x[DG][NG];
+        uint32_t cin[DG];
 #pragma unroll
-        for (int d = 0; d < 2; d++) cin[d] = colidx[min(k0 + d, klast)];
+        for (int d = 0; d < DG; d++) cin[d] = colidx[min(k0 + d, klast)];
 #pragma unroll
-        for (int d = 0; d < 2; d++) {
+        for (int d = 0; d < DG; d++) {
             a[d] = ld_fe<1>(data + min(k0 + d, klast));
             const uint64_t *xp = xb + (size_t)cin[d] * bp;
 #pragma unroll
             for (int j = 0; j < NG; j++) x[d][j] = ld_fe<1>(xp + j * GS);
-            cin[d] = colidx[min(k0 + 2 + d, klast)];
+            cin[d] = colidx[min(k0 + DG + d, klast)];
         }
         uint32_t k = k0;
         do {
 #pragma unroll
-            for (int d = 0; d < 2; d++) {
+            for (int d = 0; d < DG; d++) {
                 if (d == 0 || k + d < k1) {
 #pragma unroll
                     for (int j = 0; j < NG; j++) F::dotw_mac(acc[j], a[d], x[d][j]);
                 }
-                a[d] = ld_fe<1>(data + min(k + 2 + d, klast));
+                a[d] = ld_fe<1>(data + min(k + DG + d, klast));
                 const uint64_t *xp = xb + (size_t)cin[d] * bp;
 #pragma unroll
                 for (int j = 0; j < NG; j++) x[d][j] = ld_fe<1>(xp + j * GS);
-                cin[d] = colidx[min(k + 4 + d, klast)];
+                cin[d] = colidx[min(k + 2 * DG + d, klast)];
             }
-            k += 2;
+            k += DG;
         } while (k < k1);
     }
 #pragma unroll
