@@ -344,58 +344,54 @@ struct Field {
     }
 
     // ---- lazy dot products: acc = sum_k a_k * b_k with ONE reduction (see lcpc_mont32.cuh) -----------------
-    // Multi-limb fields accumulate unreduced double-width products; the one-limb field keeps its eager
-    // multiply-add (its reduction is two IMAD.WIDE, there is nothing to amortise).
-    struct Dot {
-        uint32_t s[LIMBS == 1 ? 2 : 4 * LIMBS + 2];
+    // Every field accumulates unreduced double-width products and pays the Montgomery reduction once per output.
+    // Multi-limb fields: one 2N+2-word sum per accumulator, every product built from zero and added (18 registers for
+    // four limbs: the fold keeps up to four of them per thread).  One-limb field: the split running accumulator of the
+    // Brakedown levels (m32::SplitAcc<2>: 4 IMAD.WIDE + 2 carry catches per term against ~22 instructions for the eager
+    // Montgomery multiply-add: the four-tensor fold is a stream over the matrix again, not an integer-pipe kernel).
+    struct DotSum {
+        uint32_t s[4 * LIMBS + 2];
     };
+    struct DotSplit1 {
+        m32::SplitAcc<2 * LIMBS> s;
+    };
+    using Dot = typename std::conditional<LIMBS == 1, DotSplit1, DotSum>::type;
     __device__ __forceinline__ static void dot_init(Dot &d) {
+        if constexpr (LIMBS == 1) {
+            m32::split_init<2>(d.s);
+        } else {
 #pragma unroll
-        for (int i = 0; i < (LIMBS == 1 ? 2 : 4 * LIMBS + 2); i++) d.s[i] = 0;
+            for (int i = 0; i < 4 * LIMBS + 2; i++) d.s[i] = 0;
+        }
     }
     __device__ __forceinline__ static void dot_mac(Dot &d, const E &a, const E &b) {
-        if constexpr (LIMBS == 1) {
-            const uint64_t acc = ft63::pack(d.s[0], d.s[1]);
-            const uint64_t r = ft63::add(acc, ft63::mul(a.v[0], b.v[0]));
-            d.s[0] = ft63::lo32(r);
-            d.s[1] = ft63::hi32(r);
-        } else {
-            uint32_t x[2 * LIMBS], y[2 * LIMBS];
-            split(x, a);
-            split(y, b);
-            m32::wide_mac<2 * LIMBS, PWord>(d.s, x, y);
-        }
+        uint32_t x[2 * LIMBS], y[2 * LIMBS];
+        split(x, a);
+        split(y, b);
+        if constexpr (LIMBS == 1) m32::split_mac<2>(d.s, x, y);
+        else m32::wide_mac<2 * LIMBS, PWord>(d.s, x, y);
     }
-    // sum * 2^-32 for multi-limb fields (callers that pre-scaled one operand class by 2^32, DOT_PRESCALE), the sum itself
-    // for the one-limb field
+    // sum * 2^-32 (for callers that pre-scaled one operand class by 2^32)
     __device__ __forceinline__ static E dot_finish_prescaled(const Dot &d) {
-        E r;
+        uint32_t z[2 * LIMBS];
         if constexpr (LIMBS == 1) {
-            r.v[0] = ft63::pack(d.s[0], d.s[1]);
+            uint32_t s[4 * LIMBS + 2];
+            m32::split_sum<2>(s, d.s);
+            m32::wide_redc<2 * LIMBS>(z, s, PWord{});
         } else {
-            uint32_t z[2 * LIMBS];
             m32::wide_redc<2 * LIMBS>(z, d.s, PWord{});
-            r = join(z);
         }
-        return r;
+        return join(z);
     }
-    static constexpr bool DOT_PRESCALE = LIMBS > 1;
-    // 2^32 in Montgomery form (one() for the one-limb field, whose dot products need no correction)
+    // 2^32 in Montgomery form
     __device__ __forceinline__ static E dot_scale() {
         E r;
-        if constexpr (LIMBS == 1) {
-            r = one();
-        } else {
 #pragma unroll
-            for (int i = 0; i < LIMBS; i++) r.v[i] = field_two32_mont(FID).v[i];
-        }
+        for (int i = 0; i < LIMBS; i++) r.v[i] = field_two32_mont(FID).v[i];
         return r;
     }
     // the sum, fully reduced, no pre-scaling needed: one extra product per dot product
-    __device__ __forceinline__ static E dot_finish(const Dot &d) {
-        if constexpr (LIMBS == 1) return dot_finish_prescaled(d);
-        else return mul(dot_finish_prescaled(d), dot_scale());
-    }
+    __device__ __forceinline__ static E dot_finish(const Dot &d) { return mul(dot_finish_prescaled(d), dot_scale()); }
 
     // The same dot product on running accumulators that cost fewer instructions per term and more registers -- for
     // the Brakedown levels, whose constant operand class (the matrix) is pre-scaled by 2^32 at plan time for EVERY field
