@@ -53,6 +53,8 @@ UNIT = "field elements/s"
 CONFIG_CASES = {
     "ligero_ft63_2^28": {"seed": 28, "n_per_row": 131072, "n_cols": 262144},
     "brakedown_ft255_2^24": {"seed": 3, "code_seed": 0, "n_per_row": 166292, "n_cols": 252931},
+    "brakedown_ft63_2^24": {"seed": 4, "code_seed": 0, "n_per_row": 166293, "n_cols": 252932},   # configs[4]'s Brakedown point
+    "ligero_ft63_2^20": {"seed": 20, "n_per_row": 8192, "n_cols": 16384},                       # configs[4]'s small end
     "fold_ft63_2^24": {"tensor_seed": 41, "n_tensors": 4},   # n_degree_tests + 1 = 4 at these widths
     "fold_ft63_2^28": {"tensor_seed": 42, "n_tensors": 4},
 }
@@ -382,6 +384,50 @@ def run_configs(torch, P, lib, _lib, ctx, stream, peak_gbs: float, d_coeffs_24) 
     ok = (root == want.get("brakedown_ft255_2^24", {}).get("root")) if "brakedown_ft255_2^24" in want else None
     out["brakedown_ft255_2^24"] = entry(ms, n, n * 32 + n_rows * nc * 32 + (2 * np2 - 1) * 32, ok, root=root,
                                         workload=f"Brakedown (code 3) commit, Ft255, BLAKE3, {n_rows} rows x {npr} -> {nc} cols")
+    del d_c, d_m, d_h, enc
+    torch.cuda.empty_cache()
+
+    # ---- Brakedown code 3 over Ft63, 2^24 coefficients: 101 x 166293 -> 252932 (configs[4])
+    k = CONFIG_CASES["brakedown_ft63_2^24"]
+    enc = P.SdigEncoding.new(FID, n, seed=k["code_seed"], ctx=ctx)
+    assert (enc.n_per_row, enc.n_cols) == (k["n_per_row"], k["n_cols"])
+    npr, nc = enc.n_per_row, enc.n_cols
+    n_rows = (n + npr - 1) // npr
+    np2 = P.next_pow2(nc)
+    d_c = torch.zeros(n_rows * npr, dtype=torch.int64, device=dev)
+    d_c[:n] = S.ft63_torch(k["seed"], n, dev)
+    d_m = torch.empty(n_rows * nc, dtype=torch.int64, device=dev)
+    d_h = torch.zeros((2 * np2 - 1) * 32, dtype=torch.uint8, device=dev)
+
+    def commit_bd63():
+        _lib.check(lib.lcpc_dev_encode(enc.plan, d_c.data_ptr(), n_rows, d_m.data_ptr()))
+        _lib.check(lib.lcpc_dev_merkleize(ctx.handle, FID, d_m.data_ptr(), n_rows, nc, nc, d_h.data_ptr()))
+
+    ms = _time_steps(torch, stream, commit_bd63, 10, 3)
+    root = bytes(d_h[-32:].cpu().numpy()).hex()
+    ok = (root == want.get("brakedown_ft63_2^24", {}).get("root")) if "brakedown_ft63_2^24" in want else None
+    out["brakedown_ft63_2^24"] = entry(ms, n, n * 8 + n_rows * nc * 8 + (2 * np2 - 1) * 32, ok, root=root,
+                                       workload=f"Brakedown (code 3) commit, Ft63, BLAKE3, {n_rows} rows x {npr} -> {nc} cols")
+    del d_c, d_m, d_h, enc
+
+    # ---- Ligero Ft63, 2^20 coefficients: 128 x 8192 -> 16384 (configs[4]'s small end: launches and dependent tails)
+    k = CONFIG_CASES["ligero_ft63_2^20"]
+    n, npr, nc = 1 << 20, k["n_per_row"], k["n_cols"]
+    n_rows = n // npr
+    enc = P.LigeroEncoding(FID, npr, nc, ctx=ctx)
+    d_c = S.ft63_torch(k["seed"], n, dev)
+    d_m = torch.empty(n_rows * nc, dtype=torch.int64, device=dev)
+    d_h = torch.zeros((2 * nc - 1) * 32, dtype=torch.uint8, device=dev)
+
+    def commit20():
+        _lib.check(lib.lcpc_dev_encode(enc.plan, d_c.data_ptr(), n_rows, d_m.data_ptr()))
+        _lib.check(lib.lcpc_dev_merkleize(ctx.handle, FID, d_m.data_ptr(), n_rows, nc, nc, d_h.data_ptr()))
+
+    ms = _time_steps(torch, stream, commit20, 50, 5)
+    root = bytes(d_h[-32:].cpu().numpy()).hex()
+    ok = (root == want.get("ligero_ft63_2^20", {}).get("root")) if "ligero_ft63_2^20" in want else None
+    out["ligero_ft63_2^20"] = entry(ms, n, n * 8 + n_rows * nc * 8 + (2 * nc - 1) * 32, ok, root=root,
+                                    workload=f"Ligero commit, Ft63, rho=1/2, BLAKE3, {n_rows} rows x {npr} -> {nc} cols")
     return out
 
 

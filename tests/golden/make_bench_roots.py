@@ -65,6 +65,25 @@ def config_answers() -> dict:
     comm = O.commit(S.ft255_np(k["seed"], 1 << 24), enc)
     out["brakedown_ft255_2^24"] = {"root": comm.get_root().hex()}
     print("brakedown ft255 2^24", out["brakedown_ft255_2^24"], flush=True)
+    out.update(config_answers_small())
+    return out
+
+
+def config_answers_small() -> dict:
+    """The two configs[4] points added late in round 2 (`--only-small` merges just these into the committed file)."""
+    from lcpc_proof_of_storage_b200 import synth as S
+
+    out = {}
+    c = bench.CONFIG_CASES
+    k = c["brakedown_ft63_2^24"]
+    enc = O.SdigEncoding.new(0, 1 << 24, k["code_seed"])
+    assert (enc.n_per_row, enc.n_cols) == (k["n_per_row"], k["n_cols"])
+    out["brakedown_ft63_2^24"] = {"root": O.commit(S.ft63_np(k["seed"], 1 << 24), enc).get_root().hex()}
+    print("brakedown ft63 2^24", out["brakedown_ft63_2^24"], flush=True)
+    k = c["ligero_ft63_2^20"]
+    enc = O.LigeroEncoding(0, k["n_per_row"], k["n_cols"])
+    out["ligero_ft63_2^20"] = {"root": O.commit(S.ft63_np(k["seed"], 1 << 20), enc).get_root().hex()}
+    print("ligero ft63 2^20", out["ligero_ft63_2^20"], flush=True)
     return out
 
 
@@ -100,6 +119,15 @@ def parity_answers() -> dict:
 def main() -> None:
     O.build()
     O.set_threads(os.cpu_count() or 1)
+    path = os.path.join(HERE, "bench_roots.json")
+    if "--only-small" in sys.argv:
+        with open(path) as f:
+            out = json.load(f)
+        out["configs"].update(config_answers_small())
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+            f.write("\n")
+        return
     enc = O.LigeroEncoding(bench.FID, bench.N_PER_ROW, bench.N_COLS)
     roots = {}
     for world in (1, 2, 4, 8):
