@@ -15,6 +15,9 @@
 
 #include "lcpc_mont32.cuh"
 
+#ifndef LCPC_FT63_DIGIT1_SUM3
+#define LCPC_FT63_DIGIT1_SUM3 1
+#endif
 #ifndef LCPC_KARATSUBA
 #define LCPC_KARATSUBA 1
 #endif
@@ -164,7 +167,24 @@ __device__ __forceinline__ uint64_t redc_digit(uint32_t w, uint64_t acc) {
 // Montgomery reduction of p00 + col1*2^32 + p11*2^64 (sums of 32x32 products, not carry-normalised;
 // col1 < 2.9 * 2^62).  The second digit's "+ P" is left out, so the digit chain ends on v - p in [-p, p)
 // and fix() finishes.  Result in [0, p).
+template <bool SUM3 = true>
 __device__ __forceinline__ uint64_t redc_cols(uint64_t p00, uint64_t col1, uint64_t p11) {
+#if LCPC_FT63_DIGIT1_SUM3
+  if constexpr (SUM3) {
+    // first digit = redc_digit(lo32(p00), col1 + P + hi32(p00)), spelled as ONE three-operand 64-bit sum
+    //     (col1 + w*Q) + {1, P_HI + 1} + {hi32(p00), ~w}        (~w + 1 = -w: the "- w * 2^32" of redc_digit)
+    // which ptxas emits as IADD3 + IADD3.X with two carries.  Written the other way it hangs hi32(p00) on the IMAD.WIDE
+    // chain as a zero-extended accumulator -- two register moves to build the {hi, 0} pair -- and subtracts w with a
+    // third instruction: 2 instructions fewer per product, both off the FMA pipe (profiles/r02_summary.md).
+    const uint32_t w = lo32(p00);
+    const uint64_t u = (col1 + wmul(w, LCPC_FT63_Q)) + (P + (1ull << 32)) + pack(hi32(p00), ~w);
+    // second digit = redc_digit(w2, p11 + hi32(u)) = p11 + hi32(u) + w2*Q - w2*2^32: the two words that join the products
+    // form ONE 64-bit addend {hi32(u), -w2}, built in place (no zero-extended pair, no separate "hi - w2")
+    const uint32_t w2 = lo32(u);
+    const uint64_t v = p11 + pack(hi32(u), 0u - w2) + wmul(w2, LCPC_FT63_Q);
+    return fix(v);
+  }
+#endif
     const uint64_t u = redc_digit(lo32(p00), col1 + P + hi32(p00));
     const uint64_t v = redc_digit(lo32(u), p11 + hi32(u));
     return fix(v);
@@ -176,7 +196,18 @@ __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
     return redc_cols(wmul(a0, b0), wmul(a0, b1) + wmul(a1, b0), wmul(a1, b1));
 }
 // a*2^-64 mod p
-__device__ __forceinline__ uint64_t to_canon(uint64_t a) { return redc_cols((uint64_t)lo32(a), (uint64_t)hi32(a), 0); }
+// a*2^-64 mod p: the same two digits with no partial products: both words that join a digit product go in as one
+// 64-bit addend ({hi32(a), ~w} and {hi32(u), -w2}), so neither needs a zero-extended register pair
+__device__ __forceinline__ uint64_t to_canon(uint64_t a) {
+#if LCPC_FT63_DIGIT1_SUM3
+    const uint32_t w = lo32(a);
+    const uint64_t u = wmul(w, LCPC_FT63_Q) + pack(hi32(a), ~w) + (P + (1ull << 32));
+    const uint32_t w2 = lo32(u);
+    return fix(pack(hi32(u), 0u - w2) + wmul(w2, LCPC_FT63_Q));
+#else
+    return redc_cols<false>((uint64_t)lo32(a), (uint64_t)hi32(a), 0);
+#endif
+}
 __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return fix(a + b + NEG_P); }
 __device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return fix(a - b); }
 }  // namespace ft63
