@@ -225,17 +225,18 @@ def kernel_algorithmic_bytes(name: str, n_rows: int) -> int:
 # pipe integer ops, A = ALU-pipe ops), derived in DESIGN.md from the arithmetic alone -- no addressing, no loop control.
 # unit = one field element through the kernel (NTT) or one BLAKE3 compression (hashing).
 INT_PIPE_MODEL = {
-    # 12 of the 16 butterfly levels: 5.06 Montgomery products (6 W + 3 I + 8 A each) and 12 modular add/sub (1 I + 4 A each)
-    "k_ntt_block": {"unit": "element", "W": 30.4, "I": 27.2, "A": 88.5},
-    "k_ntt_block_scatter": {"unit": "element", "W": 30.4, "I": 27.2, "A": 88.5},
+    # 12 of the 16 butterfly levels: 5.06 Montgomery products (6 W + 2 I + 5 A each since the digit steps are single
+    # three-operand sums; 6 W + 3 I + 8 A before) and 12 modular add/sub (1 I + 4 A each)
+    "k_ntt_block": {"unit": "element", "W": 30.4, "I": 22.1, "A": 73.3},
+    "k_ntt_block_scatter": {"unit": "element", "W": 30.4, "I": 22.1, "A": 73.3},
     # top 4 levels of a rate-1/2 row: 2.0 products per element, 3 add/sub levels
-    "k_ntt_strided": {"unit": "element", "W": 12.0, "I": 9.0, "A": 28.0},
+    "k_ntt_strided": {"unit": "element", "W": 12.0, "I": 7.0, "A": 22.0},
     # 56 G functions: 6 adds on the FMA pipe, 4 XOR + 2 PRMT + 2 funnel shifts on the ALU pipe each; 8 final XORs;
-    # 8 de-Montgomery reductions (2 W + 1 I + 6 A each)
-    "k_hash_chunks": {"unit": "compression", "W": 16, "I": 360, "A": 504},
-    "k_hash_chunks_scatter": {"unit": "compression", "W": 16, "I": 360, "A": 504},
+    # 8 de-Montgomery reductions (2 W + 2 I + 5 A each)
+    "k_hash_chunks": {"unit": "compression", "W": 16, "I": 352, "A": 496},
+    "k_hash_chunks_scatter": {"unit": "compression", "W": 16, "I": 352, "A": 496},
     # + per column 4 parent compressions (5 chunk values) and 1 Merkle node: 5 / 65 more compressions, no reductions
-    "k_hash_tree": {"unit": "compression", "W": 16, "I": 360 * 70 / 65, "A": 504 * 70 / 65},
+    "k_hash_tree": {"unit": "compression", "W": 16, "I": 352 * 70 / 65, "A": 496 * 70 / 65},
 }
 
 
