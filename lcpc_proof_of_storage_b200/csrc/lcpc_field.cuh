@@ -460,13 +460,8 @@ struct Field {
         m32::wide_redc<2 * LIMBS>(z, s, PWord{});
         return join(z);
     }
-    // 2^32 in Montgomery form, every field
-    __device__ __forceinline__ static E dotw_scale() {
-        E r;
-#pragma unroll
-        for (int i = 0; i < LIMBS; i++) r.v[i] = field_two32_mont(FID).v[i];
-        return r;
-    }
+    // 2^32 in Montgomery form (what the pre-scaled operand class is multiplied by at plan time)
+    __device__ __forceinline__ static E dotw_scale() { return dot_scale(); }
 
     __device__ static E pow(E base, uint64_t e) {
         E acc = one();

@@ -234,7 +234,8 @@ __device__ __forceinline__ void wide_mac(uint32_t (&S)[2 * N + 2], const uint32_
 // and then adds 2(2N+1) words into S, which is 40 % of its instructions at N = 8.  The sink words only count carries
 // (at most two per term and word), so any K < 2^31 is safe.
 // The accumulators are uint64_t (word pair 2i, 2i+1 of X; word pair 2i+1, 2i+2 of Y) and every carry chain is ONE asm
-// statement that unpacks its pairs, runs mad.lo.cc / madc.hi.cc over them and packs them again: ptxas then keeps each
+// statement (volatile like every other statement of this file that touches the carry flag: a chain that floated between
+// two statements of an add_cc / addc_cc sequence would clobber the flag they hand over) that unpacks its pairs, runs mad.lo.cc / madc.hi.cc over them and packs them again: ptxas then keeps each
 // pair in an aligned register pair for the whole loop.  With one 32-bit variable per word (row_mad above) it moved
 // 2.5 registers per product between the loop-carried words and the pairs IMAD.WIDE needs (IMAD.MOV: 13 % of the FMA-pipe
 // cycles of the four-limb Brakedown level, a third of all instructions of the one-limb one).
@@ -243,7 +244,7 @@ struct MadChain;
 template <>
 struct MadChain<1> {
     __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
-        asm("{ .reg .u32 l0, h0;\n\tmov.b64 {l0, h0}, %0;\n\t"
+        asm volatile("{ .reg .u32 l0, h0;\n\tmov.b64 {l0, h0}, %0;\n\t"
             "mad.lo.cc.u32 l0, %2, %3, l0;\n\tmadc.hi.cc.u32 h0, %2, %3, h0;\n\t"
             "addc.u32 %1, %1, 0;\n\tmov.b64 %0, {l0, h0}; }"
             : "+l"(P[0]), "+r"(sink) : "r"(x), "r"(y[0]));
@@ -252,7 +253,7 @@ struct MadChain<1> {
 template <>
 struct MadChain<2> {
     __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
-        asm("{ .reg .u32 l0, h0, l1, h1;\n\tmov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\t"
+        asm volatile("{ .reg .u32 l0, h0, l1, h1;\n\tmov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\t"
             "mad.lo.cc.u32 l0, %3, %4, l0;\n\tmadc.hi.cc.u32 h0, %3, %4, h0;\n\t"
             "madc.lo.cc.u32 l1, %3, %5, l1;\n\tmadc.hi.cc.u32 h1, %3, %5, h1;\n\t"
             "addc.u32 %2, %2, 0;\n\tmov.b64 %0, {l0, h0};\n\tmov.b64 %1, {l1, h1}; }"
@@ -262,7 +263,7 @@ struct MadChain<2> {
 template <>
 struct MadChain<3> {
     __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
-        asm("{ .reg .u32 l0, h0, l1, h1, l2, h2;\n\tmov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\tmov.b64 {l2, h2}, %2;\n\t"
+        asm volatile("{ .reg .u32 l0, h0, l1, h1, l2, h2;\n\tmov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\tmov.b64 {l2, h2}, %2;\n\t"
             "mad.lo.cc.u32 l0, %4, %5, l0;\n\tmadc.hi.cc.u32 h0, %4, %5, h0;\n\t"
             "madc.lo.cc.u32 l1, %4, %6, l1;\n\tmadc.hi.cc.u32 h1, %4, %6, h1;\n\t"
             "madc.lo.cc.u32 l2, %4, %7, l2;\n\tmadc.hi.cc.u32 h2, %4, %7, h2;\n\t"
@@ -273,7 +274,7 @@ struct MadChain<3> {
 template <>
 struct MadChain<4> {
     __device__ __forceinline__ static void run(uint64_t *P, uint32_t x, const uint32_t *y, uint32_t &sink) {
-        asm("{ .reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+        asm volatile("{ .reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
             "mov.b64 {l0, h0}, %0;\n\tmov.b64 {l1, h1}, %1;\n\tmov.b64 {l2, h2}, %2;\n\tmov.b64 {l3, h3}, %3;\n\t"
             "mad.lo.cc.u32 l0, %5, %6, l0;\n\tmadc.hi.cc.u32 h0, %5, %6, h0;\n\t"
             "madc.lo.cc.u32 l1, %5, %7, l1;\n\tmadc.hi.cc.u32 h1, %5, %7, h1;\n\t"
@@ -371,7 +372,7 @@ __device__ __forceinline__ void kara_init(KaraAcc<H> &k) {
 template <int H>
 __device__ __forceinline__ void cond_add(uint32_t (&C)[H + 1], const uint32_t (&v)[H], uint32_t flag) {
     if constexpr (H == 4) {
-        asm("{ .reg .pred q; setp.ne.u32 q, %5, 0;\n\t"
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0;\n\t"
             "@q add.cc.u32 %0, %0, %6;\n\t@q addc.cc.u32 %1, %1, %7;\n\t@q addc.cc.u32 %2, %2, %8;\n\t"
             "@q addc.cc.u32 %3, %3, %9;\n\t@q addc.u32 %4, %4, 0; }"
             : "+r"(C[0]), "+r"(C[1]), "+r"(C[2]), "+r"(C[3]), "+r"(C[4])
