@@ -584,8 +584,13 @@ def sharded_parity_checks(torch, dist, P, ctx, rank: int, world: int) -> dict:
     k = PARITY_CASES["brakedown"]
     enc_s = P.SdigEncoding.new_from_dims(FID, k["n_per_row"], k["n_cols"], seed=k["code_seed"], ctx=ctx)
     n_total = k["n_rows"] * k["n_per_row"] - 5
-    for mode in ("columns", "rows", "auto"):   # auto = row hashing with the chaining values stored into the owners' stores
-        sc = ShardedCommitter(enc_s, k["n_rows"], dist.group.WORLD, hashing=mode)
+    # columns = the transposing passes store into the owners' column blocks over NVLink; columns_nccl = the same blocks by
+    # pack + NCCL all-to-all; auto = row hashing with the chaining values stored into the owners' stores
+    for mode in ("columns", "columns_nccl", "rows", "auto"):
+        sc = ShardedCommitter(enc_s, k["n_rows"], dist.group.WORLD, hashing=mode.split("_")[0],
+                              fused=False if mode == "columns_nccl" else None)
+        if mode.startswith("columns"):
+            put(f"brakedown_{mode}_exchange_as_named", sc.fused == (mode == "columns"))
         e0, e1 = sc.row0 * k["n_per_row"], (sc.row0 + sc.rows_local) * k["n_per_row"]
         coeffs = torch.zeros(sc.rows_local * k["n_per_row"], dtype=torch.int64, device=dev)
         have = max(0, min(n_total, e1) - e0)

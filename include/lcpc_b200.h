@@ -306,13 +306,15 @@ double lcpc_sdig_dist(int32_t code);
 int32_t lcpc_dev_encode(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t *d_comm);
 /* lcpc_decode_rows on device memory, in place: n_rows rows of n_cols elements, row stride n_cols. */
 int32_t lcpc_dev_decode(lcpc_plan *plan, uint64_t *d_rows, size_t n_rows);
-/* Fused encode + re-shard for the one-process-per-GPU path (Ligero plans): like lcpc_dev_encode,
- * but the last pass of the transform stores every row block directly into the column-block matrix
- * of the rank that hashes those columns: peer_blocks[g] is rank g's [n_rows_total][n_cols/n_peers]
- * row-major matrix (this rank's own buffer or a peer-mapped pointer reached over NVLink), rows
- * row0 .. row0+n_rows of it are written.  d_scratch: n_rows*n_cols elements of local scratch for the
- * leading passes (may be NULL when the transform is a single pass).  The caller synchronises the
- * ranks before anyone reads its matrix. */
+/* Fused encode + re-shard for the one-process-per-GPU path: like lcpc_dev_encode, but the encoded rows are stored
+ * directly into the column-block matrix of the rank that hashes those columns: peer_blocks[g] is rank g's
+ * [n_rows_total][np2/n_peers] row-major matrix (np2 = n_cols rounded up to a power of two: the PADDED column range is
+ * what the ranks split; this rank's own buffer or a peer-mapped pointer reached over NVLink), rows row0 .. row0+n_rows
+ * of it are written.  Ligero plans: the last pass of the transform stores whole row blocks; d_scratch: n_rows*n_cols
+ * elements of local scratch for the leading passes (may be NULL when the transform is a single pass).  Brakedown plans:
+ * the two transposing passes that would write the encoded matrix (message columns, computed columns) store element by
+ * element into the owners' matrices; d_scratch is not used.  The caller synchronises the ranks before anyone reads its
+ * matrix. */
 int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_t n_rows, uint64_t row0,
                                 uint64_t *d_scratch, uint64_t *const *peer_blocks, size_t n_peers);
 /* hash_columns (lib.rs:736-775) on a column window: leaves[j] for j in [0, n_cols) of a

@@ -987,21 +987,31 @@ int32_t lcpc_dev_encode_scatter(lcpc_plan *plan, const uint64_t *d_coeffs, size_
                                 uint64_t *d_scratch, uint64_t *const *peer_blocks, size_t n_peers) {
     plan = primary(plan);  // a plan made on a multi-device context: this call runs on its first device
     if (!plan || !d_coeffs || !peer_blocks) return fail(LCPC_ERR_INVALID_ARG, "null argument");
-    if (plan->kind != 0) return fail(LCPC_ERR_INVALID_ARG, "the fused encode + re-shard is defined for Ligero plans");
-    if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || plan->n_cols % n_peers)
-        return fail(LCPC_ERR_DIMS, "n_peers must be a power of two <= 16 dividing n_cols");
+    // the PADDED column range (next power of two: Brakedown's n_cols is not one) is what the ranks split
+    size_t np2 = 1;
+    while (np2 < plan->n_cols) np2 <<= 1;
+    if (n_peers == 0 || n_peers > 16 || (n_peers & (n_peers - 1)) || np2 % n_peers)
+        return fail(LCPC_ERR_DIMS, "n_peers must be a power of two <= 16 dividing the padded column count");
     std::lock_guard<std::mutex> g(plan->mu);
     std::lock_guard<std::mutex> g2(plan->ctx->mu);
     lcpc_ctx *ctx = plan->ctx;
     CU(cudaSetDevice(ctx->device));
     ScatterDst sc{};
-    size_t cb = plan->n_cols / n_peers;
+    size_t cb = np2 / n_peers;
     sc.log_cb = 0;
     while (((size_t)1 << sc.log_cb) < cb) sc.log_cb++;
     sc.row0 = row0;
     for (size_t i = 0; i < n_peers; i++) {
         if (!peer_blocks[i]) return fail(LCPC_ERR_INVALID_ARG, "null peer pointer");
         sc.base[i] = peer_blocks[i];
+    }
+    if (plan->kind != 0) {
+        // Brakedown: the transposing passes that would write comm store into the owners' matrices instead
+        if (n_rows == 0) return LCPC_OK;
+        DevBuf tmp;
+        CU(tmp.alloc(sdig_tmp_elems(plan->sdig, n_rows) * limbs_of(plan->fid) * sizeof(uint64_t), ctx->stream));
+        CU(sdig_encode(plan->sdig, d_coeffs, plan->n_per_row, nullptr, n_rows, tmp.as<uint64_t>(), ctx->lc(), &sc));
+        return LCPC_OK;
     }
     if (plan->ntt.passes.size() > 1 && !d_scratch) return fail(LCPC_ERR_INVALID_ARG, "scratch needed for multi-pass transforms");
     cudaError_t e = ntt_encode(plan->ntt, d_coeffs, plan->n_per_row, plan->n_per_row, d_scratch, n_rows, ctx->lc(), &sc);

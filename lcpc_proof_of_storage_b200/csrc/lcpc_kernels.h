@@ -172,8 +172,10 @@ struct SdigPlan {
 // (d_msg == d_comm, msg_ld == n_cols: the rows already hold the message in their first n_per_row entries) or from the
 // coefficient matrix (msg_ld = n_per_row), in which case the pass that builds the transposed working copy also copies
 // the message into d_comm.
+// sc != nullptr (multi-GPU column blocks): d_comm is not used, both passes that would write it store every element into
+// the column-block matrix of the rank that owns its column (ScatterDst: the PADDED column range is what is split).
 cudaError_t sdig_encode(const SdigPlan &plan, const uint64_t *d_msg, size_t msg_ld, uint64_t *d_comm, size_t n_rows,
-                        uint64_t *d_tmp, const Launch &lc);
+                        uint64_t *d_tmp, const Launch &lc, const ScatterDst *sc = nullptr);
 size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows);
 
 }  // namespace lcpc

@@ -562,7 +562,14 @@ __global__ void k_reed_solomon_t(const uint64_t *__restrict__ xiT, size_t n_in, 
 template <int L>
 __global__ void __launch_bounds__(256)
 k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src_ld, uint64_t *__restrict__ dst,
-            size_t dst_ld, int zero_pad, uint64_t *__restrict__ copy, size_t copy_ld) {
+            size_t dst_ld, int zero_pad, uint64_t *__restrict__ copy, size_t copy_ld, const __grid_constant__ ScatterDst sc,
+            int sc_mode, size_t sc_col0) {
+    // sc_mode 1: the row-major copy, 2: the transposed output itself goes to the column-block matrices of the ranks that
+    // own those columns (their own HBM or a peer's over NVLink) instead of a local matrix: element (matrix row, column)
+    // lands at base[column >> log_cb][row0 + matrix row][column & (cb - 1)]
+    auto peer = [&](size_t row, size_t col) {
+        return sc.base[col >> sc.log_cb] + ((((size_t)sc.row0 + row) << sc.log_cb) + (col & (((size_t)1 << sc.log_cb) - 1))) * L;
+    };
     __shared__ uint64_t tile[L][32][33];
     const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -573,7 +580,8 @@ k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src
         for (int l = 0; l < L; l++) v.v[l] = 0;
         if (r < n_r && c < n_c) {
             v = ld_fe<L>(src + (r * src_ld + c) * L);
-            if (copy) st_fe<L>(copy + (r * copy_ld + c) * L, v);  // the same element, row-major, into a wider matrix
+            if (sc_mode == 1) st_fe<L>(peer(r, sc_col0 + c), v);
+            else if (copy) st_fe<L>(copy + (r * copy_ld + c) * L, v);  // the same element, row-major, into a wider matrix
         }
 #pragma unroll
         for (int l = 0; l < L; l++) tile[l][rr][tx] = v.v[l];
@@ -585,19 +593,22 @@ k_transpose(const uint64_t *__restrict__ src, size_t n_r, size_t n_c, size_t src
             Fe<L> v;
 #pragma unroll
             for (int l = 0; l < L; l++) v.v[l] = tile[l][tx][cc];
-            st_fe<L>(dst + (c * dst_ld + r) * L, v);
+            if (sc_mode == 2) st_fe<L>(peer(c, sc_col0 + r), v);
+            else st_fe<L>(dst + (c * dst_ld + r) * L, v);
         }
     }
 }
 
 template <int L>
 static void transpose_launch(const uint64_t *src, size_t n_r, size_t n_c, size_t src_ld, uint64_t *dst, size_t dst_ld,
-                             int zero_pad, const Launch &lc, uint64_t *copy = nullptr, size_t copy_ld = 0) {
+                             int zero_pad, const Launch &lc, uint64_t *copy = nullptr, size_t copy_ld = 0,
+                             const ScatterDst *sc = nullptr, int sc_mode = 0, size_t sc_col0 = 0) {
     if (n_r == 0 || n_c == 0) return;
     const size_t rows_cov = zero_pad ? dst_ld : n_r;
     dim3 grid((unsigned)((n_c + 31) / 32), (unsigned)((rows_cov + 31) / 32));
     lc.begin("k_transpose");
-    k_transpose<L><<<grid, 256, 0, lc.s>>>(src, n_r, n_c, src_ld, dst, dst_ld, zero_pad, copy, copy_ld);
+    k_transpose<L><<<grid, 256, 0, lc.s>>>(src, n_r, n_c, src_ld, dst, dst_ld, zero_pad, copy, copy_ld, sc ? *sc : ScatterDst{},
+                                           sc ? sc_mode : 0, sc_col0);
     lc.end();
 }
 
@@ -624,7 +635,7 @@ size_t sdig_tmp_elems(const SdigPlan &plan, size_t n_rows) {
 
 template <int FID>
 static cudaError_t sdig_encode_t(const SdigPlan &plan, const uint64_t *d_msg, size_t msg_ld, uint64_t *d_comm, size_t n_rows,
-                                 uint64_t *d_tmp, const Launch &lc) {
+                                 uint64_t *d_tmp, const Launch &lc, const ScatterDst *sc) {
     constexpr int L = Field<FID>::LIMBS;
     const size_t nl = plan.pre.size();
     if (nl == 0 || n_rows == 0) return cudaSuccess;
@@ -636,7 +647,8 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, const uint64_t *d_msg, si
     // message columns -> transposed copy (padded lanes zero, so every derived lane stays zero); when the message is not
     // in place yet (commit: the coefficient matrix), the same pass writes it into the first n_per_row columns of comm --
     // the computed columns are all written by the last transpose, so comm needs no zero fill and no separate widening pass
-    if (d_msg == d_comm) transpose_launch<L>(d_comm, n_rows, npr, n_cols, xT, bp, 1, lc);
+    if (sc) transpose_launch<L>(d_msg, n_rows, npr, msg_ld, xT, bp, 1, lc, nullptr, 0, sc, 1, 0);
+    else if (d_msg == d_comm) transpose_launch<L>(d_comm, n_rows, npr, n_cols, xT, bp, 1, lc);
     else transpose_launch<L>(d_msg, n_rows, npr, msg_ld, xT, bp, 1, lc, d_comm, n_cols);
     auto spmv = [&](const DevCsr &m, size_t x_off, uint64_t *y) {
         if (m.rows == 0) return;
@@ -703,13 +715,14 @@ static cudaError_t sdig_encode_t(const SdigPlan &plan, const uint64_t *d_msg, si
         out_start += plan.post[l].rows;
     }
     // computed part of the codeword back to the row-major matrix (the message columns are in place)
-    transpose_launch<L>(xT + npr * bp * L, n_cols - npr, n_rows, bp, d_comm + npr * L, n_cols, 0, lc);
+    if (sc) transpose_launch<L>(xT + npr * bp * L, n_cols - npr, n_rows, bp, nullptr, 0, 0, lc, nullptr, 0, sc, 2, npr);
+    else transpose_launch<L>(xT + npr * bp * L, n_cols - npr, n_rows, bp, d_comm + npr * L, n_cols, 0, lc);
     return cudaGetLastError();
 }
 
 cudaError_t sdig_encode(const SdigPlan &plan, const uint64_t *d_msg, size_t msg_ld, uint64_t *d_comm, size_t n_rows,
-                        uint64_t *d_tmp, const Launch &lc) {
-#define CALL(F) sdig_encode_t<F>(plan, d_msg, msg_ld, d_comm, n_rows, d_tmp, lc)
+                        uint64_t *d_tmp, const Launch &lc, const ScatterDst *sc) {
+#define CALL(F) sdig_encode_t<F>(plan, d_msg, msg_ld, d_comm, n_rows, d_tmp, lc, sc)
     LCPC_FIELD_SWITCH(plan.fid, CALL)
 #undef CALL
 }

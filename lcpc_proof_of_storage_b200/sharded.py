@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .lcpc2d import FIELD_LIMBS, LcColumn, LigeroEncoding, log2, next_pow2
+from .lcpc2d import FIELD_LIMBS, LcColumn, LigeroEncoding, SdigEncoding, log2, next_pow2
 
 
 def chunk_row_partition(limbs: int, n_rows: int, world: int):
@@ -257,10 +257,13 @@ class ShardedLigeroCommitter:
         want = fused if fused is not None else (isinstance(self.ops, GpuOps) and self.world > 1)
         # the transform's last pass stores whole shared-memory blocks (2^12 / 2^11 / 2^10 elements for 1 / 2 / 3-4 limbs): a
         # column block must hold at least one
+        # (Brakedown plans have no such constraint and no power-of-two n_cols: their transposing passes store element by
+        # element into the owners' blocks of the PADDED column range, lcpc_dev_encode_scatter)
+        sdig = isinstance(enc, SdigEncoding)
         ntt_block = 1 << min(log2(self.n_cols), {1: 12, 2: 11}.get(self.L, 10))
-        if fused is None and self.cb < ntt_block:
+        if fused is None and not sdig and self.cb < ntt_block:
             want = False
-        if want and isinstance(self.ops, GpuOps) and self.world > 1 and self.np2 == self.n_cols and self.world <= 16:
+        if want and isinstance(self.ops, GpuOps) and self.world > 1 and (sdig or self.np2 == self.n_cols) and self.world <= 16:
             try:
                 import ctypes as C
 
@@ -279,7 +282,8 @@ class ShardedLigeroCommitter:
                                    for b in range(3)]
                 self._bufs = [self._symm[b * per:(b + 1) * per] for b in range(3)]
                 self._k = 0
-                self._scratch = torch.empty(max(1, self.rows_local) * self.n_cols * self.L, dtype=torch.int64, device=dev)
+                self._scratch = torch.empty(1 if sdig else max(1, self.rows_local) * self.n_cols * self.L, dtype=torch.int64,
+                                            device=dev)
             except Exception:
                 if fused:
                     raise

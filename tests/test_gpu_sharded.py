@@ -112,7 +112,10 @@ def _worker_brakedown(rank, world, port, q):
         from oracle import lcpc_oracle as O
 
         ok = True
-        for fid, n_per_row, n_rows, seed in [(0, 300, 23, 0), (3, 150, 9, 1)]:
+        # both exchanges of the column-block mode: the transposing passes storing into the owners' blocks of the padded
+        # column range (fused: symmetric memory, NVLink), and the NCCL all-to-all over the padded leaf range
+        for fid, n_per_row, n_rows, seed, fused in [(0, 300, 23, 0, None), (3, 150, 9, 1, None), (0, 300, 23, 0, False),
+                                                    (1, 260, 17, 2, None)]:
             L = O.LIMBS[fid]
             oenc = O.SdigEncoding(fid, n_per_row, seed)
             n = n_rows * n_per_row - 7
@@ -120,8 +123,8 @@ def _worker_brakedown(rank, world, port, q):
             coeffs[:n] = O.random_field_elements(fid, 5, n)
             ctx = P.Context(rank, stream=torch.cuda.current_stream().cuda_stream)
             enc = P.SdigEncoding.new_from_dims(fid, n_per_row, oenc.n_cols, seed=seed, ctx=ctx)
-            sc = ShardedCommitter(enc, n_rows, None)
-            assert not sc.fused  # n_cols is not a power of two: NCCL all-to-all over the padded leaf range
+            sc = ShardedCommitter(enc, n_rows, None, fused=fused)
+            assert sc.fused == (fused is None)  # n_cols is not a power of two: the blocks are cut from the padded range
             r0, cnt = row_partition(n_rows, world)[rank]
             local = torch.from_numpy(coeffs.reshape(n_rows, n_per_row, L)[r0:r0 + cnt].copy().view(np.int64).reshape(-1)).cuda()
             sc.commit(local)
