@@ -19,6 +19,9 @@
 // Because an in-place DIF leaves element i holding X[bitrev(i)], no permutation pass
 // is needed for fffft's "io" order.
 #pragma once
+#ifndef LCPC_NTT_FULL_BLOCK_PATH
+#define LCPC_NTT_FULL_BLOCK_PATH 1
+#endif
 #include "lcpc_field.cuh"
 #include "lcpc_kernels.h"
 
@@ -256,7 +259,9 @@ __device__ __forceinline__ unsigned sm_phys(unsigned i) { return i + (i >> 4); }
 // twiddle address is then one base plus a literal offset, instead of five integer instructions per access (shift,
 // add, two LEAs for the 1-in-16 padding and the byte address) -- 14 % of the executed instructions, mostly on the
 // ALU pipe that bounds the kernel.
-template <int FID, int R, bool TW, bool GSRC, int LN2 = -1>
+// FULL (with GSRC): every element of the block exists (the block pass behind a strided pass: valid == block size), so the
+// loads are unconditional -- no index, compare and zero default per element.
+template <int FID, int R, bool TW, bool GSRC, int LN2 = -1, bool FULL = false>
 __device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int LB, int log_sub,
                                               const uint64_t *__restrict__ tw, const SmallTw<FID> &stw,
                                               const uint64_t *__restrict__ gsrc, unsigned valid) {
@@ -279,7 +284,9 @@ __device__ __forceinline__ void block_substep(uint64_t *sm, unsigned plane, int 
 #pragma unroll
         for (int m = 0; m < (1 << R); m++) {
             const unsigned i = base + ((unsigned)m << log_n2);
-            if constexpr (GSRC) {
+            if constexpr (GSRC && FULL) {
+                x[m] = ld_fe<L>(gsrc + (size_t)i * L);
+            } else if constexpr (GSRC) {
                 x[m] = i < valid ? ld_fe<L>(gsrc + (size_t)i * L) : F::zero();
             } else {
                 const unsigned p = phys(base, p0, m);
@@ -350,6 +357,10 @@ k_ntt_block(const uint64_t *src, size_t src_stride, size_t src_valid, uint64_t *
     for (size_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
         if constexpr (L == 1 && RMAX == 4) {
             if (LB == 12) {  // the full-size block: three radix-16 sub-steps with literal strides 256, 16, 1
+#if LCPC_NTT_FULL_BLOCK_PATH
+                if (valid == NB) block_substep<FID, 4, true, true, 8, true>(sm, plane, 12, 12, tw, stw, src + (row * src_stride + col0) * L, valid);
+                else
+#endif
                 block_substep<FID, 4, true, true, 8>(sm, plane, 12, 12, tw, stw, src + (row * src_stride + col0) * L, valid);
                 __syncthreads();
                 block_substep<FID, 4, true, false, 4>(sm, plane, 12, 8, tw + ((size_t)1 << 12) * L, stw, nullptr, 0u);
